@@ -1,0 +1,194 @@
+"""
+Spectral primitives.  The operator/mask builders are constructor-time host code (NumPy), as
+in the reference where they run once in `BaseStepper.__init__`; `fft` / `ifft` are device ops
+backed by libexb's shared-memory Stockham kernels.
+
+Mirrors exponax/_spectral.py (function names, arguments, shapes, error messages).
+"""
+from __future__ import annotations
+
+from typing import Literal
+
+import numpy as np
+
+from . import _array as A
+from . import _native as nat
+from ._config import complex_dtype, real_dtype
+
+
+def build_wavenumbers(num_spatial_dims: int, num_points: int, *, indexing: str = "ij", dtype=None):
+    """exponax/_spectral.py:13-49."""
+    dtype = real_dtype() if dtype is None else dtype
+    right = np.fft.rfftfreq(num_points, 1 / num_points).astype(dtype)
+    other = np.fft.fftfreq(num_points, 1 / num_points).astype(dtype)
+    grids = [other] * (num_spatial_dims - 1) + [right]
+    return np.stack(np.meshgrid(*grids, indexing=indexing))
+
+
+def build_scaled_wavenumbers(num_spatial_dims, domain_extent, num_points, *, indexing="ij", dtype=None):
+    """exponax/_spectral.py:52-83."""
+    dtype = real_dtype() if dtype is None else dtype
+    scale = dtype(2 * np.pi / domain_extent)
+    return scale * build_wavenumbers(num_spatial_dims, num_points, indexing=indexing, dtype=dtype)
+
+
+def build_derivative_operator(num_spatial_dims, domain_extent, num_points, *, indexing="ij", dtype=None):
+    """exponax/_spectral.py:86-115: 1j * (2*pi/L) * k."""
+    dtype = real_dtype() if dtype is None else dtype
+    wn = build_scaled_wavenumbers(num_spatial_dims, domain_extent, num_points, indexing=indexing, dtype=dtype)
+    return (1j * wn).astype(complex_dtype(dtype))
+
+
+def build_laplace_operator(derivative_operator, *, order: int = 2):
+    """exponax/_spectral.py:118-155."""
+    if order % 2 != 0:
+        raise ValueError("Order must be even.")
+    if order == 0:
+        return np.ones((1, *derivative_operator.shape[1:]), dtype=derivative_operator.dtype)
+    return np.sum(derivative_operator**order, axis=0, keepdims=True)
+
+
+def build_gradient_inner_product_operator(derivative_operator, velocity, *, order: int = 1):
+    """exponax/_spectral.py:158-209."""
+    if order % 2 != 1:
+        raise ValueError("Order must be odd.")
+    velocity = np.asarray(velocity, dtype=derivative_operator.real.dtype)
+    if velocity.shape != (derivative_operator.shape[0],):
+        raise ValueError(
+            f"""Expected velocity shape to be {derivative_operator.shape[0]},
+             got {velocity.shape}."""
+        )
+    operator = np.einsum("i,i...->...", velocity, derivative_operator**order)
+    return operator[None, ...].astype(derivative_operator.dtype)
+
+
+def space_indices(num_spatial_dims: int):
+    """exponax/_spectral.py:212-227."""
+    return tuple(range(-num_spatial_dims, 0))
+
+
+def spatial_shape(num_spatial_dims: int, num_points: int):
+    """exponax/_spectral.py:230-251."""
+    return (num_points,) * num_spatial_dims
+
+
+def wavenumber_shape(num_spatial_dims: int, num_points: int):
+    """exponax/_spectral.py:254-275."""
+    return (num_points,) * (num_spatial_dims - 1) + (num_points // 2 + 1,)
+
+
+def low_pass_filter_mask(num_spatial_dims, num_points, *, cutoff, axis_separate=True, indexing="ij", dtype=None):
+    """exponax/_spectral.py:278-342 (cutoff inclusive, compared in the working precision)."""
+    dtype = real_dtype() if dtype is None else dtype
+    wn = build_wavenumbers(num_spatial_dims, num_points, indexing=indexing, dtype=dtype)
+    cut = dtype(cutoff)
+    if axis_separate:
+        mask = True
+        for g in wn:
+            mask = mask & (np.abs(g) <= cut)
+    else:
+        mask = np.linalg.norm(wn, axis=0) <= cut
+    return mask[np.newaxis, ...]
+
+
+def dealias_kmax(num_points: int, cutoff: float, dtype=None) -> int:
+    """Largest integer wavenumber kept by `|k| <= cutoff` in the working precision (what the
+    kernels use instead of a mask array).  -1: nothing is kept."""
+    dtype = real_dtype() if dtype is None else dtype
+    k = np.arange(num_points // 2 + 1).astype(dtype)
+    keep = np.nonzero(k <= dtype(cutoff))[0]
+    return int(keep.max()) if keep.size else -1
+
+
+def build_scaling_array(num_spatial_dims, num_points, *,
+                        mode: Literal["norm_compensation", "reconstruction", "coef_extraction"],
+                        indexing="ij", dtype=None):
+    """exponax/_spectral.py:403-527."""
+    dtype = real_dtype() if dtype is None else dtype
+    den = {"norm_compensation": (1, 1), "reconstruction": (2, 1), "coef_extraction": (2, 2)}
+    if mode not in den:
+        raise ValueError("Invalid mode.")
+    rden, oden = den[mode]
+    right_wn = np.fft.rfftfreq(num_points, 1 / num_points)
+    other_wn = np.fft.fftfreq(num_points, 1 / num_points)
+    right = np.where(right_wn == 0, num_points, num_points / rden)
+    other = np.where(other_wn == 0, num_points, num_points / oden)
+    if num_points % 2 == 0:
+        right = np.where(right_wn == num_points // 2, num_points, right)
+        other = np.where(other_wn == -num_points // 2, num_points, other)
+    grids = [other] * (num_spatial_dims - 1) + [right]
+    return np.prod(np.stack(np.meshgrid(*grids, indexing=indexing)), axis=0, keepdims=True).astype(dtype)
+
+
+# ---------------------------------------------------------------------------- device transforms
+_PLAIN_PLANS = {}
+
+
+def _plain_plan(D: int, N: int, rd):
+    """Order-0 plan without nonlinearity, used for the standalone transforms."""
+    key = (D, N, np.dtype(rd).str, A.torch.cuda.current_device())
+    p = _PLAIN_PLANS.get(key)
+    if p is None:
+        M = int(np.prod(wavenumber_shape(D, N)))
+        p = nat.Plan(D=D, N=N, C_=1, E=1, order=0, dtype=rd, L=1.0, kmax=-1, nl={"kind": nat.NL_ZERO},
+                     exp_term=np.ones(M, complex_dtype(rd)))
+        _PLAIN_PLANS[key] = p
+    return p
+
+
+_WS = {}
+
+
+def workspace(nbytes: int):
+    """Grow-only per-device scratch buffer handed to libexb as its workspace."""
+    if nbytes <= 0:
+        return None
+    dev = A.torch.cuda.current_device()
+    w = _WS.get(dev)
+    if w is None or w.numel() < nbytes:
+        _WS[dev] = w = A.torch.empty(int(nbytes), dtype=A.torch.uint8, device="cuda")
+    return w
+
+
+def fft(field, *, num_spatial_dims: int | None = None):
+    """Real-valued FFT of a field `(C, N, .., N)` (leading batch axes allowed),
+    unnormalised == exponax.fft (exponax/_spectral.py:614-656)."""
+    rd = real_dtype()
+    t, kind = A.to_device(field, rd)
+    if num_spatial_dims is None:
+        num_spatial_dims = t.ndim - 1
+    D = num_spatial_dims
+    N = t.shape[-1]
+    if any(s != N for s in t.shape[-D:]):
+        raise ValueError("all spatial axes must have the same length")
+    lead = t.shape[:-D]
+    nf = int(np.prod(lead)) if lead else 1
+    out = A.torch.empty(tuple(lead) + wavenumber_shape(D, N), dtype=A.cplx_t(rd), device="cuda")
+    plan = _plain_plan(D, N, rd)
+    ws = workspace(plan.workspace_bytes(nf))
+    nat.check(nat.lib().exb_fft(plan.handle, A.stream_ptr(), nf, 1, A.ptr(t), A.ptr(out), A.ptr(ws)))
+    return A.from_device(out, kind)
+
+
+def ifft(field_hat, *, num_spatial_dims: int | None = None, num_points: int | None = None):
+    """Inverse of `fft` == exponax.ifft (exponax/_spectral.py:659-721)."""
+    rd = real_dtype()
+    t, kind = A.to_device(field_hat, rd, complex_=True)
+    if num_spatial_dims is None:
+        num_spatial_dims = t.ndim - 1
+    D = num_spatial_dims
+    if num_points is None:
+        if D >= 2:
+            num_points = t.shape[-2]
+        else:
+            raise ValueError("num_points must be provided if num_spatial_dims == 1.")
+    N = num_points
+    if tuple(t.shape[-D:]) != wavenumber_shape(D, N):
+        raise ValueError(f"expected trailing shape {wavenumber_shape(D, N)}, got {tuple(t.shape[-D:])}")
+    lead = t.shape[:-D]
+    nf = int(np.prod(lead)) if lead else 1
+    out = A.torch.empty(tuple(lead) + spatial_shape(D, N), dtype=A.real_t(rd), device="cuda")
+    plan = _plain_plan(D, N, rd)
+    ws = workspace(plan.workspace_bytes(nf))
+    nat.check(nat.lib().exb_ifft(plan.handle, A.stream_ptr(), nf, 1, A.ptr(t), A.ptr(out), A.ptr(ws)))
+    return A.from_device(out, kind)

@@ -1,0 +1,167 @@
+"""
+Loop transforms: `rollout`, `repeat` (exponax/_utils.py:92-254), `make_grid` (:11-66) and a
+`vmap` stand-in for `jax.vmap` over the leading batch axis.
+
+`rollout` / `repeat` dispatch on the type of `stepper_fn`: a native stepper (BaseStepper,
+RepeatedStepper, or a vmapped one) becomes ONE fused `exb_rollout` call -- for 1-D grids one
+persistent kernel that keeps every trajectory resident in shared memory for the whole loop;
+any other callable (neural networks, custom steppers, aux-taking steppers) runs the reference's
+plain autoregressive loop.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _array as A
+from ._base_stepper import BaseStepper
+from ._config import real_dtype
+from ._repeated_stepper import RepeatedStepper
+
+
+def make_grid(num_spatial_dims: int, domain_extent: float, num_points: int, *, full: bool = False,
+              zero_centered: bool = False, indexing: str = "ij"):
+    """exponax/_utils.py:11-66 (host array)."""
+    dt = real_dtype()
+    if full:
+        grid_1d = np.linspace(0, domain_extent, num_points + 1, endpoint=True).astype(dt)
+    else:
+        grid_1d = np.linspace(0, domain_extent, num_points, endpoint=False).astype(dt)
+    if zero_centered:
+        grid_1d = grid_1d - dt(domain_extent / 2)
+    return np.stack(np.meshgrid(*([grid_1d] * num_spatial_dims), indexing=indexing))
+
+
+class vmap:
+    """Batch a stepper / rollout function over the leading axis (stand-in for `jax.vmap`)."""
+
+    def __init__(self, fn):
+        self.fn = fn
+
+    def __call__(self, x, *aux):
+        fn = self.fn
+        if not aux:
+            if isinstance(fn, (BaseStepper, RepeatedStepper)):
+                return fn._step_batched(x)
+            if isinstance(fn, (_Rollout, _Repeat)):
+                return fn._call(x, batched=True)
+        outs = [fn(x[i], *(a[i] for a in aux)) for i in range(len(x))]
+        if isinstance(outs[0], np.ndarray):
+            return np.stack(outs)
+        return A.torch.stack(outs)
+
+
+def _native_target(stepper_fn):
+    """(base stepper, substeps, vmapped?) if `stepper_fn` can run as one fused rollout."""
+    vm = False
+    if isinstance(stepper_fn, vmap):
+        vm, stepper_fn = True, stepper_fn.fn
+    sub = 1
+    if isinstance(stepper_fn, RepeatedStepper):
+        sub, stepper_fn = stepper_fn.num_sub_steps, stepper_fn.stepper
+    if isinstance(stepper_fn, BaseStepper) and stepper_fn._plan_available():
+        return stepper_fn, sub, vm
+    return None
+
+
+def _stack(xs):
+    if isinstance(xs[0], np.ndarray):
+        return np.stack(xs)
+    return A.torch.stack(xs)
+
+
+class _Rollout:
+    def __init__(self, stepper_fn, n, include_init, takes_aux, constant_aux, spectral_carry):
+        self.stepper_fn, self.n = stepper_fn, n
+        self.include_init, self.takes_aux, self.constant_aux = include_init, takes_aux, constant_aux
+        self.spectral_carry = spectral_carry
+
+    def _call(self, u_0, *aux, batched=False):
+        tgt = None if self.takes_aux else _native_target(self.stepper_fn)
+        if tgt is not None and A.torch.cuda.is_available():
+            st, sub, vm = tgt
+            if not (vm or batched) and tuple(np.shape(u_0)) != st._state_shape():
+                raise ValueError(
+                    f"""Expected shape {st._state_shape()}, got {tuple(np.shape(u_0))}. For batched
+                 operation use `jax.vmap` on this function."""
+                )
+            # rollout(vmap(stepper)) stacks time first: (T, B, ...); vmap(rollout(stepper)): (B, T, ...)
+            return st._rollout_batched(u_0, self.n, include_init=self.include_init, layout_tb=vm and not batched,
+                                       final_only=False, substeps=sub, spectral_carry=self.spectral_carry)
+        # reference loop (exponax/_utils.py:137-186) for arbitrary callables
+        if batched:
+            return _stack([self._call(u_0[i], *(a[i] for a in aux)) for i in range(len(u_0))])
+        u, trj = u_0, []
+        for i in range(self.n):
+            if self.takes_aux:
+                a = aux[0] if self.constant_aux else _tree_index(aux[0], i)
+                u = self.stepper_fn(u, a)
+            else:
+                u = self.stepper_fn(u)
+            trj.append(u)
+        if self.include_init:
+            trj = [u_0 if type(u_0) is type(trj[0]) else _like(u_0, trj[0])] + trj
+        return _stack(trj)
+
+    def __call__(self, u_0, *aux):
+        return self._call(u_0, *aux)
+
+
+class _Repeat:
+    def __init__(self, stepper_fn, n, takes_aux, constant_aux, spectral_carry):
+        self.stepper_fn, self.n = stepper_fn, n
+        self.takes_aux, self.constant_aux = takes_aux, constant_aux
+        self.spectral_carry = spectral_carry
+
+    def _call(self, u_0, *aux, batched=False):
+        tgt = None if self.takes_aux else _native_target(self.stepper_fn)
+        if tgt is not None and self.n >= 1 and A.torch.cuda.is_available():
+            st, sub, vm = tgt
+            if not (vm or batched) and tuple(np.shape(u_0)) != st._state_shape():
+                raise ValueError(
+                    f"""Expected shape {st._state_shape()}, got {tuple(np.shape(u_0))}. For batched
+                 operation use `jax.vmap` on this function."""
+                )
+            return st._rollout_batched(u_0, self.n, include_init=False, layout_tb=False, final_only=True,
+                                       substeps=sub, spectral_carry=self.spectral_carry)
+        if batched:
+            return _stack([self._call(u_0[i], *(a[i] for a in aux)) for i in range(len(u_0))])
+        u = u_0
+        for i in range(self.n):
+            if self.takes_aux:
+                a = aux[0] if self.constant_aux else _tree_index(aux[0], i)
+                u = self.stepper_fn(u, a)
+            else:
+                u = self.stepper_fn(u)
+        return u
+
+    def __call__(self, u_0, *aux):
+        return self._call(u_0, *aux)
+
+
+def _tree_index(aux, i):
+    if isinstance(aux, dict):
+        return {k: _tree_index(v, i) for k, v in aux.items()}
+    if isinstance(aux, (tuple, list)):
+        return type(aux)(_tree_index(v, i) for v in aux)
+    return aux[i]
+
+
+def _like(x, ref):
+    if isinstance(ref, np.ndarray):
+        return np.asarray(x.cpu() if hasattr(x, "cpu") else x)
+    return A.torch.as_tensor(x, device=ref.device, dtype=ref.dtype)
+
+
+def rollout(stepper_fn, n: int, *, include_init: bool = False, takes_aux: bool = False,
+            constant_aux: bool = True, spectral_carry: bool = False):
+    """Autoregressive rollout returning the stacked trajectory (exponax/_utils.py:92-186).
+
+    `spectral_carry=True` (extension) keeps the carry in Fourier space between saved steps
+    instead of the reference's ifft -> fft round trip (identical up to rounding)."""
+    return _Rollout(stepper_fn, n, include_init, takes_aux, constant_aux, spectral_carry)
+
+
+def repeat(stepper_fn, n: int, *, takes_aux: bool = False, constant_aux: bool = True,
+           spectral_carry: bool = False):
+    """Apply the stepper n times, return only the final state (exponax/_utils.py:189-254)."""
+    return _Repeat(stepper_fn, n, takes_aux, constant_aux, spectral_carry)

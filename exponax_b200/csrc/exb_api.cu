@@ -1,0 +1,727 @@
+// libexb.so -- C ABI (include/exb.h) over the sm_100a kernels.  Host side only: plan creation
+// (factorisation, twiddles, coefficient upload) and launch sequencing.  No device allocation,
+// synchronisation or foreign stream use outside exb_plan_create / exb_plan_destroy.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/exb.h"
+#include "exb_kernels_1d.cuh"
+#include "exb_kernels_nd.cuh"
+
+using namespace exb;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CUDA_OK(expr)                                                                   \
+  do {                                                                                  \
+    cudaError_t e_ = (expr);                                                            \
+    if (e_ != cudaSuccess) return fail(EXB_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+  } while (0)
+
+struct exb_plan {
+  exb_desc d;
+  int64_t launches = 0;
+  virtual ~exb_plan() {}
+  virtual size_t workspace_bytes(int64_t batch) const = 0;
+  virtual int fft(cudaStream_t st, int64_t batch, int channels, const void* u, void* uh, void* ws) = 0;
+  virtual int ifft(cudaStream_t st, int64_t batch, int channels, const void* uh, void* u, void* ws) = 0;
+  virtual int nonlinear(cudaStream_t st, int64_t batch, const void* uh, void* out, void* ws) = 0;
+  virtual int step_fourier(cudaStream_t st, int64_t batch, const void* in, void* out, void* ws) = 0;
+  virtual int step(cudaStream_t st, int64_t batch, const void* in, void* out, void* ws) = 0;
+  virtual int rollout(cudaStream_t st, int64_t batch, int64_t n_saved, int substeps, unsigned flags,
+                      const void* u0, void* out, void* ws) = 0;
+};
+
+static void factorize(int N, FftDesc& fd) {
+  fd.N = N;
+  fd.nst = 0;
+  int n = N, e = 0;
+  while (n % 2 == 0) {
+    n /= 2;
+    ++e;
+  }
+  int n8 = e / 3, rem = e % 3;
+  if (rem == 1 && n8 >= 1) {  // 8^(n8-1) * 4 * 4
+    for (int i = 0; i < n8 - 1; ++i) fd.radix[fd.nst++] = 8;
+    fd.radix[fd.nst++] = 4;
+    fd.radix[fd.nst++] = 4;
+  } else {
+    for (int i = 0; i < n8; ++i) fd.radix[fd.nst++] = 8;
+    if (rem == 1) fd.radix[fd.nst++] = 2;
+    if (rem == 2) fd.radix[fd.nst++] = 4;
+  }
+  while (n % 5 == 0) {
+    n /= 5;
+    fd.radix[fd.nst++] = 5;
+  }
+  while (n % 3 == 0) {
+    n /= 3;
+    fd.radix[fd.nst++] = 3;
+  }
+  for (int p = 7; (long long)p * p <= n; p += 2)
+    while (n % p == 0) {
+      n /= p;
+      fd.radix[fd.nst++] = p;
+    }
+  if (n > 1) fd.radix[fd.nst++] = n;
+}
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+template <class T> struct PlanImpl : exb_plan {
+  NlParams<T> P;
+  EtdrkCoefs<T> K;
+  FftDesc fd;
+  cpx<T>* d_tw = nullptr;
+  std::vector<void*> d_allocs;
+  int D, N, Nh, C;
+  long long M;     // modes per channel
+  long long G;     // grid points per channel
+  int nscr;        // ETDRK scratch states
+  int max_smem = 0;
+  int sm_count = 148;
+
+  ~PlanImpl() override {
+    for (void* p : d_allocs) cudaFree(p);
+  }
+
+  int upload(const void* host, size_t bytes, void** dev) {
+    CUDA_OK(cudaMalloc(dev, bytes));
+    d_allocs.push_back(*dev);
+    CUDA_OK(cudaMemcpy(*dev, host, bytes, cudaMemcpyHostToDevice));
+    return EXB_OK;
+  }
+
+  int init(const exb_desc& desc) {
+    d = desc;
+    D = desc.num_spatial_dims;
+    N = desc.num_points;
+    C = desc.num_channels;
+    Nh = N / 2 + 1;
+    if (D < 1 || D > 3) return fail(EXB_EINVAL, "num_spatial_dims must be 1, 2 or 3 (got %d)", D);
+    if (N < 2) return fail(EXB_EINVAL, "num_points must be >= 2 (got %d)", N);
+    if (C < 1 || C > EXB_MAXC) return fail(EXB_EUNSUPPORTED, "num_channels must be in 1..%d (got %d)", EXB_MAXC, C);
+    if (desc.lin_channels != 1 && desc.lin_channels != C)
+      return fail(EXB_EINVAL, "lin_channels must be 1 or num_channels");
+    if (desc.order < 0 || desc.order > 4) return fail(EXB_EINVAL, "order %d not implemented", desc.order);
+    M = Nh;
+    G = N;
+    for (int i = 1; i < D; ++i) {
+      M *= N;
+      G *= N;
+    }
+    factorize(N, fd);
+    if (fd.nst > EXB_MAX_STAGES) return fail(EXB_EUNSUPPORTED, "too many FFT stages");
+
+    int dev = 0;
+    CUDA_OK(cudaGetDevice(&dev));
+    CUDA_OK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    CUDA_OK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+
+    // ---- nonlinear function descriptor ----
+    memset(&P, 0, sizeof(P));
+    P.kind = desc.nl_kind;
+    P.D = D;
+    P.N = N;
+    P.Nh = Nh;
+    P.C = C;
+    P.kmax = desc.dealias_kmax;
+    P.single_channel = desc.single_channel;
+    P.conservative = desc.conservative;
+    P.zero_mode_fix = desc.zero_mode_fix;
+    P.n_poly = desc.n_poly;
+    P.has_inj = desc.has_injection;
+    for (int i = 0; i < 3; ++i) P.inj_idx[i] = desc.injection_index[i];
+    P.inj_val = (T)desc.injection_value;
+    P.dscale = (T)(2.0 * M_PI / desc.domain_extent);
+    P.scale = (T)desc.nl_scale;
+    for (int i = 0; i < EXB_MAX_POLY; ++i) P.poly[i] = (T)desc.poly[i];
+    for (int i = 0; i < 3; ++i) P.gen[i] = (T)desc.general_scales[i];
+    {
+      double g = 1.0;
+      for (int i = 0; i < D; ++i) g *= N;
+      P.inv_norm = (T)(1.0 / g);
+    }
+    int order = desc.order;
+    switch (P.kind) {
+      case EXB_NL_ZERO:
+        P.n_inv = P.n_fwd = 0;
+        order = 0;  // every ETDRK order degenerates to exp(dt L) u when N == 0
+        break;
+      case EXB_NL_CONVECTION:
+        if (P.single_channel) {
+          if (P.conservative) {
+            P.n_inv = C;
+            P.n_fwd = C;
+          } else {
+            if (C != 1) return fail(EXB_EINVAL, "single-channel non-conservative convection needs 1 channel");
+            P.n_inv = 1 + D;
+            P.n_fwd = 1;
+          }
+        } else {
+          if (C != D)
+            return fail(EXB_EINVAL, "Number of channels in u_hat should match number of spatial dimensions");
+          if (P.conservative) {
+            P.n_inv = C;
+            P.n_fwd = C * C;
+          } else {
+            P.n_inv = C + C * D;
+            P.n_fwd = C;
+          }
+        }
+        break;
+      case EXB_NL_GRADIENT_NORM:
+        P.n_inv = C * D;
+        P.n_fwd = C;
+        break;
+      case EXB_NL_POLYNOMIAL:
+        if (P.n_poly < 0 || P.n_poly > EXB_MAX_POLY) return fail(EXB_EUNSUPPORTED, "at most %d polynomial coefficients", EXB_MAX_POLY);
+        P.n_inv = C;
+        P.n_fwd = C;
+        break;
+      case EXB_NL_VORTICITY_2D:
+        if (D != 2) return fail(EXB_EINVAL, "Expected num_spatial_dims = 2, got %d.", D);
+        if (C != 1) return fail(EXB_EINVAL, "vorticity convection needs 1 channel");
+        P.n_inv = 4;
+        P.n_fwd = 1;
+        break;
+      case EXB_NL_PROJECTED_3D:
+        if (D != 3) return fail(EXB_EINVAL, "ProjectedConvection3d only supports 3 spatial dimensions.");
+        if (C != 3) return fail(EXB_EINVAL, "projected convection needs 3 channels");
+        P.n_inv = 6;
+        P.n_fwd = 3;
+        break;
+      case EXB_NL_GENERAL:
+        P.n_inv = C * (1 + D);
+        P.n_fwd = 2 * C;
+        break;
+      default:
+        return fail(EXB_EINVAL, "unknown nl_kind %d", P.kind);
+    }
+    if (P.n_inv > EXB_MAX_INV || P.n_fwd > EXB_MAX_FWD) return fail(EXB_EUNSUPPORTED, "too many fields");
+
+    // ---- twiddles: N-th roots of unity in double, rounded once ----
+    {
+      std::vector<cpx<T>> tw(N);
+      for (int j = 0; j < N; ++j) {
+        long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)j / (long double)N;
+        tw[j] = cpx<T>((T)cosl(a), (T)sinl(a));
+      }
+      int rc = upload(tw.data(), sizeof(cpx<T>) * N, (void**)&d_tw);
+      if (rc) return rc;
+    }
+    // ---- ETDRK coefficients ----
+    memset(&K, 0, sizeof(K));
+    K.order = order;
+    K.E = desc.lin_channels;
+    K.M = M;
+    const size_t ne = (size_t)K.E * M;
+    if (!desc.exp_term) return fail(EXB_EINVAL, "exp_term is required");
+    int rc = upload(desc.exp_term, ne * sizeof(cpx<T>), (void**)&K.exp_term);
+    if (rc) return rc;
+    if (order >= 3) {
+      if (!desc.half_exp_term) return fail(EXB_EINVAL, "half_exp_term is required for order >= 3");
+      rc = upload(desc.half_exp_term, ne * sizeof(cpx<T>), (void**)&K.half_exp);
+      if (rc) return rc;
+    }
+    static const int ncoef[5] = {0, 1, 2, 5, 6};
+    for (int i = 0; i < ncoef[order]; ++i) {
+      if (!desc.coef[i]) return fail(EXB_EINVAL, "coef[%d] is required for order %d", i, order);
+      rc = upload(desc.coef[i], ne * sizeof(T), (void**)&K.c[i]);
+      if (rc) return rc;
+    }
+    nscr = etdrk_num_scratch(order);
+
+    if (D == 1) {
+      size_t need = smem_1d(C, nslots_1d());
+      if ((long long)need > max_smem)
+        return fail(EXB_EUNSUPPORTED,
+                    "1-D persistent kernel needs %zu B of shared memory for N=%d (limit %d); "
+                    "larger 1-D grids are not supported yet",
+                    need, N, max_smem);
+      CUDA_OK(cudaFuncSetAttribute(k1d_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+    } else {
+      CUDA_OK(cudaFuncSetAttribute(col_pass_kernel<T, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+      CUDA_OK(cudaFuncSetAttribute(col_pass_kernel<T, +1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+      CUDA_OK(cudaFuncSetAttribute(row_pass_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+      // every pass must fit at tile width >= 1
+      int maxf = P.n_fwd + 1 > C + 2 ? P.n_fwd + 1 : C + 2;
+      if ((size_t)maxf * N * sizeof(cpx<T>) > (size_t)max_smem)
+        return fail(EXB_EUNSUPPORTED, "N=%d too large for the shared-memory column pass", N);
+      int rs = P.n_inv > P.n_fwd ? P.n_inv : P.n_fwd;
+      if (rs < C) rs = C;
+      if ((size_t)2 * rs * N * sizeof(cpx<T>) > (size_t)max_smem)
+        return fail(EXB_EUNSUPPORTED, "N=%d too large for the shared-memory row pass", N);
+    }
+    return EXB_OK;
+  }
+
+  // ------------------------------------------------------------------ 1-D
+  int nslots_1d() const {
+    int s = P.n_inv > P.n_fwd ? P.n_inv : P.n_fwd;
+    if (s < C) s = C;
+    return s < 1 ? 1 : s;
+  }
+  size_t smem_1d(int ch, int nslots) const {
+    return ((size_t)2 * nslots * N + (size_t)(1 + nscr) * 2 * ch * Nh) * sizeof(cpx<T>);
+  }
+  int threads_1d(int lines) const {
+    int work = (N / 4 > 1 ? N / 4 : 1) * (lines < 1 ? 1 : (lines > 2 ? 2 : lines));
+    int t = (work + 31) / 32 * 32;
+    if (t < 32) t = 32;
+    if (t > 256) t = 256;
+    return t;
+  }
+
+  int launch_1d(cudaStream_t st, int op, long long batch, int ch, const void* in, void* out,
+                long long n_saved, int substeps, unsigned flags) {
+    if (batch <= 0) return EXB_OK;
+    K1dParams<T> p;
+    p.P = P;
+    p.K = K;
+    p.fd = fd;
+    p.tw = d_tw;
+    p.batch = batch;
+    p.op = op;
+    p.C = ch;
+    p.in = in;
+    p.out = out;
+    p.n_saved = n_saved;
+    p.substeps = substeps;
+    p.flags = flags;
+    bool plain = (op == OP1_FFT || op == OP1_IFFT);
+    p.nslots = plain ? ch : nslots_1d();
+    size_t smem = plain ? (size_t)2 * ch * N * sizeof(cpx<T>) : smem_1d(ch, p.nslots);
+    long long grid = (batch + 1) / 2;
+    int nthr = threads_1d(plain ? ch : p.nslots);
+    k1d_kernel<T><<<(unsigned)grid, nthr, smem, st>>>(p);
+    ++launches;
+    CUDA_OK(cudaGetLastError());
+    return EXB_OK;
+  }
+
+  // ------------------------------------------------------------------ N-D
+  int pick_tw(int ntiles_resident) const {
+    // widest tile (<= 16 lines) such that `ntiles_resident` tiles fit in shared memory
+    int tw = 16;
+    while (tw > 1 && (size_t)ntiles_resident * N * tw * sizeof(cpx<T>) > (size_t)max_smem - 1024) tw /= 2;
+    return tw;
+  }
+
+  // axis: 0 or 1 (3-D only for axis 1).  Geometry of a strided pass over that axis.
+  void col_geom(ColParams<T>& p, int axis) const {
+    if (D == 2 || axis == 0) {
+      p.line_stride = M / N;  // Nh (2-D) or N*Nh (3-D)
+      p.inner = M / N;
+      p.n_outer = 1;
+      p.outer_stride = 0;
+    } else {  // 3-D axis 1
+      p.line_stride = Nh;
+      p.inner = Nh;
+      p.n_outer = N;
+      p.outer_stride = (long long)N * Nh;
+    }
+  }
+
+  template <int DIR>
+  int col_plain(cudaStream_t st, int axis, long long batch, int nfields, const cpx<T>* in, cpx<T>* out) {
+    ColParams<T> p;
+    memset(&p, 0, sizeof(p));
+    p.P = P;
+    p.K = K;
+    p.fd = fd;
+    p.tw = d_tw;
+    p.mode = COL_PLAIN;
+    p.TW = pick_tw(2);
+    p.nfields = nfields;
+    p.M = M;
+    p.batch = batch;
+    p.in = in;
+    p.out = out;
+    col_geom(p, axis);
+    long long ntiles = (p.inner + p.TW - 1) / p.TW;
+    long long grid = ntiles * p.n_outer * batch * nfields;
+    size_t smem = (size_t)2 * N * p.TW * sizeof(cpx<T>);
+    col_pass_kernel<T, DIR><<<(unsigned)grid, 256, smem, st>>>(p);
+    ++launches;
+    CUDA_OK(cudaGetLastError());
+    return EXB_OK;
+  }
+
+  int col_inv_pro(cudaStream_t st, long long batch, const cpx<T>* state, cpx<T>* winv) {
+    ColParams<T> p;
+    memset(&p, 0, sizeof(p));
+    p.P = P;
+    p.K = K;
+    p.fd = fd;
+    p.tw = d_tw;
+    p.mode = COL_INV_PRO;
+    p.TW = pick_tw(C + 2);
+    p.nfields = P.n_inv;
+    p.M = M;
+    p.batch = batch;
+    p.in = state;
+    p.out = winv;
+    col_geom(p, 0);
+    long long ntiles = (p.inner + p.TW - 1) / p.TW;
+    long long grid = ntiles * batch;
+    size_t smem = (size_t)(C + 2) * N * p.TW * sizeof(cpx<T>);
+    col_pass_kernel<T, +1><<<(unsigned)grid, 256, smem, st>>>(p);
+    ++launches;
+    CUDA_OK(cudaGetLastError());
+    return EXB_OK;
+  }
+
+  int col_fwd(cudaStream_t st, long long batch, int mode, int stage, const cpx<T>* wfwd, cpx<T>* nl_out,
+              const StateBufs<T>& sb) {
+    ColParams<T> p;
+    memset(&p, 0, sizeof(p));
+    p.P = P;
+    p.K = K;
+    p.fd = fd;
+    p.tw = d_tw;
+    p.mode = mode;
+    p.TW = pick_tw(P.n_fwd + 1);
+    p.nfields = P.n_fwd;
+    p.stage = stage;
+    p.M = M;
+    p.batch = batch;
+    p.in = wfwd;
+    p.out = nl_out;
+    p.sb = sb;
+    col_geom(p, 0);
+    long long ntiles = (p.inner + p.TW - 1) / p.TW;
+    long long grid = ntiles * batch;
+    size_t smem = (size_t)(P.n_fwd + 1) * N * p.TW * sizeof(cpx<T>);
+    col_pass_kernel<T, -1><<<(unsigned)grid, 256, smem, st>>>(p);
+    ++launches;
+    CUDA_OK(cudaGetLastError());
+    return EXB_OK;
+  }
+
+  int row_pass(cudaStream_t st, int mode, long long batch, int nin, int nout, const void* in,
+               long long in_bs, void* out, long long out_bs) {
+    RowParams<T> p;
+    memset(&p, 0, sizeof(p));
+    p.P = P;
+    p.fd = fd;
+    p.tw = d_tw;
+    p.mode = mode;
+    p.nin = nin;
+    p.nout = nout;
+    p.rows = G / N;
+    p.batch = batch;
+    p.in_batch_stride = in_bs;
+    p.out_batch_stride = out_bs;
+    p.in = in;
+    p.out = out;
+    int nslots = nin > nout ? nin : nout;
+    size_t smem = (size_t)2 * nslots * N * sizeof(cpx<T>);
+    long long grid = ((p.rows + 1) / 2) * batch;
+    int nthr = threads_1d(nslots);
+    row_pass_kernel<T><<<(unsigned)grid, nthr, smem, st>>>(p);
+    ++launches;
+    CUDA_OK(cudaGetLastError());
+    return EXB_OK;
+  }
+
+  // physical (batch stride in_bs reals, `ch` fields) -> spectral dst (dense, ch fields)
+  int fft_nd(cudaStream_t st, long long batch, int ch, const T* src, long long in_bs, cpx<T>* dst) {
+    int rc = row_pass(st, ROW_R2C, batch, ch, ch, src, in_bs, dst, (long long)ch * M);
+    if (rc) return rc;
+    if (D == 3) {
+      rc = col_plain<-1>(st, 1, batch, ch, dst, dst);
+      if (rc) return rc;
+    }
+    return col_plain<-1>(st, 0, batch, ch, dst, dst);
+  }
+
+  // spectral src (dense; untouched) -> physical dst; tmp: dense spectral scratch of the same size
+  int ifft_nd(cudaStream_t st, long long batch, int ch, const cpx<T>* src, cpx<T>* tmp, T* dst, long long out_bs) {
+    int rc = col_plain<+1>(st, 0, batch, ch, src, tmp);
+    if (rc) return rc;
+    if (D == 3) {
+      rc = col_plain<+1>(st, 1, batch, ch, tmp, tmp);
+      if (rc) return rc;
+    }
+    return row_pass(st, ROW_C2R, batch, ch, ch, tmp, (long long)ch * M, dst, out_bs);
+  }
+
+  // workspace carving (N-D)
+  struct Ws {
+    cpx<T>* S[4];
+    cpx<T>* Uh;
+    cpx<T>* Winv;
+    cpx<T>* Wfwd;
+  };
+  size_t state_bytes(long long batch) const { return align_up((size_t)batch * C * M * sizeof(cpx<T>), 256); }
+  int winv_fields() const { return P.n_inv > C ? P.n_inv : C; }
+  int wfwd_fields() const { return P.n_fwd > C ? P.n_fwd : C; }
+  size_t workspace_bytes(int64_t batch) const override {
+    if (D == 1 || batch <= 0) return 0;
+    size_t sb = state_bytes(batch);
+    size_t fb = align_up((size_t)batch * M * sizeof(cpx<T>), 256);
+    return sb * (size_t)(nscr + 1) + fb * (size_t)(winv_fields() + wfwd_fields());
+  }
+  Ws carve(void* ws, long long batch) const {
+    Ws w;
+    unsigned char* p = (unsigned char*)ws;
+    size_t sb = state_bytes(batch);
+    size_t fb = align_up((size_t)batch * M * sizeof(cpx<T>), 256);
+    for (int i = 0; i < 4; ++i) w.S[i] = nullptr;
+    for (int i = 0; i < nscr; ++i) {
+      w.S[i] = (cpx<T>*)p;
+      p += sb;
+    }
+    w.Uh = (cpx<T>*)p;
+    p += sb;
+    w.Winv = (cpx<T>*)p;
+    p += fb * winv_fields();
+    w.Wfwd = (cpx<T>*)p;
+    return w;
+  }
+
+  // N(state) -> forward fields in w.Wfwd (all passes except the final forward column pass)
+  int nl_front_nd(cudaStream_t st, long long batch, const cpx<T>* state, const Ws& w) {
+    int rc = col_inv_pro(st, batch, state, w.Winv);
+    if (rc) return rc;
+    if (D == 3) {
+      rc = col_plain<+1>(st, 1, batch, P.n_inv, w.Winv, w.Winv);
+      if (rc) return rc;
+    }
+    rc = row_pass(st, ROW_NL, batch, P.n_inv, P.n_fwd, w.Winv, (long long)P.n_inv * M, w.Wfwd,
+                  (long long)P.n_fwd * M);
+    if (rc) return rc;
+    if (D == 3) {
+      rc = col_plain<-1>(st, 1, batch, P.n_fwd, w.Wfwd, w.Wfwd);
+      if (rc) return rc;
+    }
+    return EXB_OK;
+  }
+
+  int step_fourier_nd(cudaStream_t st, long long batch, const cpx<T>* in, cpx<T>* out, const Ws& w) {
+    if (K.order == 0) {
+      long long total = batch * C * M;
+      int grid = (int)((total + 255) / 256 < (long long)sm_count * 16 ? (total + 255) / 256 : (long long)sm_count * 16);
+      etdrk0_kernel<T><<<grid, 256, 0, st>>>(K, C, total, in, out);
+      ++launches;
+      CUDA_OK(cudaGetLastError());
+      return EXB_OK;
+    }
+    StateBufs<T> sb;
+    sb.U = in;
+    sb.OUT = out;
+    for (int i = 0; i < 4; ++i) sb.S[i] = w.S[i];
+    for (int s = 0; s < K.order; ++s) {
+      int si = etdrk_stage_input(K.order, s);
+      const cpx<T>* src = si < 0 ? in : w.S[si];
+      int rc = nl_front_nd(st, batch, src, w);
+      if (rc) return rc;
+      rc = col_fwd(st, batch, COL_FWD_EPI, s, w.Wfwd, nullptr, sb);
+      if (rc) return rc;
+    }
+    return EXB_OK;
+  }
+
+  // ------------------------------------------------------------------ entry points
+  int need_ws(void* ws, int64_t batch) {
+    if (workspace_bytes(batch) > 0 && !ws) return fail(EXB_EINVAL, "workspace is NULL but %zu bytes are required", workspace_bytes(batch));
+    return EXB_OK;
+  }
+
+  int fft(cudaStream_t st, int64_t batch, int channels, const void* u, void* uh, void* ws) override {
+    if (channels < 1) return fail(EXB_EINVAL, "channels must be >= 1");
+    if (D == 1) return launch_1d(st, OP1_FFT, batch * channels, 1, u, uh, 0, 0, 0);
+    return fft_nd(st, batch, channels, (const T*)u, (long long)channels * G, (cpx<T>*)uh);
+  }
+
+  int ifft(cudaStream_t st, int64_t batch, int channels, const void* uh, void* u, void* ws) override {
+    if (channels < 1) return fail(EXB_EINVAL, "channels must be >= 1");
+    if (D == 1) return launch_1d(st, OP1_IFFT, batch * channels, 1, uh, u, 0, 0, 0);
+    if (channels > winv_fields()) return fail(EXB_EUNSUPPORTED, "ifft supports at most %d channels with this plan", winv_fields());
+    int rc = need_ws(ws, batch);
+    if (rc) return rc;
+    Ws w = carve(ws, batch);
+    return ifft_nd(st, batch, channels, (const cpx<T>*)uh, w.Winv, (T*)u, (long long)channels * G);
+  }
+
+  int nonlinear(cudaStream_t st, int64_t batch, const void* uh, void* out, void* ws) override {
+    if (P.kind == EXB_NL_ZERO) {
+      CUDA_OK(cudaMemsetAsync(out, 0, (size_t)batch * C * M * sizeof(cpx<T>), st));
+      return EXB_OK;
+    }
+    if (D == 1) return launch_1d(st, OP1_NL, batch, C, uh, out, 0, 0, 0);
+    int rc = need_ws(ws, batch);
+    if (rc) return rc;
+    Ws w = carve(ws, batch);
+    rc = nl_front_nd(st, batch, (const cpx<T>*)uh, w);
+    if (rc) return rc;
+    StateBufs<T> sb;
+    memset(&sb, 0, sizeof(sb));
+    return col_fwd(st, batch, COL_FWD_NL, 0, w.Wfwd, (cpx<T>*)out, sb);
+  }
+
+  int step_fourier(cudaStream_t st, int64_t batch, const void* in, void* out, void* ws) override {
+    if (D == 1) return launch_1d(st, OP1_STEP_FOURIER, batch, C, in, out, 0, 1, 0);
+    int rc = need_ws(ws, batch);
+    if (rc) return rc;
+    Ws w = carve(ws, batch);
+    return step_fourier_nd(st, batch, (const cpx<T>*)in, (cpx<T>*)out, w);
+  }
+
+  int step(cudaStream_t st, int64_t batch, const void* in, void* out, void* ws) override {
+    return rollout(st, batch, 1, 1, EXB_ROLLOUT_FINAL_ONLY, in, out, ws);
+  }
+
+  int rollout(cudaStream_t st, int64_t batch, int64_t n_saved, int substeps, unsigned flags, const void* u0,
+              void* out, void* ws) override {
+    if (n_saved < 0 || substeps < 1) return fail(EXB_EINVAL, "n_saved must be >= 0 and substeps >= 1");
+    const bool include_init = flags & EXB_ROLLOUT_INCLUDE_INIT;
+    const bool layout_tb = flags & EXB_ROLLOUT_LAYOUT_TB;
+    const bool final_only = flags & EXB_ROLLOUT_FINAL_ONLY;
+    const bool spectral_carry = flags & EXB_ROLLOUT_SPECTRAL_CARRY;
+    if (final_only && n_saved < 1) return fail(EXB_EINVAL, "FINAL_ONLY needs n_saved >= 1");
+    if (D == 1) {
+      if (n_saved == 0 && !include_init) return EXB_OK;
+      return launch_1d(st, OP1_ROLLOUT, batch, C, u0, out, n_saved, substeps, flags);
+    }
+    int rc = need_ws(ws, batch);
+    if (rc) return rc;
+    Ws w = carve(ws, batch);
+    const long long fsz = (long long)C * G;
+    const long long Tn = final_only ? 1 : n_saved + (include_init ? 1 : 0);
+    T* o = (T*)out;
+    auto slot = [&](long long s, long long& bs) -> T* {
+      if (final_only) {
+        bs = fsz;
+        return o;
+      }
+      if (layout_tb) {
+        bs = fsz;
+        return o + (size_t)s * batch * fsz;
+      }
+      bs = Tn * fsz;
+      return o + (size_t)s * fsz;
+    };
+    if (include_init && !final_only) {
+      long long bs;
+      T* dst = slot(0, bs);
+      long long total = batch * fsz;
+      int grid = (int)((total + 255) / 256 < (long long)sm_count * 16 ? (total + 255) / 256 : (long long)sm_count * 16);
+      copy_batched_kernel<T><<<grid, 256, 0, st>>>((const T*)u0, fsz, dst, bs, fsz, batch);
+      ++launches;
+      CUDA_OK(cudaGetLastError());
+    }
+    rc = fft_nd(st, batch, C, (const T*)u0, fsz, w.Uh);
+    if (rc) return rc;
+    T* phys_scratch = (T*)w.Wfwd;  // >= C*G reals per batch element (M*2 >= G)
+    for (long long s = 0; s < n_saved; ++s) {
+      for (int sub = 0; sub < substeps; ++sub) {
+        rc = step_fourier_nd(st, batch, w.Uh, w.Uh, w);
+        if (rc) return rc;
+      }
+      const bool last = s == n_saved - 1;
+      const bool store = !final_only || last;
+      if (!store && spectral_carry) continue;
+      long long bs = fsz;
+      T* dst = phys_scratch;
+      if (store) dst = slot(final_only ? 0 : s + (include_init ? 1 : 0), bs);
+      rc = ifft_nd(st, batch, C, w.Uh, w.Winv, dst, bs);
+      if (rc) return rc;
+      if (last) break;
+      if (!spectral_carry) {
+        rc = fft_nd(st, batch, C, dst, bs, w.Uh);
+        if (rc) return rc;
+      }
+    }
+    return EXB_OK;
+  }
+};
+
+// ---------------------------------------------------------------------------------- C ABI
+extern "C" {
+
+const char* exb_last_error(void) { return g_err.c_str(); }
+const char* exb_version(void) { return "exb 0.1 (sm_100a)"; }
+
+int exb_plan_create(const exb_desc* desc, exb_plan** out) {
+  if (!desc || !out) return fail(EXB_EINVAL, "null argument");
+  if (desc->struct_size != (int32_t)sizeof(exb_desc))
+    return fail(EXB_EINVAL, "exb_desc size mismatch (got %d, expected %zu)", desc->struct_size, sizeof(exb_desc));
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(EXB_ECUDA, "no CUDA device available (%s); libexb has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  }
+  *out = nullptr;
+  int rc;
+  if (desc->dtype == EXB_F32) {
+    auto* p = new PlanImpl<float>();
+    rc = p->init(*desc);
+    if (rc) {
+      delete p;
+      return rc;
+    }
+    *out = p;
+  } else if (desc->dtype == EXB_F64) {
+    auto* p = new PlanImpl<double>();
+    rc = p->init(*desc);
+    if (rc) {
+      delete p;
+      return rc;
+    }
+    *out = p;
+  } else {
+    return fail(EXB_EINVAL, "unknown dtype %d", desc->dtype);
+  }
+  return EXB_OK;
+}
+
+void exb_plan_destroy(exb_plan* plan) { delete plan; }
+
+size_t exb_workspace_bytes(const exb_plan* plan, int64_t batch) { return plan ? plan->workspace_bytes(batch) : 0; }
+
+int exb_fft(exb_plan* plan, void* stream, int64_t batch, int32_t channels, const void* u, void* u_hat, void* ws) {
+  if (!plan) return fail(EXB_EINVAL, "null plan");
+  return plan->fft((cudaStream_t)stream, batch, channels, u, u_hat, ws);
+}
+int exb_ifft(exb_plan* plan, void* stream, int64_t batch, int32_t channels, const void* u_hat, void* u, void* ws) {
+  if (!plan) return fail(EXB_EINVAL, "null plan");
+  return plan->ifft((cudaStream_t)stream, batch, channels, u_hat, u, ws);
+}
+int exb_nonlinear_fun(exb_plan* plan, void* stream, int64_t batch, const void* u_hat, void* out_hat, void* ws) {
+  if (!plan) return fail(EXB_EINVAL, "null plan");
+  return plan->nonlinear((cudaStream_t)stream, batch, u_hat, out_hat, ws);
+}
+int exb_step_fourier(exb_plan* plan, void* stream, int64_t batch, const void* in, void* out, void* ws) {
+  if (!plan) return fail(EXB_EINVAL, "null plan");
+  return plan->step_fourier((cudaStream_t)stream, batch, in, out, ws);
+}
+int exb_step(exb_plan* plan, void* stream, int64_t batch, const void* in, void* out, void* ws) {
+  if (!plan) return fail(EXB_EINVAL, "null plan");
+  return plan->step((cudaStream_t)stream, batch, in, out, ws);
+}
+int exb_rollout(exb_plan* plan, void* stream, int64_t batch, int64_t n_saved, int32_t substeps, uint32_t flags,
+                const void* u0, void* out, void* ws) {
+  if (!plan) return fail(EXB_EINVAL, "null plan");
+  return plan->rollout((cudaStream_t)stream, batch, n_saved, substeps, flags, u0, out, ws);
+}
+int64_t exb_launch_count(const exb_plan* plan) { return plan ? plan->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,296 @@
+// 2-D / 3-D path.  A D-dimensional real transform is (D-1) strided "column" passes over the
+// outer axes (complex FFTs on [N x TW] tiles staged in shared memory) plus one "row" pass over
+// the contiguous last axis.  Everything that is not a butterfly is fused into those passes:
+//   * inverse column pass over axis 0  : prologue = dealias mask, i*k, inverse Laplacian, curl
+//   * row pass                         : c2r -> pointwise nonlinearity -> r2c, two rows per
+//                                        complex FFT (two-for-one), physical fields never in HBM
+//   * forward column pass over axis 0  : epilogue = dealias mask, scale, Leray projection,
+//                                        injection and the ETDRK stage update
+// Reference semantics: exponax/nonlin_fun/_base.py:99-137 (mask placement), exponax/_spectral.py
+// :614-721 (rfftn / irfftn), exponax/etdrk/*.py (stage updates).
+#pragma once
+#include "exb_fft.cuh"
+#include "exb_kernels_1d.cuh"  // pack2 / unpack2
+#include "exb_nl.cuh"
+
+namespace exb {
+
+enum ColMode { COL_PLAIN = 0, COL_INV_PRO = 1, COL_FWD_EPI = 2, COL_FWD_NL = 3 };
+enum RowMode { ROW_NL = 0, ROW_R2C = 1, ROW_C2R = 2 };
+
+template <class T> struct ColParams {
+  NlParams<T> P;
+  EtdrkCoefs<T> K;
+  FftDesc fd;
+  const cpx<T>* tw;
+  int mode;
+  int TW;                  // tile width (lines per CTA)
+  int nfields;             // fields per batch element (PLAIN); n_inv / n_fwd otherwise
+  int stage;               // ETDRK stage (FWD_EPI)
+  long long line_stride;   // elements between successive points of a line
+  long long inner;         // contiguous positions across which lines are tiled
+  long long n_outer;       // independent slabs per field (3-D axis-1 pass: N)
+  long long outer_stride;  // elements between slabs
+  long long M;             // elements per field
+  long long batch;
+  const cpx<T>* in;        // PLAIN / FWD: fields; INV_PRO: stage input state (batch, C, M)
+  cpx<T>* out;             // PLAIN / INV_PRO: fields; FWD_NL: N(u) (batch, C, M)
+  StateBufs<T> sb;         // FWD_EPI
+};
+
+// decode the spatial indices of tile element (i along the line, iw along the inner direction);
+// only used by the passes over axis 0 (prologue / epilogue), where inner = everything else.
+template <class T>
+__device__ __forceinline__ ModeK<T> col_mode(const NlParams<T>& P, int i, long long iw) {
+  if (P.D == 2) return make_mode(P, i, (int)iw, 0);
+  int i1 = (int)(iw / P.Nh);
+  int i2 = (int)(iw - (long long)i1 * P.Nh);
+  return make_mode(P, i, i1, i2);
+}
+
+template <class T, int DIR> __global__ void col_pass_kernel(const ColParams<T> p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cpx<T>* sm = reinterpret_cast<cpx<T>*>(smem_raw);
+  const int N = p.fd.N, TW = p.TW;
+  const size_t tile = (size_t)N * TW;
+  const long long ntiles = (p.inner + TW - 1) / TW;
+  long long bid = blockIdx.x;
+  const long long t = bid % ntiles;
+  bid /= ntiles;
+  const long long w0 = t * TW;
+  const int wv = (int)((p.inner - w0) < TW ? (p.inner - w0) : TW);
+  const cpx<T> zero((T)0, (T)0);
+
+  if (p.mode == COL_PLAIN) {
+    const long long o = bid % p.n_outer;
+    bid /= p.n_outer;
+    const long long fb = bid;  // batch * nfields + field
+    const size_t base = (size_t)fb * p.M + (size_t)o * p.outer_stride + w0;
+    cpx<T>* A = sm;
+    cpx<T>* B = sm + tile;
+    for (int q = threadIdx.x; q < N * TW; q += blockDim.x) {
+      int i = q / TW, w = q - i * TW;
+      A[q] = w < wv ? p.in[base + (size_t)i * p.line_stride + w] : zero;
+    }
+    __syncthreads();
+    cpx<T>* R = fft_lines<T, DIR>(A, B, TW, 1, TW, true, p.fd, p.tw);
+    for (int q = threadIdx.x; q < N * TW; q += blockDim.x) {
+      int i = q / TW, w = q - i * TW;
+      if (w < wv) p.out[base + (size_t)i * p.line_stride + w] = R[q];
+    }
+    return;
+  }
+
+  const NlParams<T>& P = p.P;
+  const int C = P.C;
+  const long long b = bid;
+
+  if (p.mode == COL_INV_PRO) {
+    cpx<T>* Ust = sm;                       // C tiles of the stage input
+    cpx<T>* A = sm + (size_t)C * tile;
+    cpx<T>* B = A + tile;
+    for (int q = threadIdx.x; q < C * N * TW; q += blockDim.x) {
+      int ch = q / (N * TW);
+      int r = q - ch * (N * TW);
+      int i = r / TW, w = r - i * TW;
+      Ust[q] = w < wv ? p.in[((size_t)b * C + ch) * p.M + (size_t)i * p.line_stride + w0 + w] : zero;
+    }
+    __syncthreads();
+    for (int f = 0; f < P.n_inv; ++f) {
+      for (int q = threadIdx.x; q < N * TW; q += blockDim.x) {
+        int i = q / TW, w = q - i * TW;
+        cpx<T> v = zero;
+        if (w < wv) {
+          ModeK<T> m = col_mode(P, i, w0 + w);
+          cpx<T> uh[EXB_MAXC];
+#pragma unroll
+          for (int ch = 0; ch < EXB_MAXC; ++ch) uh[ch] = ch < C ? Ust[(size_t)ch * tile + q] : zero;
+          v = nl_inv_field(P, f, uh, m);
+        }
+        A[q] = v;
+      }
+      __syncthreads();
+      cpx<T>* R = fft_lines<T, DIR>(A, B, TW, 1, TW, true, p.fd, p.tw);
+      const size_t obase = ((size_t)b * P.n_inv + f) * p.M + w0;
+      for (int q = threadIdx.x; q < N * TW; q += blockDim.x) {
+        int i = q / TW, w = q - i * TW;
+        if (w < wv) p.out[obase + (size_t)i * p.line_stride + w] = R[q];
+      }
+      __syncthreads();
+    }
+    return;
+  }
+
+  // COL_FWD_EPI / COL_FWD_NL: transform all n_fwd fields of this tile, then the per-mode epilogue
+  cpx<T>* res[EXB_MAX_FWD];
+  cpx<T>* scratch = sm + (size_t)P.n_fwd * tile;
+  for (int g = 0; g < P.n_fwd; ++g) {
+    cpx<T>* A = sm + (size_t)g * tile;
+    const size_t ibase = ((size_t)b * P.n_fwd + g) * p.M + w0;
+    for (int q = threadIdx.x; q < N * TW; q += blockDim.x) {
+      int i = q / TW, w = q - i * TW;
+      A[q] = w < wv ? p.in[ibase + (size_t)i * p.line_stride + w] : zero;
+    }
+  }
+  __syncthreads();
+  for (int g = 0; g < P.n_fwd; ++g) {
+    cpx<T>* A = sm + (size_t)g * tile;
+    // the scratch of field g is whatever buffer is currently free
+    cpx<T>* R = fft_lines<T, DIR>(A, scratch, TW, 1, TW, true, p.fd, p.tw);
+    if (R != A) {
+      // result landed in the scratch: that buffer now belongs to field g, A becomes the scratch.
+      // Keep the slot order simple by remembering the pointer.
+      res[g] = R;
+      scratch = A;
+    } else {
+      res[g] = A;
+    }
+  }
+  for (int q = threadIdx.x; q < N * TW; q += blockDim.x) {
+    int i = q / TW, w = q - i * TW;
+    if (w >= wv) continue;
+    ModeK<T> m = col_mode(P, i, w0 + w);
+    cpx<T> W[EXB_MAX_FWD], n[EXB_MAXC];
+    for (int g = 0; g < P.n_fwd; ++g) W[g] = res[g][q];
+    nl_from_fwd(P, W, m, n);
+    const long long mode = (long long)i * p.line_stride + w0 + w;
+#pragma unroll
+    for (int ch = 0; ch < EXB_MAXC; ++ch) {
+      if (ch < C) {
+        const size_t off = ((size_t)b * C + ch) * p.M + mode;
+        if (p.mode == COL_FWD_NL) {
+          p.out[off] = n[ch];
+        } else {
+          const long long ci = (long long)(p.K.E == 1 ? 0 : ch) * p.K.M + mode;
+          etdrk_update(p.K, p.stage, ci, off, n[ch], p.sb);
+        }
+      }
+    }
+  }
+}
+
+template <class T> struct RowParams {
+  NlParams<T> P;
+  FftDesc fd;
+  const cpx<T>* tw;
+  int mode;
+  int nin, nout;             // fields per batch element read / written
+  long long rows;            // rows per field = N^(D-1)
+  long long batch;
+  long long in_batch_stride;   // elements (of the in type) between batch elements
+  long long out_batch_stride;  // elements (of the out type) between batch elements
+  const void* in;
+  void* out;
+};
+
+// one CTA = one pair of rows (r1, r1+1) of one batch element, all fields
+template <class T> __global__ void row_pass_kernel(const RowParams<T> p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cpx<T>* sm = reinterpret_cast<cpx<T>*>(smem_raw);
+  const NlParams<T>& P = p.P;
+  const int N = p.fd.N, Nh = N / 2 + 1;
+  const long long npairs = (p.rows + 1) / 2;
+  const long long b = blockIdx.x / npairs;
+  const long long rp = blockIdx.x - b * npairs;
+  const long long r1 = 2 * rp, r2 = r1 + 1;
+  const bool has2 = r2 < p.rows;
+  const int nslots = p.nin > p.nout ? p.nin : p.nout;
+  cpx<T>* A = sm;
+  cpx<T>* B = sm + (size_t)nslots * N;
+  const cpx<T> zero((T)0, (T)0);
+
+  if (p.mode == ROW_R2C) {
+    const T* in = (const T*)p.in + (size_t)b * p.in_batch_stride;
+    for (int q = threadIdx.x; q < p.nin * N; q += blockDim.x) {
+      int f = q / N, x = q - f * N;
+      T a = in[((size_t)f * p.rows + r1) * N + x];
+      T c = has2 ? in[((size_t)f * p.rows + r2) * N + x] : (T)0;
+      A[q] = cpx<T>(a, c);
+    }
+    __syncthreads();
+    cpx<T>* R = fft_lines<T, -1>(A, B, p.nin, N, 1, false, p.fd, p.tw);
+    cpx<T>* out = (cpx<T>*)p.out + (size_t)b * p.out_batch_stride;
+    for (int q = threadIdx.x; q < p.nin * Nh; q += blockDim.x) {
+      int f = q / Nh, k = q - f * Nh;
+      cpx<T> X1, X2;
+      unpack2(R + (size_t)f * N, N, k, X1, X2);
+      out[((size_t)f * p.rows + r1) * Nh + k] = X1;
+      if (has2) out[((size_t)f * p.rows + r2) * Nh + k] = X2;
+    }
+    return;
+  }
+
+  // ROW_NL / ROW_C2R start from half-complex rows
+  {
+    const cpx<T>* in = (const cpx<T>*)p.in + (size_t)b * p.in_batch_stride;
+    for (int q = threadIdx.x; q < p.nin * Nh; q += blockDim.x) {
+      int f = q / Nh, k = q - f * Nh;
+      cpx<T> F1 = in[((size_t)f * p.rows + r1) * Nh + k];
+      cpx<T> F2 = has2 ? in[((size_t)f * p.rows + r2) * Nh + k] : zero;
+      pack2(A + (size_t)f * N, N, k, F1, F2);
+    }
+  }
+  __syncthreads();
+  cpx<T>* R = fft_lines<T, +1>(A, B, p.nin, N, 1, false, p.fd, p.tw);
+  cpx<T>* O = (R == A) ? B : A;
+
+  if (p.mode == ROW_C2R) {
+    T* out = (T*)p.out + (size_t)b * p.out_batch_stride;
+    for (int q = threadIdx.x; q < p.nin * N; q += blockDim.x) {
+      int f = q / N, x = q - f * N;
+      cpx<T> v = R[q];
+      out[((size_t)f * p.rows + r1) * N + x] = v.x * P.inv_norm;
+      if (has2) out[((size_t)f * p.rows + r2) * N + x] = v.y * P.inv_norm;
+    }
+    return;
+  }
+
+  for (int x = threadIdx.x; x < N; x += blockDim.x) {
+    T i1[EXB_MAX_INV], i2[EXB_MAX_INV], o1[EXB_MAX_FWD], o2[EXB_MAX_FWD];
+    for (int f = 0; f < p.nin; ++f) {
+      cpx<T> v = R[(size_t)f * N + x];
+      i1[f] = v.x * P.inv_norm;
+      i2[f] = v.y * P.inv_norm;
+    }
+    nl_pointwise(P, i1, o1);
+    nl_pointwise(P, i2, o2);
+    for (int g = 0; g < p.nout; ++g) R[(size_t)g * N + x] = cpx<T>(o1[g], o2[g]);
+  }
+  __syncthreads();
+  cpx<T>* W = fft_lines<T, -1>(R, O, p.nout, N, 1, false, p.fd, p.tw);
+  cpx<T>* out = (cpx<T>*)p.out + (size_t)b * p.out_batch_stride;
+  for (int q = threadIdx.x; q < p.nout * Nh; q += blockDim.x) {
+    int g = q / Nh, k = q - g * Nh;
+    cpx<T> X1, X2;
+    unpack2(W + (size_t)g * N, N, k, X1, X2);
+    out[((size_t)g * p.rows + r1) * Nh + k] = X1;
+    if (has2) out[((size_t)g * p.rows + r2) * Nh + k] = X2;
+  }
+}
+
+// order-0 step / generic per-mode scale: out = exp_term * in
+template <class T>
+__global__ void etdrk0_kernel(const EtdrkCoefs<T> K, int C, long long total, const cpx<T>* in, cpx<T>* out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    long long mode = i % K.M;
+    int ch = (int)((i / K.M) % C);
+    long long ci = (long long)(K.E == 1 ? 0 : ch) * K.M + mode;
+    out[i] = K.exp_term[ci] * in[i];
+  }
+}
+
+// strided copy of `batch` contiguous chunks of `n` elements
+template <class T>
+__global__ void copy_batched_kernel(const T* in, long long in_stride, T* out, long long out_stride, long long n,
+                                    long long batch) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n * batch; i += stride) {
+    long long b = i / n, j = i - b * n;
+    out[b * out_stride + j] = in[b * in_stride + j];
+  }
+}
+
+}  // namespace exb

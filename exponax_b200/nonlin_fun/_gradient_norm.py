@@ -1,0 +1,20 @@
+from .. import _native as nat
+from ._base import BaseNonlinearFun
+
+
+class GradientNormNonlinearFun(BaseNonlinearFun):
+    """exponax/nonlin_fun/_gradient_norm.py:8-101.  The zero-mode fix (subtracting the spatial
+    mean of |grad u|^2) is applied as "DC mode of the forward transform := 0"."""
+
+    def __init__(self, num_spatial_dims: int, num_points: int, *, derivative_operator,
+                 dealiasing_fraction: float, zero_mode_fix: bool = True, scale: float = 1.0):
+        super().__init__(num_spatial_dims, num_points, dealiasing_fraction=dealiasing_fraction)
+        self.derivative_operator = derivative_operator
+        self.zero_mode_fix = zero_mode_fix
+        self.scale = scale
+
+    def _native_desc(self, num_channels):
+        return {"kind": nat.NL_GRADIENT_NORM, "scale": self.scale, "zero_mode_fix": self.zero_mode_fix}
+
+    def __call__(self, u_hat):
+        return self._native_call(u_hat)

@@ -1,0 +1,151 @@
+/*
+ * exb.h -- C ABI of libexb.so, the B200-native (sm_100a) ETDRK spectral
+ * time-stepping core behind the exponax stepper API.
+ *
+ * The reference (Ceyron/exponax) has no FFI layer of its own: the hot path is
+ * Python on jax.numpy.  Each entry point below replaces the body of one
+ * reference method; a maintainer binds them with ctypes / jax.ffi as shown in
+ * INTEGRATION.md.
+ *
+ *   exb_fft            <- exponax/_spectral.py:614-656   (fft = rfftn, unnormalised)
+ *   exb_ifft           <- exponax/_spectral.py:659-721   (ifft = irfftn, 1/N^D)
+ *   exb_nonlinear_fun  <- exponax/nonlin_fun/*.py  __call__(u_hat)
+ *   exb_step_fourier   <- exponax/_base_stepper.py:222-239 + etdrk/_etdrk_{0..4}.py step_fourier
+ *   exb_step           <- exponax/_base_stepper.py:201-220  (fft -> step_fourier -> ifft)
+ *   exb_rollout        <- exponax/_utils.py:92-254 (rollout / repeat) composed with
+ *                         exponax/_repeated_stepper.py:56-102 (sub-steps with spectral carry)
+ *
+ * Conventions
+ *   - every array pointer is a DEVICE pointer owned by the caller (C-contiguous,
+ *     reference layout: state (batch, C, N, .., N) real; spectral state
+ *     (batch, C, N, .., N/2+1) complex interleaved re,im);
+ *   - `stream` is a cudaStream_t passed as void*; the library only enqueues work
+ *     on it -- no allocation, no synchronisation, no other stream -- so calls can
+ *     be captured in CUDA graphs / XLA command buffers;
+ *   - `workspace` is a caller-owned device buffer of at least
+ *     exb_workspace_bytes(plan, batch) bytes (may be NULL when that is 0);
+ *   - device memory is allocated only in exb_plan_create (twiddles, coefficient
+ *     tables) and released in exb_plan_destroy;
+ *   - return value 0 on success, <0 on error; exb_last_error() gives the
+ *     thread-local message.  There is NO CPU fallback: without a CUDA device
+ *     every compute entry point fails with EXB_ECUDA.
+ */
+#ifndef EXB_H_
+#define EXB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EXB_OK 0
+#define EXB_EINVAL (-1)
+#define EXB_EUNSUPPORTED (-2)
+#define EXB_ECUDA (-3)
+
+#define EXB_F32 0
+#define EXB_F64 1
+
+/* nonlinear function kinds (exponax/nonlin_fun/) */
+#define EXB_NL_ZERO 0            /* _zero.py:34-38 */
+#define EXB_NL_CONVECTION 1      /* _convection.py:104-245 (4 variants via flags) */
+#define EXB_NL_GRADIENT_NORM 2   /* _gradient_norm.py:78-101 */
+#define EXB_NL_POLYNOMIAL 3      /* _polynomial.py:64-76 */
+#define EXB_NL_VORTICITY_2D 4    /* _vorticity_convection.py:78-99, 166-182 */
+#define EXB_NL_PROJECTED_3D 5    /* _projected_convection.py:114-136, 202-226 (+ _leray.py:114-136) */
+#define EXB_NL_GENERAL 6         /* _general_nonlinear.py:78-119 */
+
+#define EXB_MAX_POLY 8
+
+/* exb_rollout flags */
+#define EXB_ROLLOUT_INCLUDE_INIT 1u   /* prepend u0 (rollout(include_init=True)) */
+#define EXB_ROLLOUT_LAYOUT_TB 2u      /* output (T, B, C, ..) instead of (B, T, C, ..) */
+#define EXB_ROLLOUT_FINAL_ONLY 4u     /* ex.repeat: write only the last state, shape (B, C, ..) */
+#define EXB_ROLLOUT_SPECTRAL_CARRY 8u /* keep the carry in Fourier space between saved steps
+                                         (Hermitian-projected; differs from the reference's
+                                         ifft->fft round trip at rounding level only) */
+
+typedef struct exb_plan exb_plan;
+
+typedef struct exb_desc {
+  int32_t struct_size;       /* sizeof(exb_desc), ABI guard */
+  int32_t num_spatial_dims;  /* D in {1,2,3} */
+  int32_t num_points;        /* N per axis */
+  int32_t num_channels;      /* C */
+  int32_t lin_channels;      /* E in {1, C}: leading extent of the coefficient arrays */
+  int32_t order;             /* ETDRK order 0..4 */
+  int32_t dtype;             /* EXB_F32 / EXB_F64 */
+  int32_t dealias_kmax;      /* keep |k_d| <= kmax on every axis; <0: no dealiasing mask */
+  double domain_extent;      /* L */
+  /* nonlinear function */
+  int32_t nl_kind;
+  int32_t single_channel;    /* convection */
+  int32_t conservative;      /* convection */
+  int32_t zero_mode_fix;     /* gradient norm / general */
+  double nl_scale;           /* convection scale / gradient-norm scale / vorticity convection scale */
+  int32_t n_poly;            /* polynomial: number of coefficients (<= EXB_MAX_POLY) */
+  int32_t reserved0;
+  double poly[EXB_MAX_POLY];
+  double general_scales[3];  /* general: (b0, b1, b2) as in GeneralNonlinearFun.scale_list */
+  /* Kolmogorov injection: constant real value added (un-masked) to channel 0 of N(u) at one
+     spectral index; has_injection = 0 disables */
+  int32_t has_injection;
+  int32_t injection_index[3];
+  double injection_value;
+  /* ETDRK coefficient tables, HOST pointers, copied to the device in exb_plan_create.
+     exp_term/half_exp_term: complex (E, modes); coef[i]: real (E, modes); unused ones NULL.
+     modes = N^(D-1) * (N/2+1), C-order.   (etdrk/_base_etdrk.py:61-62, _etdrk_{1..4}.py) */
+  const void *exp_term;
+  const void *half_exp_term;
+  const void *coef[6];
+} exb_desc;
+
+/* thread-local description of the last error on this thread */
+const char *exb_last_error(void);
+/* library version string */
+const char *exb_version(void);
+
+/* create a plan on the CURRENT cuda device */
+int exb_plan_create(const exb_desc *desc, exb_plan **out);
+void exb_plan_destroy(exb_plan *plan);
+
+/* bytes of caller-provided workspace the calls below need for `batch` trajectories */
+size_t exb_workspace_bytes(const exb_plan *plan, int64_t batch);
+
+/* u (batch, C, N..N) real  ->  u_hat (batch, C, N.., N/2+1) complex; channels: number of
+   leading fields per batch element (pass plan's C for a state) */
+int exb_fft(exb_plan *plan, void *stream, int64_t batch, int32_t channels, const void *u,
+            void *u_hat, void *workspace);
+/* inverse; u_hat is NOT modified */
+int exb_ifft(exb_plan *plan, void *stream, int64_t batch, int32_t channels, const void *u_hat,
+             void *u, void *workspace);
+
+/* out_hat = N(u_hat) (dealiasing, derivative operators, projection, injection included) */
+int exb_nonlinear_fun(exb_plan *plan, void *stream, int64_t batch, const void *u_hat,
+                      void *out_hat, void *workspace);
+
+/* one ETDRK step in Fourier space; u_hat_in and u_hat_out may alias */
+int exb_step_fourier(exb_plan *plan, void *stream, int64_t batch, const void *u_hat_in,
+                     void *u_hat_out, void *workspace);
+
+/* one ETDRK step in physical space; u_in and u_out may alias */
+int exb_step(exb_plan *plan, void *stream, int64_t batch, const void *u_in, void *u_out,
+             void *workspace);
+
+/* n_saved * substeps ETDRK steps starting from u0 (batch, C, N..N).  After every `substeps`
+   steps the state is transformed to physical space and (unless FINAL_ONLY) stored:
+     default        out (batch, T, C, N..N)      T = n_saved (+1 with INCLUDE_INIT)
+     LAYOUT_TB      out (T, batch, C, N..N)
+     FINAL_ONLY     out (batch, C, N..N)         (ex.repeat) */
+int exb_rollout(exb_plan *plan, void *stream, int64_t batch, int64_t n_saved, int32_t substeps,
+                uint32_t flags, const void *u0, void *out, void *workspace);
+
+/* number of kernel launches issued through this plan so far (bench bookkeeping) */
+int64_t exb_launch_count(const exb_plan *plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EXB_H_ */

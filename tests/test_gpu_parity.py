@@ -1,0 +1,436 @@
+"""
+GPU parity: the CUDA path (through the C ABI, via the exponax-style Python classes) against the
+NumPy oracle on identical seeded inputs.  Tolerances are those of BASELINE.json's north_star:
+relative L2 <= 1e-5 per step in float32, <= 1e-12 in float64, <= 1e-4 over 100-step rollouts of
+non-chaotic equations.
+"""
+import numpy as np
+import pytest
+import torch
+
+import exponax_b200 as ex
+from oracle import exponax_np as ox
+
+pytestmark = pytest.mark.gpu
+
+F32_STEP = 1e-5
+F64_STEP = 1e-12
+ROLLOUT_100 = 1e-4
+
+
+def rel(a, b):
+    a = np.asarray(a)
+    b = np.asarray(b)
+    nb = np.linalg.norm(b)
+    return float(np.linalg.norm(a - b) / (nb if nb > 0 else 1.0))
+
+
+def dev(x):
+    return torch.as_tensor(x, device="cuda")
+
+
+def host(x):
+    return x.cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+
+
+def ic(D, N, seeds, C=1, dtype=np.float32):
+    return np.stack([
+        np.concatenate([ox.random_truncated_fourier_series(D, N, cutoff=min(5, N // 4), seed=100 * s + c,
+                                                           max_one=True, dtype=dtype) for c in range(C)])
+        for s in seeds
+    ]).astype(dtype)
+
+
+def per_sample(fn, batch):
+    return np.stack([fn(x) for x in batch])
+
+
+@pytest.fixture(autouse=True)
+def _f32():
+    ex.config.update("enable_x64", False)
+    yield
+    ex.config.update("enable_x64", False)
+
+
+# ------------------------------------------------------------------ transforms
+@pytest.mark.parametrize("D,N", [(1, 16), (1, 25), (1, 200), (1, 256), (1, 81), (1, 30), (1, 38), (1, 2),
+                                 (2, 16), (2, 25), (2, 60), (2, 7), (3, 8), (3, 12), (3, 15)])
+def test_fft_ifft_vs_numpy(D, N):
+    rng = np.random.default_rng(D * 1000 + N)
+    u = rng.standard_normal((3, 2) + (N,) * D).astype(np.float32)
+    uh = host(ex.fft(dev(u), num_spatial_dims=D))
+    ref = ox.fft(u, num_spatial_dims=D)
+    assert uh.shape == ref.shape
+    assert rel(uh, ref) < 2e-6
+    back = host(ex.ifft(dev(ref), num_spatial_dims=D, num_points=N))
+    assert rel(back, u) < 2e-6
+    # non-Hermitian input: irfftn semantics (imaginary parts of DC / Nyquist along the last axis dropped)
+    z = (rng.standard_normal(ref.shape) + 1j * rng.standard_normal(ref.shape)).astype(np.complex64)
+    assert rel(host(ex.ifft(dev(z), num_spatial_dims=D, num_points=N)),
+               ox.ifft(z, num_spatial_dims=D, num_points=N)) < 2e-6
+
+
+def test_fft_numpy_in_numpy_out():
+    u = np.random.default_rng(0).standard_normal((1, 64)).astype(np.float32)
+    uh = ex.fft(u, num_spatial_dims=1)
+    assert isinstance(uh, np.ndarray) and rel(uh, np.fft.rfft(u)) < 2e-6
+
+
+def test_fft_f64():
+    ex.config.update("enable_x64", True)
+    u = np.random.default_rng(0).standard_normal((2, 1, 50, 50))
+    uh = host(ex.fft(dev(u), num_spatial_dims=2))
+    assert uh.dtype == np.complex128 and rel(uh, np.fft.rfftn(u, axes=(-2, -1))) < 1e-14
+
+
+# ------------------------------------------------------------------ nonlinear functions
+def _nl_cases():
+    cases = []
+    for D, N in [(1, 64), (1, 25), (2, 16), (2, 9), (3, 8)]:
+        for sc in (True, False):
+            for cons in (True, False):
+                cases.append(("conv", D, N, dict(single_channel=sc, conservative=cons, scale=1.3)))
+        cases.append(("gradnorm", D, N, dict(zero_mode_fix=True, scale=0.7)))
+        cases.append(("gradnorm", D, N, dict(zero_mode_fix=False, scale=1.0)))
+        cases.append(("poly", D, N, dict(coefficients=(0.5, -1.0, 2.0, 0.3))))
+        cases.append(("general", D, N, dict(scale_list=(0.4, -1.0, 0.6), zero_mode_fix=True)))
+    for N in (16, 15, 32):
+        cases.append(("vort", 2, N, dict(convection_scale=1.1)))
+        cases.append(("vortk", 2, N, dict(convection_scale=1.0, injection_mode=2, injection_scale=0.8)))
+    for N in (8, 12):
+        cases.append(("proj", 3, N, dict()))
+        cases.append(("projk", 3, N, dict(injection_mode=2, injection_scale=1.5)))
+    return cases
+
+
+@pytest.mark.parametrize("kind,D,N,kw", _nl_cases(), ids=lambda v: str(v) if not isinstance(v, dict) else "kw")
+def test_nonlinear_fun_vs_oracle(kind, D, N, kw):
+    L = 3.0
+    edop = ex.spectral.build_derivative_operator(D, L, N)
+    odop = ox.build_derivative_operator(D, L, N)
+    frac = 2 / 3
+    if kind == "conv":
+        C = 1 if kw["single_channel"] else D
+        f = ex.nonlin_fun.ConvectionNonlinearFun(D, N, derivative_operator=edop, dealiasing_fraction=frac, **kw)
+        o = ox.ConvectionNonlinearFun(D, N, derivative_operator=odop, dealiasing_fraction=frac, **kw)
+    elif kind == "gradnorm":
+        C = 1
+        f = ex.nonlin_fun.GradientNormNonlinearFun(D, N, derivative_operator=edop, dealiasing_fraction=frac, **kw)
+        o = ox.GradientNormNonlinearFun(D, N, derivative_operator=odop, dealiasing_fraction=frac, **kw)
+    elif kind == "poly":
+        C = 2
+        f = ex.nonlin_fun.PolynomialNonlinearFun(D, N, dealiasing_fraction=frac, **kw)
+        o = ox.PolynomialNonlinearFun(D, N, dealiasing_fraction=frac, **kw)
+    elif kind == "general":
+        C = 1
+        f = ex.nonlin_fun.GeneralNonlinearFun(D, N, derivative_operator=edop, dealiasing_fraction=frac, **kw)
+        o = ox.GeneralNonlinearFun(D, N, derivative_operator=odop, dealiasing_fraction=frac, **kw)
+    elif kind in ("vort", "vortk"):
+        C = 1
+        cls_e = ex.nonlin_fun.VorticityConvection2d if kind == "vort" else ex.nonlin_fun.VorticityConvection2dKolmogorov
+        cls_o = ox.VorticityConvection2d if kind == "vort" else ox.VorticityConvection2dKolmogorov
+        f = cls_e(D, N, derivative_operator=edop, dealiasing_fraction=frac, **kw)
+        o = cls_o(D, N, derivative_operator=odop, dealiasing_fraction=frac, **kw)
+    else:
+        C = 3
+        cls_e = ex.nonlin_fun.ProjectedConvection3d if kind == "proj" else ex.nonlin_fun.ProjectedConvection3dKolmogorov
+        cls_o = ox.ProjectedConvection3d if kind == "proj" else ox.ProjectedConvection3dKolmogorov
+        f = cls_e(D, N, derivative_operator=edop, dealiasing_fraction=frac, **kw)
+        o = cls_o(D, N, derivative_operator=odop, dealiasing_fraction=frac, **kw)
+    rng = np.random.default_rng(7)
+    u = rng.standard_normal((3, C) + (N,) * D).astype(np.float32)  # odd batch: exercises the unpaired row
+    uh = ox.fft(u, num_spatial_dims=D)
+    got = host(f(dev(uh)))
+    ref = per_sample(o, uh)
+    assert got.shape == ref.shape
+    assert rel(got, ref) < 5e-6, rel(got, ref)
+
+
+def test_convection_channel_mismatch_raises():
+    D, N = 2, 16
+    dop = ex.spectral.build_derivative_operator(D, 1.0, N)
+    f = ex.nonlin_fun.ConvectionNonlinearFun(D, N, derivative_operator=dop)
+    with pytest.raises(ValueError, match="channels"):
+        f(dev(np.zeros((3, N, N // 2 + 1), np.complex64)))
+
+
+# ------------------------------------------------------------------ single steps, 1-D
+@pytest.mark.parametrize("N", [256, 200, 100, 81, 64, 25])
+@pytest.mark.parametrize("order", [0, 1, 2, 3, 4])
+def test_burgers_1d_step(N, order):
+    L, dt = 2 * np.pi, 0.01
+    u0 = ic(1, N, range(5))
+    st = ex.stepper.Burgers(1, L, N, dt, order=order)
+    ost = ox.Burgers(1, L, N, dt, order=order)
+    got = host(ex.vmap(st)(dev(u0)))
+    ref = per_sample(ost, u0)
+    assert rel(got, ref) < F32_STEP
+    # single un-batched call + step_fourier
+    assert rel(host(st(dev(u0[0]))), ref[0]) < F32_STEP
+    uh = ox.fft(u0[0], num_spatial_dims=1)
+    assert rel(host(st.step_fourier(dev(uh))), ost.step_fourier(uh)) < F32_STEP
+
+
+@pytest.mark.parametrize("order", [1, 2, 3, 4])
+def test_burgers_1d_step_f64(order):
+    ex.config.update("enable_x64", True)
+    N, L, dt = 200, 2 * np.pi, 0.01
+    u0 = ic(1, N, range(3), dtype=np.float64)
+    st = ex.stepper.Burgers(1, L, N, dt, order=order)
+    ost = ox.Burgers(1, L, N, dt, order=order, dtype=np.float64)
+    got = host(ex.vmap(st)(dev(u0)))
+    assert got.dtype == np.float64
+    assert rel(got, per_sample(ost, u0)) < F64_STEP
+
+
+def _steppers_1d():
+    return [
+        ("KuramotoSivashinsky", dict(), (1, 60.0, 128, 0.1)),
+        ("KuramotoSivashinskyConservative", dict(), (1, 100.0, 200, 0.1)),
+        ("KuramotoSivashinskyConservative", dict(order=4), (1, 60.0, 96, 0.1)),
+        ("KortewegDeVries", dict(), (1, 20.0, 128, 0.001)),
+        ("KortewegDeVries", dict(order=4, conservative=True), (1, 20.0, 100, 0.001)),
+        ("Burgers", dict(conservative=True), (1, 1.0, 50, 0.01)),
+        ("Advection", dict(velocity=0.7), (1, 10.0, 100, 0.1)),
+        ("Diffusion", dict(diffusivity=0.1), (1, 10.0, 100, 0.1)),
+        ("AdvectionDiffusion", dict(), (1, 10.0, 81, 0.1)),
+        ("Dispersion", dict(dispersivity=0.3), (1, 10.0, 64, 0.01)),
+        ("HyperDiffusion", dict(), (1, 10.0, 64, 0.1)),
+    ]
+
+
+@pytest.mark.parametrize("name,kw,args", _steppers_1d(), ids=lambda v: v if isinstance(v, str) else "")
+def test_steppers_1d_step(name, kw, args):
+    D, L, N, dt = args
+    u0 = ic(1, N, range(4))
+    st = getattr(ex.stepper, name)(D, L, N, dt, **kw)
+    ost = getattr(ox, name)(D, L, N, dt, **kw)
+    assert rel(host(ex.vmap(st)(dev(u0))), per_sample(ost, u0)) < F32_STEP
+
+
+@pytest.mark.parametrize("name", ["FisherKPP", "AllenCahn", "SwiftHohenberg"])
+@pytest.mark.parametrize("D,N", [(1, 64), (2, 24)])
+def test_reaction_steppers(name, D, N):
+    L, dt = 10.0, 0.01
+    u0 = 0.5 * ic(D, N, range(3)) + 0.2
+    st = getattr(ex.stepper.reaction, name)(D, L, N, dt)
+    ost = getattr(ox, name)(D, L, N, dt)
+    assert rel(host(ex.vmap(st)(dev(u0))), per_sample(ost, u0)) < F32_STEP
+
+
+# ------------------------------------------------------------------ loops, 1-D
+def test_repeat_100_steps_burgers():
+    N, L, dt = 256, 2 * np.pi, 0.01
+    u0 = ic(1, N, range(6))
+    st = ex.stepper.Burgers(1, L, N, dt)
+    ost = ox.Burgers(1, L, N, dt)
+    ref = per_sample(ox.repeat(ost, 100), u0)
+    got = host(ex.vmap(ex.repeat(st, 100))(dev(u0)))
+    assert got.shape == u0.shape and rel(got, ref) < ROLLOUT_100
+    got_sc = host(ex.vmap(ex.repeat(st, 100, spectral_carry=True))(dev(u0)))
+    assert rel(got_sc, ref) < ROLLOUT_100
+
+
+def test_rollout_layouts_and_init():
+    N, L, dt, T = 100, 2 * np.pi, 0.01, 7
+    u0 = ic(1, N, range(5))
+    st = ex.stepper.Burgers(1, L, N, dt)
+    ost = ox.Burgers(1, L, N, dt)
+    ref = per_sample(ox.rollout(ost, T, include_init=True), u0)  # (B, T+1, C, N)
+    bt = host(ex.vmap(ex.rollout(st, T, include_init=True))(dev(u0)))
+    assert bt.shape == (5, T + 1, 1, N) and rel(bt, ref) < 1e-5
+    np.testing.assert_array_equal(bt[:, 0], u0)
+    tb = host(ex.rollout(ex.vmap(st), T, include_init=True)(dev(u0)))
+    assert tb.shape == (T + 1, 5, 1, N) and rel(tb, ref.transpose(1, 0, 2, 3)) < 1e-5
+    no_init = host(ex.vmap(ex.rollout(st, T))(dev(u0)))
+    assert no_init.shape == (5, T, 1, N) and rel(no_init, ref[:, 1:]) < 1e-5
+    single = host(ex.rollout(st, T, include_init=True)(dev(u0[0])))
+    assert single.shape == (T + 1, 1, N) and rel(single, ref[0]) < 1e-5
+    # repeat == last rollout entry; manual loop == rollout (tests/test_utils.py:49-81)
+    rep = host(ex.repeat(st, T)(dev(u0[0])))
+    assert rel(rep, ref[0, -1]) < 1e-5
+    u = dev(u0[0])
+    for _ in range(T):
+        u = st(u)
+    assert rel(host(u), ref[0, -1]) < 1e-5
+
+
+def test_rollout_numpy_host_buffers():
+    N, L, dt, T = 64, 2 * np.pi, 0.01, 4
+    u0 = ic(1, N, range(3))
+    st = ex.stepper.Burgers(1, L, N, dt)
+    out = ex.vmap(ex.rollout(st, T))(u0)
+    assert isinstance(out, np.ndarray)
+    assert rel(out, per_sample(ox.rollout(ox.Burgers(1, L, N, dt), T), u0)) < 1e-5
+
+
+def test_repeated_stepper():
+    N, L, dt, k = 81, 10.0, 0.01, 5
+    u0 = ic(1, N, range(3))
+    st = ex.stepper.Burgers(1, L, N, dt)
+    ost = ox.Burgers(1, L, N, dt)
+    rs = ex.RepeatedStepper(st, k)
+    assert rs.dt == pytest.approx(k * dt)
+    ref = per_sample(ox.RepeatedStepper(ost, k), u0)
+    assert rel(host(ex.vmap(rs)(dev(u0))), ref) < 1e-5
+    assert rel(host(rs(dev(u0[0]))), ref[0]) < 1e-5
+    # == repeat(stepper, k) up to the carry representation (tests/test_repeated_stepper.py:29)
+    assert rel(host(ex.vmap(ex.repeat(st, k))(dev(u0))), ref) < 1e-3
+    # rollout of a repeated stepper: every k-th state
+    trj = host(ex.vmap(ex.rollout(rs, 3))(dev(u0)))
+    oref = per_sample(ox.rollout(ox.RepeatedStepper(ost, k), 3), u0)
+    assert trj.shape == (3, 3, 1, N) and rel(trj, oref) < 1e-5
+    uh = ox.fft(u0[0], num_spatial_dims=1)
+    assert rel(host(rs.step_fourier(dev(uh))), ox.RepeatedStepper(ost, k).step_fourier(uh)) < 1e-5
+
+
+def test_ks_short_horizon_and_spectrum():
+    """Chaotic config c1: parity on a short horizon + time-averaged amplitude spectrum."""
+    L, N, dt = 100.0, 200, 0.1
+    u0 = ox.random_truncated_fourier_series(1, N, cutoff=5, seed=0)
+    st = ex.stepper.KuramotoSivashinskyConservative(1, L, N, dt)
+    ost = ox.KuramotoSivashinskyConservative(1, L, N, dt)
+    trj = host(ex.rollout(st, 500, include_init=True)(dev(u0)))
+    ref = ox.rollout(ost, 500, include_init=True)(u0)
+    assert trj.shape == (501, 1, 200)
+    assert rel(trj[:51], ref[:51]) < 1e-4
+    assert np.all(np.isfinite(trj))
+    sg = ox.get_spectrum_1d(trj[200:]).mean(axis=0)[0]
+    sr = ox.get_spectrum_1d(ref[200:]).mean(axis=0)[0]
+    band = slice(1, 40)
+    assert np.linalg.norm(sg[band] - sr[band]) / np.linalg.norm(sr[band]) < 0.35
+
+
+# ------------------------------------------------------------------ 2-D / 3-D steps
+def _steppers_nd():
+    return [
+        ("NavierStokesVorticity", dict(diffusivity=0.1), (2, 2 * np.pi, 60, 0.01), 1),
+        ("NavierStokesVorticity", dict(order=4, drag=-0.1), (2, 2 * np.pi, 32, 0.01), 1),
+        ("KolmogorovFlowVorticity", dict(), (2, 2 * np.pi, 64, 0.01), 1),
+        ("KolmogorovFlowVorticity", dict(order=3), (2, 2 * np.pi, 25, 0.01), 1),
+        ("KuramotoSivashinsky", dict(), (2, 30.0, 48, 0.1), 1),
+        ("Burgers", dict(), (2, 1.0, 32, 0.001), 2),
+        ("Burgers", dict(conservative=True), (2, 1.0, 30, 0.001), 2),
+        ("Burgers", dict(single_channel=True), (2, 1.0, 32, 0.001), 1),
+        ("Diffusion", dict(diffusivity=0.1), (2, 10.0, 40, 0.1), 1),
+        ("Advection", dict(), (3, 10.0, 12, 0.1), 1),
+        ("Burgers", dict(), (3, 1.0, 12, 0.001), 3),
+        ("Burgers", dict(conservative=True, order=3), (3, 1.0, 10, 0.001), 3),
+        ("KuramotoSivashinsky", dict(), (3, 30.0, 12, 0.1), 1),
+        ("NavierStokesVelocity", dict(), (3, 2 * np.pi, 16, 0.01), 3),
+        ("NavierStokesVelocity", dict(order=4, drag=-0.05), (3, 2 * np.pi, 12, 0.01), 3),
+        ("KolmogorovFlowVelocity", dict(), (3, 2 * np.pi, 16, 0.01), 3),
+        ("KolmogorovFlowVelocity", dict(order=1), (3, 2 * np.pi, 9, 0.01), 3),
+    ]
+
+
+@pytest.mark.parametrize("name,kw,args,C", _steppers_nd(), ids=lambda v: v if isinstance(v, str) else "")
+def test_steppers_nd_step(name, kw, args, C):
+    D, L, N, dt = args
+    u0 = ic(D, N, range(3), C=C)
+    st = getattr(ex.stepper, name)(D, L, N, dt, **kw)
+    ost = getattr(ox, name)(D, L, N, dt, **kw)
+    ref = per_sample(ost, u0)
+    assert rel(host(ex.vmap(st)(dev(u0))), ref) < F32_STEP
+    uh = ox.fft(u0[0], num_spatial_dims=D)
+    assert rel(host(st.step_fourier(dev(uh))), ost.step_fourier(uh)) < F32_STEP
+
+
+def test_taylor_green_2d_vs_analytic_and_oracle():
+    """validation/validate_taylor_green.ipynb: recorded f32 errors 1.85e-7 (1 step), 1.0e-5 (100 steps)."""
+    L, N, dt, nu = 2 * np.pi, 60, 0.01, 0.1
+    grid = ox.make_grid(2, L, N)
+
+    def tg(t):
+        return (2 * np.sin(grid[0:1]) * np.sin(grid[1:2]) * np.exp(-2 * nu * t)).astype(np.float32)
+
+    st = ex.stepper.NavierStokesVorticity(2, L, N, dt, diffusivity=nu)
+    ost = ox.NavierStokesVorticity(2, L, N, dt, diffusivity=nu)
+    assert rel(host(st(dev(tg(0.0)))), tg(dt)) < 1e-6
+    got = host(ex.repeat(st, 100)(dev(tg(0.0))))
+    assert rel(got, tg(100 * dt)) < 3e-5
+    assert rel(got, ox.repeat(ost, 100)(tg(0.0))) < ROLLOUT_100
+
+
+def test_nd_rollout_and_repeated():
+    D, L, N, dt = 2, 2 * np.pi, 32, 0.01
+    u0 = ic(D, N, range(3))
+    st = ex.stepper.KolmogorovFlowVorticity(D, L, N, dt)
+    ost = ox.KolmogorovFlowVorticity(D, L, N, dt)
+    ref = per_sample(ox.rollout(ost, 4, include_init=True), u0)
+    bt = host(ex.vmap(ex.rollout(st, 4, include_init=True))(dev(u0)))
+    assert bt.shape == ref.shape and rel(bt, ref) < 2e-5
+    tb = host(ex.rollout(ex.vmap(st), 4)(dev(u0)))
+    assert rel(tb, ref[:, 1:].transpose(1, 0, 2, 3, 4)) < 2e-5
+    rs = ex.RepeatedStepper(st, 3)
+    assert rel(host(ex.vmap(rs)(dev(u0))), per_sample(ox.RepeatedStepper(ost, 3), u0)) < 2e-5
+    sc = host(ex.vmap(ex.repeat(st, 6, spectral_carry=True))(dev(u0)))
+    assert rel(sc, per_sample(ox.repeat(ost, 6), u0)) < 5e-5
+
+
+def test_navier_stokes_3d_taylor_green_100_steps():
+    """Config c4 at reduced resolution: 3-D Taylor-Green, 100 steps, rel-L2 <= 1e-4 vs oracle."""
+    L, N, dt = 2 * np.pi, 24, 0.005
+    g = ox.make_grid(3, L, N)
+    u0 = np.stack([np.sin(g[0]) * np.cos(g[1]) * np.cos(g[2]),
+                   -np.cos(g[0]) * np.sin(g[1]) * np.cos(g[2]),
+                   np.zeros_like(g[0])]).astype(np.float32)
+    st = ex.stepper.NavierStokesVelocity(3, L, N, dt, diffusivity=0.01)
+    ost = ox.NavierStokesVelocity(3, L, N, dt, diffusivity=0.01)
+    got = host(ex.repeat(st, 100)(dev(u0)))
+    assert rel(got, ox.repeat(ost, 100)(u0)) < ROLLOUT_100
+
+
+def test_nd_f64():
+    ex.config.update("enable_x64", True)
+    D, L, N, dt = 2, 2 * np.pi, 30, 0.01
+    u0 = ic(D, N, range(2), dtype=np.float64)
+    st = ex.stepper.KolmogorovFlowVorticity(D, L, N, dt)
+    ost = ox.KolmogorovFlowVorticity(D, L, N, dt, dtype=np.float64)
+    assert rel(host(ex.vmap(st)(dev(u0))), per_sample(ost, u0)) < F64_STEP
+
+
+# ------------------------------------------------------------------ error paths
+def test_wrong_shape_raises():
+    st = ex.stepper.Burgers(1, 1.0, 32, 0.1)
+    with pytest.raises(ValueError, match="Expected shape"):
+        st(dev(np.zeros((2, 32), np.float32)))
+    with pytest.raises(ValueError, match="Expected shape"):
+        st(dev(np.zeros((1, 31), np.float32)))
+    with pytest.raises(ValueError):
+        ex.stepper.NavierStokesVorticity(3, 1.0, 16, 0.1)
+    with pytest.raises(ValueError):
+        ex.stepper.NavierStokesVelocity(2, 1.0, 16, 0.1)
+    with pytest.raises(NotImplementedError):
+        ex.stepper.Burgers(1, 1.0, 32, 0.1, order=5)
+
+
+def test_custom_nonlinear_fun_extension_api():
+    """docs/examples/creating_your_own_solvers_1d.ipynb: user subclasses of BaseNonlinearFun /
+    BaseStepper run through the standalone device transforms (unfused, still on the GPU)."""
+    class MyNl(ex.nonlin_fun.BaseNonlinearFun):
+        def __init__(self, D, N, *, derivative_operator, dealiasing_fraction=2 / 3):
+            super().__init__(D, N, dealiasing_fraction=dealiasing_fraction)
+            self.derivative_operator = derivative_operator
+
+        def __call__(self, u_hat):
+            u = self.ifft(u_hat)
+            return -0.5 * torch.as_tensor(self.derivative_operator, device="cuda") * self.fft(u**2)
+
+    class MyBurgers(ex.BaseStepper):
+        def __init__(self, D, L, N, dt):
+            super().__init__(D, L, N, dt, num_channels=1, order=2)
+
+        def _build_linear_operator(self, dop):
+            return 0.1 * ex.spectral.build_laplace_operator(dop)
+
+        def _build_nonlinear_fun(self, dop):
+            return MyNl(self.num_spatial_dims, self.num_points, derivative_operator=dop)
+
+    N, L, dt = 64, 2 * np.pi, 0.01
+    u0 = ic(1, N, [0])[0]
+    got = host(MyBurgers(1, L, N, dt)(dev(u0)))
+    ref = ox.Burgers(1, L, N, dt, conservative=True, single_channel=True)(u0)
+    assert rel(got, ref) < F32_STEP
+    trj = host(ex.rollout(MyBurgers(1, L, N, dt), 3)(dev(u0)))
+    assert trj.shape == (3, 1, N)

@@ -1,0 +1,201 @@
+"""
+CPU tests of the product's host side: constructor arithmetic (operators, masks, ETDRK
+coefficient tables) against the oracle, the C-ABI library (loads, exports every symbol of
+include/exb.h, fails loudly without a GPU), and API surface / error behaviour.
+"""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import exponax_b200 as ex
+from exponax_b200 import _native as nat
+from oracle import exponax_np as ox
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    import __graft_entry__ as g
+    g.build()
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "exb.h")).read()
+    declared = set(re.findall(r"\b(exb_[a-z_0-9]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    lib = ctypes.CDLL(nat.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in exb.h but not exported"
+    assert declared == set(nat.SYMBOLS), declared ^ set(nat.SYMBOLS)
+    assert b"sm_100a" in nat.lib().exb_version()
+
+
+def test_desc_struct_size_matches_header_guard():
+    d = nat.ExbDesc()
+    d.struct_size = 3  # wrong on purpose
+    h = ctypes.c_void_p()
+    rc = nat.lib().exb_plan_create(ctypes.byref(d), ctypes.byref(h))
+    assert rc == -1 and b"size mismatch" in nat.lib().exb_last_error()
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    st = ex.stepper.Burgers(1, 1.0, 32, 0.1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        st(np.zeros((1, 32), np.float32))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ex.fft(np.zeros((1, 32), np.float32))
+    # plan creation itself refuses without a device
+    with pytest.raises(nat.ExbError, match="no CUDA device"):
+        nat.Plan(D=1, N=8, C_=1, E=1, order=0, dtype=np.float32, L=1.0, kmax=-1, nl={"kind": nat.NL_ZERO},
+                 exp_term=np.ones(5, np.complex64))
+
+
+def test_product_does_not_import_oracle():
+    """the oracle is test infrastructure: nothing under exponax_b200/ may import or call it."""
+    pkg = os.path.join(ROOT, "exponax_b200")
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|oracle\.exponax_np|exponax_np", re.M)
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cc")):
+                assert not pat.search(open(os.path.join(dp, f)).read()), (dp, f)
+
+
+@pytest.mark.parametrize("D,N", [(1, 10), (1, 11), (2, 10), (2, 11), (3, 6)])
+def test_operator_builders_match_oracle(D, N):
+    L = 3.0
+    np.testing.assert_array_equal(ex.spectral.build_wavenumbers(D, N), ox.build_wavenumbers(D, N))
+    dop = ex.spectral.build_derivative_operator(D, L, N)
+    np.testing.assert_array_equal(dop, ox.build_derivative_operator(D, L, N))
+    for order in (0, 2, 4):
+        np.testing.assert_array_equal(ex.spectral.build_laplace_operator(dop, order=order),
+                                      ox.build_laplace_operator(dop, order=order))
+    for mode in ("norm_compensation", "reconstruction", "coef_extraction"):
+        np.testing.assert_array_equal(ex.spectral.build_scaling_array(D, N, mode=mode),
+                                      ox.build_scaling_array(D, N, mode=mode))
+    np.testing.assert_array_equal(ex.spectral.low_pass_filter_mask(D, N, cutoff=3),
+                                  ox.low_pass_filter_mask(D, N, cutoff=3))
+
+
+@pytest.mark.parametrize("N", [16, 25, 64, 96, 100, 200, 256, 512, 513, 2048])
+@pytest.mark.parametrize("frac", [2 / 3, 1 / 2, 0.9, 1.0])
+def test_kmax_equals_mask(N, frac):
+    """the kernels use `|k| <= kmax` instead of the mask array: both must select the same modes."""
+    nl = ex.nonlin_fun.PolynomialNonlinearFun(1, N, dealiasing_fraction=frac, coefficients=(0.0,))
+    k = np.arange(N // 2 + 1)
+    np.testing.assert_array_equal(nl.dealiasing_mask[0], k <= nl._kmax)
+    onl = ox.PolynomialNonlinearFun(1, N, dealiasing_fraction=frac, coefficients=(0.0,))
+    np.testing.assert_array_equal(nl.dealiasing_mask, onl.dealiasing_mask)
+
+
+def test_two_thirds_rule_cutoffs():
+    for N, kmax in [(200, 65), (256, 84), (512, 169), (2048, 681)]:
+        nl = ex.nonlin_fun.PolynomialNonlinearFun(1, N, dealiasing_fraction=2 / 3, coefficients=(0.0,))
+        assert nl._kmax == kmax
+
+
+def _stepper_pairs():
+    return [
+        ("Burgers", (1, 2 * np.pi, 64, 0.01), dict(order=2)),
+        ("Burgers", (2, 1.0, 16, 0.01), dict(order=4)),
+        ("KuramotoSivashinsky", (1, 60.0, 64, 0.1), dict(order=3)),
+        ("KuramotoSivashinskyConservative", (1, 100.0, 200, 0.1), dict()),
+        ("KortewegDeVries", (1, 20.0, 64, 0.001), dict(order=4)),
+        ("KortewegDeVries", (1, 20.0, 64, 0.001), dict(advect_over_diffuse=True, diffuse_over_diffuse=True)),
+        ("NavierStokesVorticity", (2, 2 * np.pi, 16, 0.01), dict()),
+        ("KolmogorovFlowVorticity", (2, 2 * np.pi, 16, 0.01), dict(order=1)),
+        ("NavierStokesVelocity", (3, 2 * np.pi, 8, 0.01), dict()),
+        ("KolmogorovFlowVelocity", (3, 2 * np.pi, 8, 0.01), dict()),
+        ("Advection", (2, 10.0, 16, 0.1), dict(velocity=np.array([0.1, 0.3]))),
+        ("Diffusion", (2, 10.0, 16, 0.1), dict(diffusivity=np.array([0.1, 0.3]))),
+        ("AdvectionDiffusion", (1, 10.0, 16, 0.1), dict()),
+        ("Dispersion", (1, 10.0, 16, 0.1), dict(advect_on_diffusion=True)),
+        ("HyperDiffusion", (2, 10.0, 16, 0.1), dict(diffuse_on_diffuse=True)),
+    ]
+
+
+@pytest.mark.parametrize("name,args,kw", _stepper_pairs(), ids=lambda v: v if isinstance(v, str) else "")
+@pytest.mark.parametrize("x64", [False, True])
+def test_ctor_tables_match_oracle(name, args, kw, x64):
+    ex.config.update("enable_x64", x64)
+    try:
+        st = getattr(ex.stepper, name)(*args, **kw)
+    finally:
+        ex.config.update("enable_x64", False)
+    ost = getattr(ox, name)(*args, dtype=np.float64 if x64 else np.float32, **kw)
+    a, b = st._integrator, ost._integrator
+    assert a._exp_term.dtype == (np.complex128 if x64 else np.complex64)
+    np.testing.assert_array_equal(a._exp_term, b._exp_term)
+    for nm in ("_half_exp_term", "_coef_1", "_coef_2", "_coef_3", "_coef_4", "_coef_5", "_coef_6"):
+        if hasattr(b, nm):
+            np.testing.assert_array_equal(getattr(a, nm), getattr(b, nm))
+            if nm.startswith("_coef"):
+                assert not np.iscomplexobj(getattr(a, nm))  # real even for complex L
+    assert st.num_channels == ost.num_channels and st.dx == ost.dx
+
+
+def test_reaction_ctor_tables():
+    for name in ("FisherKPP", "AllenCahn", "SwiftHohenberg"):
+        st = getattr(ex.stepper.reaction, name)(2, 10.0, 16, 0.01)
+        ost = getattr(ox, name)(2, 10.0, 16, 0.01)
+        np.testing.assert_array_equal(st._integrator._coef_2, ost._integrator._coef_2)
+        assert tuple(st._nonlinear_fun.coefficients) == tuple(ost._integrator._nonlinear_fun.coefficients)
+
+
+def test_guards_and_messages():
+    with pytest.raises(ValueError, match="Expected num_spatial_dims = 2"):
+        ex.stepper.NavierStokesVorticity(3, 1.0, 8, 0.1)
+    with pytest.raises(ValueError, match="Expected num_spatial_dims = 2"):
+        ex.stepper.KolmogorovFlowVorticity(1, 1.0, 8, 0.1)
+    with pytest.raises(ValueError, match="Expected num_spatial_dims = 3"):
+        ex.stepper.NavierStokesVelocity(2, 1.0, 8, 0.1)
+    with pytest.raises(ValueError, match="only supports 3 spatial dimensions"):
+        ex.nonlin_fun.ProjectedConvection3d(2, 8, derivative_operator=ex.spectral.build_derivative_operator(2, 1.0, 8))
+    with pytest.raises(ValueError, match="exactly 3 elements"):
+        ex.nonlin_fun.GeneralNonlinearFun(1, 8, derivative_operator=ex.spectral.build_derivative_operator(1, 1.0, 8),
+                                          dealiasing_fraction=2 / 3, scale_list=(1.0, 2.0))
+    with pytest.raises(NotImplementedError, match="Order 7"):
+        ex.stepper.Burgers(1, 1.0, 8, 0.1, order=7)
+    with pytest.raises(ValueError, match="Order must be even"):
+        ex.spectral.build_laplace_operator(ex.spectral.build_derivative_operator(1, 1.0, 8), order=3)
+    st = ex.stepper.Burgers(1, 1.0, 32, 0.1)
+    with pytest.raises(ValueError, match="Expected shape"):
+        st(np.zeros((2, 32), np.float32))
+
+    class Bad(ex.BaseStepper):
+        def _build_linear_operator(self, dop):
+            return np.zeros((2, 3), np.complex64)
+
+        def _build_nonlinear_fun(self, dop):
+            return ex.nonlin_fun.ZeroNonlinearFun(self.num_spatial_dims, self.num_points)
+
+    with pytest.raises(ValueError, match="Expected linear operator to have shape"):
+        Bad(1, 1.0, 8, 0.1, num_channels=1, order=0)
+
+
+def test_repeated_stepper_attributes():
+    st = ex.stepper.Burgers(1, 3.0, 30, 0.1)
+    rs = ex.RepeatedStepper(st, 4)
+    assert rs.dt == pytest.approx(0.4) and rs.num_points == 30 and rs.num_channels == 1
+    assert rs.dx == st.dx and rs.domain_extent == 3.0 and rs.num_spatial_dims == 1
+
+
+def test_rollout_generic_callable_cpu():
+    """rollout/repeat accept arbitrary callables (exponax/_utils.py:111-114): plain loop path."""
+    f = lambda u: 0.5 * u  # noqa: E731
+    u0 = np.ones((1, 4), np.float32)
+    trj = ex.rollout(f, 3, include_init=True)(u0)
+    assert trj.shape == (4, 1, 4) and np.allclose(trj[-1], 0.125)
+    assert np.allclose(ex.repeat(f, 3)(u0), 0.125)
+    g = lambda u, a: u + a  # noqa: E731
+    assert np.allclose(ex.rollout(g, 3, takes_aux=True)(u0, 1.0)[-1], 4.0)
+    aux = np.arange(3, dtype=np.float32)
+    assert np.allclose(ex.repeat(g, 3, takes_aux=True, constant_aux=False)(u0, aux), 1 + 0 + 1 + 2)
+    b = ex.vmap(ex.rollout(f, 2))(np.ones((5, 1, 4), np.float32))
+    assert b.shape == (5, 2, 1, 4)
