@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""
+bench.py -- ETDRK grid-point*steps/s of the exponax hot path on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c1] [--impl reference]
+
+A bench "step" = one pass of the hot path over one batch of synthetic input = ONE fused
+rollout call (`ex.vmap(ex.rollout(stepper, T))(u0)` == one `exb_rollout`) of `B` trajectories
+x `T` ETDRK steps.  Default workload = BASELINE.json configs[1] (c2): Burgers 1-D ETDRK2,
+N=256, B=16384 per GPU, T=1000, every step saved (16.8 GB trajectory per call).
+
+  value  : N^D * B * T * K / device-time, inputs resident in HBM, CUDA events, max over ranks
+  e2e    : same call with HOST buffers (pinned), H2D of u0 and D2H of the result inside the timed
+           region, through the public Python API
+  roofline / cpu_baseline / clocks / gpu_launches: see DESIGN.md "Measurement"
+
+Multi-GPU: one process per GPU (torchrun), the batch axis is sharded, no data-path collective
+(trajectories are independent) -> weak scaling: per-GPU batch fixed, value = all ranks' units /
+max-over-ranks time.
+
+`--impl reference` times the reference algorithm on the host cores: the NumPy/SciPy oracle
+port of exponax (JAX is not installable here), bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (stepper name, D, L, N, dt, kwargs, C, B per GPU, T steps per call, save mode)
+    "c1": dict(stepper="KuramotoSivashinskyConservative", D=1, L=100.0, N=200, dt=0.1, kw={}, C=1, B=1, T=500,
+               final_only=False, desc="KS-conservative 1-D N=200 L=100 dt=0.1, 500-step rollout, batch 1"),
+    "c2": dict(stepper="Burgers", D=1, L=2 * np.pi, N=256, dt=0.01, kw=dict(diffusivity=0.1), C=1, B=16384, T=1000,
+               final_only=False,
+               desc="Burgers 1-D ETDRK2 N=256, 16384 trajectories x 1000 steps per GPU, every step saved"),
+    "c3": dict(stepper="KolmogorovFlowVorticity", D=2, L=2 * np.pi, N=512, dt=0.01, kw=dict(diffusivity=0.001), C=1,
+               B=512, T=20, final_only=True,
+               desc="KolmogorovFlowVorticity 2-D 512x512 ETDRK2 2/3-dealiased, batch 512 per GPU, repeat"),
+    "c4": dict(stepper="NavierStokesVelocity", D=3, L=2 * np.pi, N=256, dt=0.005, kw=dict(diffusivity=0.01), C=3,
+               B=16, T=2, final_only=True,
+               desc="NavierStokesVelocity 3-D 256^3 Taylor-Green ETDRK2, batch 16 per GPU, repeat"),
+}
+
+
+def algorithmic_bytes_per_call(w, itemsize=4, spectral_carry=False):
+    """SURVEY section 8(d) / BASELINE.md section 3: ALGORITHMIC bytes per rollout call (per GPU)."""
+    N, D, C, B, T = w["N"], w["D"], w["C"], w["B"], w["T"]
+    F = itemsize * N**D
+    if D == 1:
+        # persistent kernel: read u0 once, write each saved snapshot once
+        saved = 1 if w["final_only"] else T
+        return B * C * F * (1 + saved)
+    # pass model per ETDRK2 step: stage = [2C + 2(D-1)(n_inv+n_fwd) + n_op] F, n_op = 0 / 2C
+    n_inv, n_fwd = {"KolmogorovFlowVorticity": (4, 1), "NavierStokesVelocity": (6, 3)}[w["stepper"]]
+    per_stage = 2 * C + 2 * (D - 1) * (n_inv + n_fwd)
+    step = (2 * per_stage + 2 * C) * F          # c3: 26 F, c4: 90 F
+    carry = 0 if spectral_carry else 4 * C * F  # physical carry: the step's own ifft + fft (+4 F per channel)
+    return B * T * (step + carry)
+
+
+def synth_ic(w, B, seed0=0):
+    """Synthetic `ex.ic`-style initial conditions (NumPy restatement, PCG64 seeds)."""
+    from oracle import exponax_np as ox  # input generator only (harness), never on the timed path
+    N, D, C = w["N"], w["D"], w["C"]
+    rng = np.random.default_rng(seed0)
+    if D == 1:
+        # truncated Fourier series, cutoff 5, max |u| = 1 (vectorised over the batch)
+        k = np.arange(1, 6)
+        x = np.arange(N) * (2 * np.pi / N)
+        a = rng.standard_normal((B, C, 5, 1)).astype(np.float32)
+        b = rng.standard_normal((B, C, 5, 1)).astype(np.float32)
+        u = (a * np.cos(k[:, None] * x) + b * np.sin(k[:, None] * x)).sum(axis=2)
+        u /= np.abs(u).max(axis=-1, keepdims=True)
+        return u.astype(np.float32)
+    if D == 2:
+        base = np.stack([ox.gaussian_random_field(2, N, powerlaw_exponent=3.5, seed=seed0 + i) for i in range(8)])
+        reps = (B + 7) // 8
+        amp = (1.0 + 0.01 * (np.arange(reps * 8, dtype=np.float32) % 16))[:B]
+        return (np.tile(base, (reps, 1, 1, 1))[:B] * amp[:, None, None, None]).astype(np.float32)
+    g = ox.make_grid(3, w["L"], N)
+    tg = np.stack([np.sin(g[0]) * np.cos(g[1]) * np.cos(g[2]), -np.cos(g[0]) * np.sin(g[1]) * np.cos(g[2]),
+                   np.zeros_like(g[0])]).astype(np.float32)
+    amp = 1.0 + 0.01 * (np.arange(B, dtype=np.float32) % 16)
+    return (tg[None] * amp[:, None, None, None, None]).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15 and len(r) >= 9] or \
+               [r for (_, r) in self.rows if len(r) >= 9]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = [float(r[1]) for r in rows]
+        reasons = set()
+        for r in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(rows[0][2]),
+                "power_w_max": max(float(r[3]) for r in rows), "samples": len(rows), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------ CPU reference
+def cpu_reference_run(w, steps, warmup, budget_s=20.0):
+    """Times the oracle port of the reference on the host cores: bounded sample of the workload."""
+    from oracle import exponax_np as ox
+    cores = os.cpu_count() or 1
+    ox.set_fft_workers(cores)
+    N, D = w["N"], w["D"]
+    Bs = {"c1": 1, "c2": 1024, "c3": 4, "c4": 1}[w["name"]]
+    Ts = {"c1": 500, "c2": 50, "c3": 5, "c4": 1}[w["name"]]
+    st = getattr(ox, w["stepper"])(D, w["L"], N, w["dt"], **w["kw"])
+    u0 = synth_ic(w, Bs)
+    # oracle classes broadcast over a batch axis placed between channel and space for C == 1
+    if w["C"] == 1:
+        x0 = np.ascontiguousarray(np.moveaxis(u0, 0, 1))  # (1, B, N..)
+        fn = ox.repeat(st.step, Ts)
+        run = lambda: fn(x0)  # noqa: E731
+    else:
+        fn = ox.repeat(st.step, Ts)
+        run = lambda: [fn(u) for u in u0]  # noqa: E731
+    for _ in range(max(1, min(warmup, 1))):
+        run()
+    times = []
+    t_start = time.perf_counter()
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        run()
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > budget_s and len(times) >= 1:
+            break
+    units = (N**D) * Bs * Ts
+    ms = 1e3 * sum(times) / len(times)
+    return dict(value=units / (ms * 1e-3), unit="grid-point*steps/s", cores=cores, kind="port",
+                sample=f"{w['stepper']} N={N}^{D} batch {Bs} x {Ts} steps (repeat), scipy.fft workers={cores}, "
+                       f"{len(times)} timed passes",
+                ms_per_step=ms, steps=len(times))
+
+
+# ------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="exb", choices=["exb", "reference"])
+    ap.add_argument("--batch", type=int, default=None, help="override per-GPU batch")
+    ap.add_argument("--T", type=int, default=None, help="override ETDRK steps per call")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--spectral-carry", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    w = dict(WORKLOADS[args.workload], name=args.workload)
+    if args.batch:
+        w["B"] = args.batch
+    if args.T:
+        w["T"] = args.T
+    args.warmup = max(args.warmup, 3) if args.impl == "exb" else args.warmup
+    N, D, C, B, T = w["N"], w["D"], w["C"], w["B"], w["T"]
+    config = {"workload": f"{args.workload}: {w['desc']}", "stepper": w["stepper"], "N": N, "D": D,
+              "batch_per_gpu": B, "etdrk_steps_per_call": T, "order": 2, "precision": "f32",
+              "parallelism": f"batch-shard x{args.gpus} (no collective)",
+              "save": "final state only (ex.repeat)" if w["final_only"] else "every step (ex.rollout)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = cpu_reference_run(w, args.steps, args.warmup, budget_s=120.0)
+        line = {"impl": "reference", "metric": "ETDRK grid-point*steps/s", "value": r["value"], "unit": r["unit"],
+                "n_gpus": args.gpus, "steps": r["steps"], "warmup": min(args.warmup, 1), "ms_per_step": r["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config,
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": r["value"], "unit": r["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "note": "NumPy/SciPy port of exponax (oracle/) on the host cores; JAX cannot be installed here"}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import exponax_b200 as ex
+    from exponax_b200 import _native as nat
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    stepper = getattr(ex.stepper, w["stepper"])(D, w["L"], N, w["dt"], **w["kw"])
+    u0_host = synth_ic(w, B, seed0=1000 * rank)
+    u0 = torch.as_tensor(u0_host, device="cuda")
+    if w["final_only"]:
+        fn = ex.vmap(ex.repeat(stepper, T, spectral_carry=args.spectral_carry))
+    else:
+        fn = ex.vmap(ex.rollout(stepper, T, spectral_carry=args.spectral_carry))
+    plan = stepper._plan()
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    out = None
+    for _ in range(args.warmup):
+        out = fn(u0)
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = plan.launch_count()
+    evs = []
+    barrier()
+    t_wall0 = time.time()
+    for _ in range(args.steps):
+        flush.zero_()  # evict L2 between timed iterations (outside the event pair)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn(u0)
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    t_wall1 = time.time()
+    launches = plan.launch_count() - launches0
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    tmax = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    total_ms = float(tmax.item())
+    units_per_call = (N**D) * B * T
+    value = units_per_call * world * args.steps / (total_ms * 1e-3)
+    ms_per_step = total_ms / args.steps
+    assert torch.isfinite(out).all(), "non-finite result"
+
+    # ---- roofline of the dominant kernel (per launch == per call for the 1-D persistent kernel;
+    #      for N-D the pass kernels of one call are taken together) ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    abytes = algorithmic_bytes_per_call(w, spectral_carry=args.spectral_carry)
+    achieved = abytes / (ms_per_step * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json (measured copy bandwidth)" if peaks else "fallback 6.65 TB/s",
+                "algorithmic_bytes_per_call": abytes, "kernel_launches_per_call": launches / args.steps}
+    if D == 1:
+        # the persistent 1-D kernel is FP32/shared-memory bound (AI ~ 40 FLOP/B): report the FLOP side too
+        nfft = 8 if not args.spectral_carry else 7  # real N-point transforms per ETDRK2 rollout step (Burgers)
+        flops = units_per_call / N * nfft * 2.5 * N * np.log2(N)
+        roofline["fp32_fft_tflops"] = flops / (ms_per_step * 1e-3) / 1e12
+        roofline["note"] = ("1-D persistent kernel: state resident in shared memory, HBM sees only snapshots; "
+                            "bound by FP32/shared-memory throughput, not HBM (SURVEY 8d)")
+
+    # ---- e2e through the public API with host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        pinned_in = torch.from_numpy(u0_host).pin_memory()
+        res_shape = tuple(out.shape)
+        pinned_out = torch.empty(res_shape, dtype=out.dtype, pin_memory=True)
+        nchunk = 8 if B >= 64 else 1
+        bounds = np.linspace(0, B, nchunk + 1).astype(int)
+        # N-D plans share one workspace: keep their chunks on one stream
+        streams = [torch.cuda.Stream() for _ in range(2 if D == 1 else 1)]
+
+        def e2e_call():
+            # chunked over the batch so the D2H of chunk i overlaps the compute of chunk i+1
+            for i in range(nchunk):
+                s = streams[i % len(streams)]
+                lo, hi = int(bounds[i]), int(bounds[i + 1])
+                with torch.cuda.stream(s):
+                    d = pinned_in[lo:hi].to("cuda", non_blocking=True)
+                    r = fn(d)
+                    pinned_out[lo:hi].copy_(r, non_blocking=True)
+            for s in streams:
+                s.synchronize()
+
+        e2e_call()
+        barrier()
+        t0 = time.perf_counter()
+        n_e2e = max(1, min(args.steps, 3))
+        for _ in range(n_e2e):
+            e2e_call()
+        barrier()
+        dt_e2e = time.perf_counter() - t0
+        te = torch.tensor([dt_e2e], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": units_per_call * world * n_e2e / float(te.item()), "unit": "grid-point*steps/s",
+               "h2d_bytes_per_step": int(u0_host.nbytes), "d2h_bytes_per_step": int(pinned_out.numel() * 4),
+               "calls": n_e2e, "note": "pinned host buffers, 8 batch chunks on 2 streams (copy/compute overlap)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if not args.no_cpu and world == 1:
+        r = cpu_reference_run(w, steps=3, warmup=1, budget_s=20.0)
+        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    line = {"metric": "ETDRK grid-point*steps/s", "value": value, "unit": "grid-point*steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(config, l2="256 MB flush between timed iterations; outputs >> L2"),
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "trajectory_steps_per_s": value / (N**D)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -434,3 +434,48 @@ def test_custom_nonlinear_fun_extension_api():
     assert rel(got, ref) < F32_STEP
     trj = host(ex.rollout(MyBurgers(1, L, N, dt), 3)(dev(u0)))
     assert trj.shape == (3, 1, N)
+
+
+# ------------------------------------------------------------------ BASELINE.json full sizes
+def test_full_size_c3_kolmogorov_512():
+    """Config c3 at full resolution (512^2), small batch: 5 steps vs the oracle."""
+    D, L, N, dt = 2, 2 * np.pi, 512, 0.01
+    u0 = np.stack([ox.gaussian_random_field(2, N, powerlaw_exponent=3.5, seed=s) for s in range(3)])
+    st = ex.stepper.KolmogorovFlowVorticity(D, L, N, dt, diffusivity=0.001)
+    ost = ox.KolmogorovFlowVorticity(D, L, N, dt, diffusivity=0.001)
+    got = host(ex.vmap(ex.repeat(st, 5))(dev(u0)))
+    ref = per_sample(ox.repeat(ost, 5), u0)
+    assert np.all(np.isfinite(got))
+    assert rel(got, ref) < 5e-5, rel(got, ref)
+
+
+def test_full_size_c2_burgers_256_1000_steps():
+    """Config c2: N=256, 1000 steps (non-chaotic, decaying): rel-L2 <= 1e-4 x 10 steps-of-100 budget."""
+    N, L, dt = 256, 2 * np.pi, 0.01
+    u0 = ic(1, N, range(4))
+    st = ex.stepper.Burgers(1, L, N, dt, diffusivity=0.1)
+    ost = ox.Burgers(1, L, N, dt, diffusivity=0.1)
+    trj = host(ex.vmap(ex.rollout(st, 1000))(dev(u0)))
+    ref = per_sample(ox.rollout(ost, 1000), u0)
+    assert rel(trj[:, 99], ref[:, 99]) < ROLLOUT_100
+    assert rel(trj[:, -1], ref[:, -1]) < 1e-3
+    # size-independent property: the decaying Burgers flow never gains energy
+    e = (trj.astype(np.float64) ** 2).sum(axis=(-1, -2))
+    assert np.all(np.diff(e, axis=1) <= 1e-6 * e[:, :-1])
+
+
+def test_full_size_c4_navier_stokes_128():
+    """Config c4 at 128^3 (256^3 oracle is too slow for the suite): one step vs the oracle."""
+    L, N, dt = 2 * np.pi, 128, 0.005
+    g = ox.make_grid(3, L, N)
+    u0 = np.stack([np.sin(g[0]) * np.cos(g[1]) * np.cos(g[2]),
+                   -np.cos(g[0]) * np.sin(g[1]) * np.cos(g[2]),
+                   np.zeros_like(g[0])]).astype(np.float32)
+    st = ex.stepper.NavierStokesVelocity(3, L, N, dt, diffusivity=0.01)
+    ost = ox.NavierStokesVelocity(3, L, N, dt, diffusivity=0.01)
+    got = host(ex.repeat(st, 2)(dev(u0)))
+    assert rel(got, ox.repeat(ost, 2)(u0)) < 2e-5
+    # divergence stays ~0 (Leray projection)
+    gh = ox.fft(got, num_spatial_dims=3)
+    div = np.sum(ox.build_derivative_operator(3, L, N) * gh, axis=0)
+    assert np.abs(div).max() / np.abs(gh).max() < 1e-4
