@@ -6,10 +6,12 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/exb.h"
 #include "exb_kernels_1d.cuh"
+#include "exb_fast1d.h"
 #include "exb_kernels_nd.cuh"
 
 using namespace exb;
@@ -287,6 +289,27 @@ template <class T> struct PlanImpl : exb_plan {
     return t;
   }
 
+  // ---- fast path: N = R*R, f32, one channel (exb_kernels_1d_fast.cuh) ----
+  bool fast_1d_ok() const {
+    if constexpr (std::is_same<T, float>::value) {
+      if (D != 1 || C != 1 || K.E != 1) return false;
+      if (getenv("EXB_DISABLE_FAST_1D")) return false;
+      return exb_fast1d_supported(N, P, K.order);
+    }
+    return false;
+  }
+  int launch_fast(cudaStream_t st, const K1dParams<T>& pt) {
+    if constexpr (std::is_same<T, float>::value) {
+      const char* err = nullptr;
+      int rc = N == 256 ? exb_launch_fast1d_r16(st, pt, nscr, max_smem, &err)
+                        : exb_launch_fast1d_r8(st, pt, nscr, max_smem, &err);
+      if (rc) return fail(rc, "%s", err ? err : "fast 1-D launch failed");
+      ++launches;
+      return EXB_OK;
+    }
+    return fail(EXB_EUNSUPPORTED, "fast 1-D path is f32 only");
+  }
+
   int launch_1d(cudaStream_t st, int op, long long batch, int ch, const void* in, void* out,
                 long long n_saved, int substeps, unsigned flags) {
     if (batch <= 0) return EXB_OK;
@@ -303,6 +326,7 @@ template <class T> struct PlanImpl : exb_plan {
     p.n_saved = n_saved;
     p.substeps = substeps;
     p.flags = flags;
+    if (op == OP1_ROLLOUT && fast_1d_ok()) return launch_fast(st, p);
     bool plain = (op == OP1_FFT || op == OP1_IFFT);
     p.nslots = plain ? ch : nslots_1d();
     size_t smem = plain ? (size_t)2 * ch * N * sizeof(cpx<T>) : smem_1d(ch, p.nslots);

@@ -1,0 +1,74 @@
+// Shared body of exb_fast1d_r{8,16}.cu: instantiations + launcher for one radix EXB_FAST_R.
+#include "exb_fast1d.h"
+#include "exb_kernels_1d_fast.cuh"
+
+using namespace exb;
+
+namespace {
+
+template <int R, class S, int NI, int NF>
+int launch_fast_t(cudaStream_t st, const K1dParams<float>& p, int nscr, int max_smem, const char** err) {
+  constexpr int NN = R * R, NNh = NN / 2 + 1;
+  const int warps = 4, groups = warps * (32 / R);
+  FastLayout lay;
+  int off = 0;
+  auto take = [&](int bytes) {
+    int o = off;
+    off += (bytes + 15) / 16 * 16;
+    return o;
+  };
+  lay.off_tw2 = take(R * R * 8);
+  lay.off_exp = take(NNh * 8);
+  lay.off_hexp = take(NNh * 8);
+  for (int i = 0; i < 6; ++i) lay.off_c[i] = take(NNh * 4);
+  lay.nstate = 1 + nscr;
+  lay.nhp = (NNh + 1) / 2 * 2;
+  lay.pair_bytes = (lay.nstate * 2 * lay.nhp + (R + 1) * R) * 8;
+  lay.off_pairs = take(0);
+  size_t smem = (size_t)off + (size_t)groups * lay.pair_bytes;
+  if ((long long)smem > max_smem) {
+    *err = "fast 1-D kernel: not enough shared memory";
+    return EXB_EUNSUPPORTED;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(k1d_fast_kernel<R, S, NI, NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    if (e != cudaSuccess) {
+      *err = cudaGetErrorString(e);
+      return EXB_ECUDA;
+    }
+    attr_set = true;
+  }
+  long long npairs = (p.batch + 1) / 2;
+  long long grid = (npairs + groups - 1) / groups;
+  k1d_fast_kernel<R, S, NI, NF><<<(unsigned)grid, warps * 32, smem, st>>>(p, lay);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    *err = cudaGetErrorString(e);
+    return EXB_ECUDA;
+  }
+  return EXB_OK;
+}
+
+template <int R>
+int launch_fast_r(cudaStream_t st, const K1dParams<float>& p, int nscr, int max_smem, const char** err) {
+  const NlParams<float>& P = p.P;
+  const int kind = p.K.order == 0 ? EXB_NL_POLYNOMIAL : P.kind;  // order 0 never evaluates N
+  switch (kind) {
+    case EXB_NL_CONVECTION:
+      if (P.conservative) return launch_fast_t<R, NlS<EXB_NL_CONVECTION, 3, 1, 1>, 1, 1>(st, p, nscr, max_smem, err);
+      return launch_fast_t<R, NlS<EXB_NL_CONVECTION, 0, 1, 1>, 2, 1>(st, p, nscr, max_smem, err);
+    case EXB_NL_GRADIENT_NORM:
+      return launch_fast_t<R, NlS<EXB_NL_GRADIENT_NORM, -1, 1, 1>, 1, 1>(st, p, nscr, max_smem, err);
+    case EXB_NL_POLYNOMIAL:
+    case EXB_NL_ZERO:
+      return launch_fast_t<R, NlS<EXB_NL_POLYNOMIAL, -1, 1, 1>, 1, 1>(st, p, nscr, max_smem, err);
+    case EXB_NL_GENERAL:
+      return launch_fast_t<R, NlS<EXB_NL_GENERAL, -1, 1, 1>, 2, 2>(st, p, nscr, max_smem, err);
+    default:
+      *err = "fast 1-D kernel: unsupported nonlinear function";
+      return EXB_EUNSUPPORTED;
+  }
+}
+
+}  // namespace

@@ -1,0 +1,432 @@
+// Fast 1-D persistent rollout kernel for N = R*R (R = 16 -> N = 256, R = 8 -> N = 64), f32, C = 1.
+//
+// Work decomposition (B200: 148 SMs, 64K regs, 227 KB smem / SM):
+//   * a PAIR of trajectories shares every complex FFT (two-for-one: z = x1 + i*x2);
+//   * a pair is owned by R threads (a half-warp for N = 256) for the whole rollout: every
+//     synchronisation is a __syncwarp, there is no __syncthreads after the table load;
+//   * each thread keeps R points of the line in registers; an N-point FFT is two in-register
+//     radix-R passes with ONE shared-memory exchange in between (padded, conflict-free);
+//   * the pointwise nonlinearity happens in registers between the inverse and forward
+//     transforms (the output mapping of the inverse FFT is the input mapping of the forward);
+//   * spectral state, ETDRK stage buffers and coefficient tables live in shared memory; HBM
+//     sees the initial condition once and the saved snapshots;
+//   * the nonlinear function is a compile-time descriptor S (NlS<...>): no per-element branching.
+// Reference semantics identical to k1d_kernel (exb_kernels_1d.cuh); parity is tested against
+// the same oracle.
+#pragma once
+#include "exb_kernels_1d.cuh"
+
+namespace exb {
+
+struct FastLayout {
+  int off_tw2;       // [R][R] inter-pass twiddles w_N^(j*r), forward sign
+  int off_exp;       // cpx[Nh]
+  int off_hexp;      // cpx[Nh]
+  int off_c[6];      // float[Nh] each
+  int off_pairs;     // start of per-pair storage
+  int pair_bytes;    // bytes per pair
+  int nstate;        // spectral state arrays per pair (1 + scratch)
+  int nhp;           // padded Nh (complex elements) per trajectory
+};
+
+// ---- in-register DFTs; output position p holds X[xidx<R>(p)] --------------------------------
+template <int R> __host__ __device__ constexpr int xidx(int p) { return R == 16 ? 4 * (p & 3) + (p >> 2) : p; }
+
+template <int DIR> __device__ __forceinline__ void dft16_reg(cpx<float>* v) {
+  // n = n1 + 4*n2, k = 4*k1 + k2 :  w16^(nk) = w4^(n1 k1) * w16^(n1 k2) * w4^(n2 k2)
+  const float c = 0.92387953251128675613f, s = 0.38268343236508977173f, h = 0.70710678118654752440f;
+#pragma unroll
+  for (int n1 = 0; n1 < 4; ++n1) {
+    cpx<float> t[4] = {v[n1], v[n1 + 4], v[n1 + 8], v[n1 + 12]};
+    dft4<float, DIR>(t);
+    v[n1] = t[0];
+    v[n1 + 4] = t[1];
+    v[n1 + 8] = t[2];
+    v[n1 + 12] = t[3];
+  }
+  // twiddles w16^(n1*k2) on v[n1 + 4*k2]; forward twiddle = (wr, -wi)
+#define EXB_MULW(a, wr, wi)                                                            \
+  a = DIR < 0 ? cpx<float>(a.x * (wr) + a.y * (wi), a.y * (wr) - a.x * (wi))           \
+              : cpx<float>(a.x * (wr) - a.y * (wi), a.y * (wr) + a.x * (wi))
+  EXB_MULW(v[1 + 4], c, s);     // w^1
+  EXB_MULW(v[2 + 4], h, h);     // w^2
+  EXB_MULW(v[3 + 4], s, c);     // w^3
+  EXB_MULW(v[1 + 8], h, h);     // w^2
+  v[2 + 8] = rot90<float, DIR>(v[2 + 8]);  // w^4 = -i
+  EXB_MULW(v[3 + 8], -h, h);    // w^6
+  EXB_MULW(v[1 + 12], s, c);    // w^3
+  EXB_MULW(v[2 + 12], -h, h);   // w^6
+  EXB_MULW(v[3 + 12], -c, -s);  // w^9
+#undef EXB_MULW
+#pragma unroll
+  for (int k2 = 0; k2 < 4; ++k2) dft4<float, DIR>(v + 4 * k2);  // v[4*k2 + k1] = X[4*k1 + k2]
+}
+
+template <int R, int DIR> __device__ __forceinline__ void dft_reg(cpx<float>* v) {
+  if (R == 16) dft16_reg<DIR>(v);
+  if (R == 8) dft8<float, DIR>(v);
+}
+
+// N = R*R point FFT of the line held as v[r] = x[j + R*r] by the R threads j of a group.
+// On return v[r] = X[j + R*r].  xb: per-pair exchange buffer ((R+1)*R complex, padded).
+template <int R, int DIR>
+__device__ __forceinline__ void fft_reg(cpx<float> (&v)[R], cpx<float>* xb, int j, const cpx<float>* tw2) {
+  dft_reg<R, DIR>(v);
+  __syncwarp();
+#pragma unroll
+  for (int p = 0; p < R; ++p) xb[(R + 1) * j + xidx<R>(p)] = v[p];  // pad(R*j + X-index)
+  __syncwarp();
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    cpx<float> t = xb[j + (R + 1) * r];                             // pad(j + R*r)
+    if (r > 0) t = t * twd<float, DIR>(tw2[r * R + j]);
+    v[r] = t;
+  }
+  dft_reg<R, DIR>(v);
+  if (R == 16) {
+    cpx<float> o[R];
+#pragma unroll
+    for (int p = 0; p < R; ++p) o[xidx<R>(p)] = v[p];
+#pragma unroll
+    for (int p = 0; p < R; ++p) v[p] = o[p];
+  }
+}
+
+template <int R, class S, int NINV, int NFWD> struct Fast1d {
+  static constexpr int N = R * R;
+  static constexpr int Nh = N / 2 + 1;
+  static constexpr int NOWN = R / 2 + 1;  // modes owned per thread: k = j + R*r (r < R/2) [+ N/2 for j == 0]
+
+  const K1dParams<float>& p;
+  const FastLayout& lay;
+  const cpx<float>* tw2;
+  cpx<float>* st;   // pair state base: [array][traj][nhp]
+  cpx<float>* xb;   // exchange buffer
+  int j;            // thread index within the pair group
+  const cpx<float>* sE;
+  const cpx<float>* sEh;
+  const float* sc[6];
+
+  __device__ Fast1d(const K1dParams<float>& p_, const FastLayout& l_) : p(p_), lay(l_) {}
+
+  __device__ __forceinline__ cpx<float>* state(int a) const { return st + (size_t)a * 2 * lay.nhp; }
+
+  // packed line element n from the half-complex fields F1, F2 of the two trajectories
+  template <int KINDN>  // 0: k = n < N/2 (direct), 1: DC or Nyquist, 2: upper (conjugate of mode N - n)
+  static __device__ __forceinline__ cpx<float> pack(cpx<float> F1, cpx<float> F2) {
+    if (KINDN == 1) return cpx<float>(F1.x, F2.x);                 // irfft drops these imaginary parts
+    if (KINDN == 0) return cpx<float>(F1.x - F2.y, F1.y + F2.x);   // F1 + i F2
+    return cpx<float>(F1.x + F2.y, F2.x - F1.y);                   // conj(F1) + i conj(F2)
+  }
+
+  // Build the packed inverse lines from spectral state `src`.  NLF: apply the nonlinear
+  // function's prologue (mask, i*k, ...); otherwise the plain state (output transform).
+  template <int NL, bool NLF>
+  __device__ __forceinline__ void build_lines(const cpx<float>* src, cpx<float> (&z)[NL][R]) const {
+    const NlParams<float>& P = p.P;
+    auto elem = [&](int r, int k, int kindn) {
+      cpx<float> u1[EXB_MAXC], u2[EXB_MAXC];
+      u1[0] = src[k];
+      u2[0] = src[lay.nhp + k];
+      u1[1] = u1[2] = u2[1] = u2[2] = cpx<float>(0.f, 0.f);
+      ModeK<float> m = make_mode<float, S>(P, k, 0, 0);
+#pragma unroll
+      for (int f = 0; f < NL; ++f) {
+        cpx<float> F1 = NLF ? nl_inv_field<float, S>(P, f, u1, m) : u1[0];
+        cpx<float> F2 = NLF ? nl_inv_field<float, S>(P, f, u2, m) : u2[0];
+        z[f][r] = kindn == 0 ? pack<0>(F1, F2) : (kindn == 1 ? pack<1>(F1, F2) : pack<2>(F1, F2));
+      }
+    };
+    // r = 0: n = j (DC for j == 0)
+    elem(0, j, j == 0 ? 1 : 0);
+#pragma unroll
+    for (int r = 1; r < R / 2; ++r) elem(r, j + R * r, 0);
+    // r = R/2: n = N/2 + j: Nyquist for j == 0, otherwise the conjugate of mode N/2 - j
+    elem(R / 2, j == 0 ? N / 2 : N / 2 - j, j == 0 ? 1 : 2);
+#pragma unroll
+    for (int r = R / 2 + 1; r < R; ++r) elem(r, N - (j + R * r), 2);
+  }
+
+  // Two-for-one split of a forward-transformed line held in registers: for every owned mode slot
+  // (k = j + R*slot, slot < R/2; slot R/2 = Nyquist, valid for j == 0 only) X1, X2.
+  __device__ __forceinline__ void unpack_owned(const cpx<float> (&v)[R], cpx<float> (&X1)[NOWN],
+                                               cpx<float> (&X2)[NOWN]) const {
+    __syncwarp();
+#pragma unroll
+    for (int r = R / 2; r < R; ++r) xb[j + (R + 1) * r] = v[r];  // upper half: partners of the owned modes
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < R / 2; ++r) {
+      // partner of k = j + R*r is n' = N - k = (R - j) + R*(R - 1 - r)  (j > 0);  N - R*r = R*(R - r) (j == 0)
+      const int pidx = (j == 0) ? (R + 1) * (R - r) : (R - j) + (R + 1) * (R - 1 - r);
+      cpx<float> zk = v[r];
+      cpx<float> zp = (r == 0 && j == 0) ? zk : xb[pidx];
+      X1[r] = cpx<float>(0.5f * (zk.x + zp.x), 0.5f * (zk.y - zp.y));
+      X2[r] = cpx<float>(0.5f * (zk.y + zp.y), -0.5f * (zk.x - zp.x));
+    }
+    X1[R / 2] = cpx<float>(v[R / 2].x, 0.f);  // Nyquist (meaningful for j == 0)
+    X2[R / 2] = cpx<float>(v[R / 2].y, 0.f);
+  }
+
+  // N(src) -> per owned mode, both trajectories
+  __device__ __forceinline__ void eval_nl(const cpx<float>* src, cpx<float> (&n1)[NOWN], cpx<float> (&n2)[NOWN]) const {
+    const NlParams<float>& P = p.P;
+    cpx<float> w[NFWD][R];
+    {
+      cpx<float> z[NINV][R];
+      build_lines<NINV, true>(src, z);
+#pragma unroll
+      for (int f = 0; f < NINV; ++f) fft_reg<R, +1>(z[f], xb, j, tw2);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        float i1[NINV], i2[NINV], o1[NFWD], o2[NFWD];
+#pragma unroll
+        for (int f = 0; f < NINV; ++f) {
+          i1[f] = z[f][r].x * P.inv_norm;
+          i2[f] = z[f][r].y * P.inv_norm;
+        }
+        nl_pointwise<float, S>(P, i1, o1);
+        nl_pointwise<float, S>(P, i2, o2);
+#pragma unroll
+        for (int g = 0; g < NFWD; ++g) w[g][r] = cpx<float>(o1[g], o2[g]);
+      }
+    }
+    cpx<float> W1[NFWD][NOWN], W2[NFWD][NOWN];
+#pragma unroll
+    for (int g = 0; g < NFWD; ++g) {
+      fft_reg<R, -1>(w[g], xb, j, tw2);
+      unpack_owned(w[g], W1[g], W2[g]);
+    }
+#pragma unroll
+    for (int sl = 0; sl < NOWN; ++sl) {
+      const int k = sl < R / 2 ? j + R * sl : N / 2;
+      ModeK<float> m = make_mode<float, S>(P, k, 0, 0);
+      cpx<float> wa[NFWD], wb[NFWD], a[EXB_MAXC], b[EXB_MAXC];
+#pragma unroll
+      for (int g = 0; g < NFWD; ++g) {
+        wa[g] = W1[g][sl];
+        wb[g] = W2[g][sl];
+      }
+      nl_from_fwd<float, S>(P, wa, m, a);
+      nl_from_fwd<float, S>(P, wb, m, b);
+      n1[sl] = a[0];
+      n2[sl] = b[0];
+    }
+  }
+
+  // one ETDRK step on the shared-memory state (array 0); stage formulas: exponax/etdrk/_etdrk_{0..4}.py
+  __device__ __forceinline__ void etdrk_step(int order) {
+    cpx<float>* U = state(0);
+    const int nhp = lay.nhp;
+    if (order == 0) {
+#pragma unroll
+      for (int sl = 0; sl < NOWN; ++sl) {
+        const int k = sl < R / 2 ? j + R * sl : N / 2;
+        if (sl < R / 2 || j == 0) {
+          cpx<float> e = sE[k];
+          U[k] = e * U[k];
+          U[nhp + k] = e * U[nhp + k];
+        }
+      }
+      __syncwarp();
+      return;
+    }
+    for (int s = 0; s < order; ++s) {
+      const int si = etdrk_stage_input(order, s);
+      const cpx<float>* src = si < 0 ? U : state(1 + si);
+      cpx<float> n1[NOWN], n2[NOWN];
+      eval_nl(src, n1, n2);
+      cpx<float>* S0 = state(lay.nstate > 1 ? 1 : 0);
+      cpx<float>* S1 = state(lay.nstate > 2 ? 2 : 0);
+      cpx<float>* S2 = state(lay.nstate > 3 ? 3 : 0);
+      cpx<float>* S3 = state(lay.nstate > 4 ? 4 : 0);
+#pragma unroll
+      for (int sl = 0; sl < NOWN; ++sl) {
+        const int k = sl < R / 2 ? j + R * sl : N / 2;
+        if (sl < R / 2 || j == 0) {
+#pragma unroll
+          for (int tr = 0; tr < 2; ++tr) {
+            const int o = tr * nhp + k;
+            const cpx<float> n = tr == 0 ? n1[sl] : n2[sl];
+            if (order == 1) {
+              U[o] = sE[k] * U[o] + sc[0][k] * n;
+            } else if (order == 2) {
+              if (s == 0) {
+                S0[o] = sE[k] * U[o] + sc[0][k] * n;
+                S1[o] = n;
+              } else {
+                U[o] = S0[o] + sc[1][k] * (n - S1[o]);
+              }
+            } else if (order == 3) {
+              if (s == 0) {
+                S0[o] = sEh[k] * U[o] + sc[0][k] * n;
+                S1[o] = n;
+              } else if (s == 1) {
+                S0[o] = sE[k] * U[o] + sc[1][k] * (2.f * n - S1[o]);
+                S2[o] = n;
+              } else {
+                U[o] = sE[k] * U[o] + sc[2][k] * S1[o] + sc[3][k] * S2[o] + sc[4][k] * n;
+              }
+            } else {
+              if (s == 0) {
+                S0[o] = sEh[k] * U[o] + sc[0][k] * n;
+                S1[o] = n;
+              } else if (s == 1) {
+                S2[o] = sEh[k] * U[o] + sc[1][k] * n;
+                S3[o] = n;
+              } else if (s == 2) {
+                S2[o] = sEh[k] * S0[o] + sc[2][k] * (2.f * n - S1[o]);
+                S3[o] = S3[o] + n;
+              } else {
+                U[o] = sE[k] * U[o] + sc[3][k] * S1[o] + sc[4][k] * (2.f * S3[o]) + sc[5][k] * n;
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+};
+
+template <int R, class S, int NINV, int NFWD>
+__global__ void __launch_bounds__(128, 4) k1d_fast_kernel(const K1dParams<float> p, const FastLayout lay) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int N = R * R, Nh = N / 2 + 1;
+  constexpr int GROUPS_PER_WARP = 32 / R;
+  using F1 = Fast1d<R, S, NINV, NFWD>;
+  constexpr int NOWN = F1::NOWN;
+  // ---- cooperative load of the tables ----
+  {
+    cpx<float>* tw2 = (cpx<float>*)(smem_raw + lay.off_tw2);
+    for (int q = threadIdx.x; q < R * R; q += blockDim.x) {
+      int r = q / R, jj = q - r * R;
+      tw2[q] = p.tw[(r * jj) % N];
+    }
+    cpx<float>* e = (cpx<float>*)(smem_raw + lay.off_exp);
+    cpx<float>* eh = (cpx<float>*)(smem_raw + lay.off_hexp);
+    for (int q = threadIdx.x; q < Nh; q += blockDim.x) {
+      e[q] = p.K.exp_term[q];
+      if (p.K.half_exp) eh[q] = p.K.half_exp[q];
+      for (int i = 0; i < 6; ++i)
+        if (p.K.c[i]) ((float*)(smem_raw + lay.off_c[i]))[q] = p.K.c[i][q];
+    }
+  }
+  __syncthreads();
+
+  F1 F(p, lay);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int group = (blockIdx.x * (blockDim.x >> 5) + warp) * GROUPS_PER_WARP + lane / R;
+  const int local_group = warp * GROUPS_PER_WARP + lane / R;
+  const int j = lane % R;
+  F.j = j;
+  F.tw2 = (const cpx<float>*)(smem_raw + lay.off_tw2);
+  unsigned char* pb = smem_raw + lay.off_pairs + (size_t)local_group * lay.pair_bytes;
+  F.st = (cpx<float>*)pb;
+  F.xb = (cpx<float>*)(pb + (size_t)lay.nstate * 2 * lay.nhp * sizeof(cpx<float>));
+  F.sE = (const cpx<float>*)(smem_raw + lay.off_exp);
+  F.sEh = (const cpx<float>*)(smem_raw + lay.off_hexp);
+  for (int i = 0; i < 6; ++i) F.sc[i] = (const float*)(smem_raw + lay.off_c[i]);
+  const int order = p.K.order;
+
+  const long long t1 = 2ll * group, t2 = t1 + 1;
+  const bool act1 = t1 < p.batch, act2 = t2 < p.batch;
+  const bool include_init = (p.flags & EXB_ROLLOUT_INCLUDE_INIT) != 0;
+  const bool layout_tb = (p.flags & EXB_ROLLOUT_LAYOUT_TB) != 0;
+  const bool final_only = (p.flags & EXB_ROLLOUT_FINAL_ONLY) != 0;
+  const bool spectral_carry = (p.flags & EXB_ROLLOUT_SPECTRAL_CARRY) != 0;
+  const long long Tn = final_only ? 1 : p.n_saved + (include_init ? 1 : 0);
+  float* out = (float*)p.out;
+  // output pointers of slot 0 and the slot stride (elements)
+  float* o1 = nullptr;
+  float* o2 = nullptr;
+  size_t slot_stride = 0;
+  if (final_only) {
+    o1 = out + (size_t)t1 * N;
+    o2 = out + (size_t)t2 * N;
+  } else if (layout_tb) {
+    o1 = out + (size_t)t1 * N;
+    o2 = out + (size_t)t2 * N;
+    slot_stride = (size_t)p.batch * N;
+  } else {
+    o1 = out + (size_t)t1 * Tn * N;
+    o2 = out + (size_t)t2 * Tn * N;
+    slot_stride = N;
+  }
+  o1 += j;
+  o2 += j;
+  auto store_phys = [&](const cpx<float> (&v)[R], long long slot, float scale) {
+    float* a = o1 + (size_t)slot * slot_stride;
+    float* b = o2 + (size_t)slot * slot_stride;
+    if (act1) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) a[R * r] = v[r].x * scale;
+    }
+    if (act2) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) b[R * r] = v[r].y * scale;
+    }
+  };
+
+  cpx<float>* U = F.state(0);
+  auto to_state = [&](cpx<float> (&line)[R]) {
+    fft_reg<R, -1>(line, F.xb, j, F.tw2);
+    cpx<float> X1[NOWN], X2[NOWN];
+    F.unpack_owned(line, X1, X2);
+#pragma unroll
+    for (int sl = 0; sl < R / 2; ++sl) {
+      U[j + R * sl] = X1[sl];
+      U[lay.nhp + j + R * sl] = X2[sl];
+    }
+    if (j == 0) {
+      U[N / 2] = X1[R / 2];
+      U[lay.nhp + N / 2] = X2[R / 2];
+    }
+    __syncwarp();
+  };
+
+  // ---- u0 -> spectral state ----
+  {
+    cpx<float> v[R];
+    const float* in = (const float*)p.in;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float a = act1 ? in[(size_t)t1 * N + j + R * r] : 0.f;
+      float b = act2 ? in[(size_t)t2 * N + j + R * r] : 0.f;
+      v[r] = cpx<float>(a, b);
+    }
+    if (include_init && !final_only) store_phys(v, 0, 1.0f);
+    to_state(v);
+  }
+
+  const float invN = p.P.inv_norm;
+  for (long long s = 0; s < p.n_saved; ++s) {
+    for (int sub = 0; sub < p.substeps; ++sub) F.etdrk_step(order);
+    const bool last = (s == p.n_saved - 1);
+    const bool store = !final_only || last;
+    if (store || !spectral_carry) {
+      cpx<float> z[1][R];
+      F.template build_lines<1, false>(U, z);
+      fft_reg<R, +1>(z[0], F.xb, j, F.tw2);
+      if (store) store_phys(z[0], final_only ? 0 : s + (include_init ? 1 : 0), invN);
+      if (last) break;
+      if (!spectral_carry) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) z[0][r] = cpx<float>(z[0][r].x * invN, z[0][r].y * invN);
+        to_state(z[0]);
+        continue;
+      }
+    }
+    if (last) break;
+    // spectral carry: the reference's irfft -> rfft round trip == Hermitian projection
+    if (j == 0) {
+      U[0].y = 0.f;
+      U[N / 2].y = 0.f;
+      U[lay.nhp].y = 0.f;
+      U[lay.nhp + N / 2].y = 0.f;
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace exb

@@ -7,6 +7,20 @@
 
 namespace exb {
 
+// Compile-time description of the nonlinear function.  Members < 0 (or 0 for D / C) mean "read it
+// from NlParams at run time" (generic kernels); the fast kernels pass fully static descriptors so
+// that every `switch (kind)` below folds away.
+//   VAR (convection only): bit 0 = conservative, bit 1 = single_channel
+template <int KIND, int VAR, int DD, int CC> struct NlS {
+  static constexpr int kind = KIND, var = VAR, D = DD, C = CC;
+};
+using NlDyn = NlS<-1, -1, 0, 0>;
+#define EXB_S_KIND (S::kind >= 0 ? S::kind : P.kind)
+#define EXB_S_D (S::D > 0 ? S::D : P.D)
+#define EXB_S_C (S::C > 0 ? S::C : P.C)
+#define EXB_S_CONS (S::var >= 0 ? (S::var & 1) : P.conservative)
+#define EXB_S_SINGLE (S::var >= 0 ? ((S::var >> 1) & 1) : P.single_channel)
+
 // wavenumber data of one spectral mode
 template <class T> struct ModeK {
   T kd[3];     // (2*pi/L) * k_d ; derivative operator is i*kd[d]   (_spectral.py:86-115)
@@ -16,15 +30,16 @@ template <class T> struct ModeK {
 };
 
 // idx[d]: array index along spatial axis d (last axis: 0..N/2 directly)
-template <class T>
+template <class T, class S = NlDyn>
 __device__ __forceinline__ ModeK<T> make_mode(const NlParams<T>& P, int i0, int i1, int i2) {
   ModeK<T> m;
   int idx[3] = {i0, i1, i2};
   bool keep = true, inj = P.has_inj != 0, dc = true;
+  const int D = EXB_S_D;
 #pragma unroll
   for (int d = 0; d < 3; ++d) {
-    if (d < P.D) {
-      int k = (d == P.D - 1) ? idx[d] : wavenumber_of(idx[d], P.N);
+    if (d < D) {
+      int k = (d == D - 1) ? idx[d] : wavenumber_of(idx[d], P.N);
       m.kd[d] = P.dscale * (T)k;
       int ak = k < 0 ? -k : k;
       if (P.kmax >= 0 && ak > P.kmax) keep = false;
@@ -50,16 +65,16 @@ template <class T> __device__ __forceinline__ cpx<T> pick3c(const cpx<T>* a, int
 // ---- inverse-transform input field f of the nonlinear function, at one mode ----------------
 // uh[c]: stage input, channel c (c < C <= 3).  Pre-dealiasing (nonlin_fun/_base.py:117-137)
 // is applied here: modes outside the mask yield 0.
-template <class T>
+template <class T, class S = NlDyn>
 __device__ __forceinline__ cpx<T> nl_inv_field(const NlParams<T>& P, int f, const cpx<T>* uh,
                                                const ModeK<T>& m) {
   const cpx<T> zero((T)0, (T)0);
   if (!m.keep) return zero;
-  const int C = P.C, D = P.D;
-  switch (P.kind) {
+  const int C = EXB_S_C, D = EXB_S_D;
+  switch (EXB_S_KIND) {
     case EXB_NL_CONVECTION: {
-      if (P.conservative) return pick3c(uh, f);  // single or multi: u only
-      if (P.single_channel) {                     // u, d_d u   (_convection.py:207-217)
+      if (EXB_S_CONS) return pick3c(uh, f);  // single or multi: u only
+      if (EXB_S_SINGLE) {                     // u, d_d u   (_convection.py:207-217)
         if (f == 0) return uh[0];
         return mul_i(pick3(m.kd, f - 1) * uh[0]);
       }
@@ -104,13 +119,13 @@ __device__ __forceinline__ cpx<T> nl_inv_field(const NlParams<T>& P, int f, cons
 // ---- pointwise products in physical space ----------------------------------------------------
 // in[f]: the n_inv inverse-transformed fields at one grid point (already scaled by 1/N^D);
 // out[g]: the n_fwd fields to be forward-transformed.
-template <class T>
+template <class T, class S = NlDyn>
 __device__ __forceinline__ void nl_pointwise(const NlParams<T>& P, const T* in, T* out) {
-  const int C = P.C, D = P.D;
-  switch (P.kind) {
+  const int C = EXB_S_C, D = EXB_S_D;
+  switch (EXB_S_KIND) {
     case EXB_NL_CONVECTION: {
-      if (P.conservative) {
-        if (P.single_channel) {
+      if (EXB_S_CONS) {
+        if (EXB_S_SINGLE) {
 #pragma unroll
           for (int c = 0; c < EXB_MAXC; ++c)
             if (c < C) out[c] = in[c] * in[c];
@@ -121,7 +136,7 @@ __device__ __forceinline__ void nl_pointwise(const NlParams<T>& P, const T* in, 
             for (int d = 0; d < EXB_MAXC; ++d)
               if (c < C && d < C) out[c * C + d] = in[c] * in[d];
         }
-      } else if (P.single_channel) {
+      } else if (EXB_S_SINGLE) {
         T s = (T)0;
 #pragma unroll
         for (int d = 0; d < 3; ++d)
@@ -200,18 +215,18 @@ __device__ __forceinline__ void nl_pointwise(const NlParams<T>& P, const T* in, 
 // ---- N(u)_c at one mode from the forward-transformed fields W[g] ---------------------------
 // Post-dealiasing (nonlin_fun/_base.py:99-115) applied here; the Kolmogorov injection is
 // added un-masked.
-template <class T>
+template <class T, class S = NlDyn>
 __device__ __forceinline__ void nl_from_fwd(const NlParams<T>& P, const cpx<T>* W, const ModeK<T>& m,
                                             cpx<T>* out) {
   const cpx<T> zero((T)0, (T)0);
-  const int C = P.C, D = P.D;
+  const int C = EXB_S_C, D = EXB_S_D;
 #pragma unroll
   for (int c = 0; c < EXB_MAXC; ++c) out[c] = zero;
   if (m.keep) {
-    switch (P.kind) {
+    switch (EXB_S_KIND) {
       case EXB_NL_CONVECTION: {
-        if (P.conservative) {
-          if (P.single_channel) {  // -s * 0.5 * (sum_d i kd) * F(u^2)  (_convection.py:192-205)
+        if (EXB_S_CONS) {
+          if (EXB_S_SINGLE) {  // -s * 0.5 * (sum_d i kd) * F(u^2)  (_convection.py:192-205)
             T sd = (T)0;
 #pragma unroll
             for (int d = 0; d < 3; ++d)
@@ -234,7 +249,7 @@ __device__ __forceinline__ void nl_from_fwd(const NlParams<T>& P, const cpx<T>* 
         } else {
 #pragma unroll
           for (int c = 0; c < EXB_MAXC; ++c)
-            if (c < (P.single_channel ? 1 : C)) out[c] = (-P.scale) * W[c];
+            if (c < (EXB_S_SINGLE ? 1 : C)) out[c] = (-P.scale) * W[c];
         }
         break;
       }
