@@ -9,7 +9,31 @@ namespace {
 template <int R, class S, int NI, int NF>
 int launch_fast_t(cudaStream_t st, const K1dParams<float>& p, int nscr, int max_smem, const char** err) {
   constexpr int NN = R * R, NNh = NN / 2 + 1;
-  const int warps = 4, groups = warps * (32 / R);
+  // CTA shape: 2 CTAs per SM, sized so that the pairs of one SM split into equal rounds
+  // (all CTAs take the same time; a partially filled last round is pure loss).
+  const int gpw = 32 / R;  // pair groups per warp
+  int sms = 148;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  static const int nstate_of_order[5] = {1, 1, 2, 4, 5};
+  const int nstate = nstate_of_order[p.K.order];
+  const long long npairs_all = (p.batch + 1) / 2;
+  const int pair_bytes_est = (nstate * 2 * (((NNh + 1) / 2) * 2) + (R + 1) * R) * 8;
+  // shared memory per SM: 228 KB minus 2 x (coefficient/twiddle tables + 1 KB system reserve)
+  int max_pairs_sm = (228 * 1024 - 2 * (R * R * 8 + NNh * 40 + 256 + 1024)) / pair_bytes_est;
+  max_pairs_sm -= max_pairs_sm % (2 * gpw);
+  if (max_pairs_sm > 16 * gpw) max_pairs_sm = 16 * gpw;                 // register bound: 16 warps/SM
+  if (max_pairs_sm < 2 * gpw) max_pairs_sm = 2 * gpw;
+  long long pairs_per_sm = (npairs_all + sms - 1) / sms;
+  long long rounds = (pairs_per_sm + max_pairs_sm - 1) / max_pairs_sm;
+  long long pairs_per_round = (pairs_per_sm + rounds - 1) / rounds;     // per SM
+  int warps = (int)((pairs_per_round + 2 * gpw - 1) / (2 * gpw));       // 2 CTAs per SM
+  if (warps < 1) warps = 1;
+  if (warps > 8) warps = 8;
+  const int groups = warps * gpw;
   FastLayout lay;
   int off = 0;
   auto take = [&](int bytes) {
@@ -21,7 +45,8 @@ int launch_fast_t(cudaStream_t st, const K1dParams<float>& p, int nscr, int max_
   lay.off_exp = take(NNh * 8);
   lay.off_hexp = take(NNh * 8);
   for (int i = 0; i < 6; ++i) lay.off_c[i] = take(NNh * 4);
-  lay.nstate = 1 + nscr;
+  lay.nstate = nstate;
+  (void)nscr;
   lay.nhp = (NNh + 1) / 2 * 2;
   lay.pair_bytes = (lay.nstate * 2 * lay.nhp + (R + 1) * R) * 8;
   lay.off_pairs = take(0);

@@ -232,7 +232,8 @@ template <int R, class S, int NINV, int NFWD> struct Fast1d {
       return;
     }
     for (int s = 0; s < order; ++s) {
-      const int si = etdrk_stage_input(order, s);
+      // order 2 runs in place (a overwrites u): 2 state arrays instead of 3
+      const int si = order == 2 ? -1 : etdrk_stage_input(order, s);
       const cpx<float>* src = si < 0 ? U : state(1 + si);
       cpx<float> n1[NOWN], n2[NOWN];
       eval_nl(src, n1, n2);
@@ -252,10 +253,10 @@ template <int R, class S, int NINV, int NFWD> struct Fast1d {
               U[o] = sE[k] * U[o] + sc[0][k] * n;
             } else if (order == 2) {
               if (s == 0) {
-                S0[o] = sE[k] * U[o] + sc[0][k] * n;
-                S1[o] = n;
+                U[o] = sE[k] * U[o] + sc[0][k] * n;
+                S0[o] = n;
               } else {
-                U[o] = S0[o] + sc[1][k] * (n - S1[o]);
+                U[o] = U[o] + sc[1][k] * (n - S0[o]);
               }
             } else if (order == 3) {
               if (s == 0) {
@@ -290,7 +291,7 @@ template <int R, class S, int NINV, int NFWD> struct Fast1d {
 };
 
 template <int R, class S, int NINV, int NFWD>
-__global__ void __launch_bounds__(128, 4) k1d_fast_kernel(const K1dParams<float> p, const FastLayout lay) {
+__global__ void __launch_bounds__(256, 2) k1d_fast_kernel(const K1dParams<float> p, const FastLayout lay) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int N = R * R, Nh = N / 2 + 1;
   constexpr int GROUPS_PER_WARP = 32 / R;
