@@ -12,6 +12,7 @@
 #include "../../include/exb.h"
 #include "exb_kernels_1d.cuh"
 #include "exb_fast1d.h"
+#include "exb_fastnd.h"
 #include "exb_kernels_nd.cuh"
 
 using namespace exb;
@@ -247,6 +248,9 @@ template <class T> struct PlanImpl : exb_plan {
       if (rc) return rc;
     }
     nscr = etdrk_num_scratch(order);
+    if constexpr (std::is_same<T, float>::value) {
+      fast_nd = D >= 2 && !getenv("EXB_DISABLE_FAST_ND") && exb_fastnd_supported(D, N, P);
+    }
 
     if (D == 1) {
       size_t need = smem_1d(C, nslots_1d());
@@ -339,6 +343,31 @@ template <class T> struct PlanImpl : exb_plan {
   }
 
   // ------------------------------------------------------------------ N-D
+  bool fast_nd = false;  // set in init(): register-FFT kernels available for this (D, N, N(u))
+  int fast_tw() const { return N == 512 ? 8 : 16; }
+  int launch_col_fast(cudaStream_t st, ColParams<T>& p, int dir, long long units) {
+    if constexpr (std::is_same<T, float>::value) {
+      p.TW = fast_tw();
+      long long ntiles = (p.inner + p.TW - 1) / p.TW;
+      const char* err = nullptr;
+      int rc = exb_fastnd_col(st, p, dir, ntiles * units, &err);
+      if (rc) return fail(rc, "%s", err ? err : "fast column pass failed");
+      ++launches;
+      return EXB_OK;
+    }
+    return fail(EXB_EUNSUPPORTED, "fast N-D path is f32 only");
+  }
+  int launch_row_fast(cudaStream_t st, RowParams<T>& p) {
+    if constexpr (std::is_same<T, float>::value) {
+      const char* err = nullptr;
+      int rc = exb_fastnd_row(st, p, &err);
+      if (rc) return fail(rc, "%s", err ? err : "fast row pass failed");
+      ++launches;
+      return EXB_OK;
+    }
+    return fail(EXB_EUNSUPPORTED, "fast N-D path is f32 only");
+  }
+
   int pick_tw(int ntiles_resident) const {
     // widest tile (<= 16 lines) such that `ntiles_resident` tiles fit in shared memory
     int tw = 16;
@@ -377,6 +406,7 @@ template <class T> struct PlanImpl : exb_plan {
     p.in = in;
     p.out = out;
     col_geom(p, axis);
+    if (fast_nd) return launch_col_fast(st, p, DIR, p.n_outer * batch * nfields);
     long long ntiles = (p.inner + p.TW - 1) / p.TW;
     long long grid = ntiles * p.n_outer * batch * nfields;
     size_t smem = (size_t)2 * N * p.TW * sizeof(cpx<T>);
@@ -401,6 +431,7 @@ template <class T> struct PlanImpl : exb_plan {
     p.in = state;
     p.out = winv;
     col_geom(p, 0);
+    if (fast_nd) return launch_col_fast(st, p, +1, batch);
     long long ntiles = (p.inner + p.TW - 1) / p.TW;
     long long grid = ntiles * batch;
     size_t smem = (size_t)(C + 2) * N * p.TW * sizeof(cpx<T>);
@@ -428,6 +459,7 @@ template <class T> struct PlanImpl : exb_plan {
     p.out = nl_out;
     p.sb = sb;
     col_geom(p, 0);
+    if (fast_nd) return launch_col_fast(st, p, -1, batch);
     long long ntiles = (p.inner + p.TW - 1) / p.TW;
     long long grid = ntiles * batch;
     size_t smem = (size_t)(P.n_fwd + 1) * N * p.TW * sizeof(cpx<T>);
@@ -453,6 +485,7 @@ template <class T> struct PlanImpl : exb_plan {
     p.out_batch_stride = out_bs;
     p.in = in;
     p.out = out;
+    if (fast_nd) return launch_row_fast(st, p);
     int nslots = nin > nout ? nin : nout;
     size_t smem = (size_t)2 * nslots * N * sizeof(cpx<T>);
     long long grid = ((p.rows + 1) / 2) * batch;

@@ -1,0 +1,88 @@
+// Register-resident FFT core of the fast 2-D / 3-D kernels: an N-point complex line
+// (N = 64, 128, 256, 512; N = 8 * P) is held by P threads, 8 points each.  Two or three
+// in-register radix passes (8 x 8 x N/64) are joined by exchanges through shared memory; the
+// caller supplies the exchange addressing (contiguous padded line, or a column of a [N][TW]
+// tile) and the synchronisation (warp, named barrier or CTA).
+//   entry: v[q] = x[j + P*q]      exit: v[q] = X[j + P*q]      (unnormalised; DIR=-1 forward)
+#pragma once
+#include "exb_fft.cuh"
+
+namespace exb {
+
+template <int DIR, int R> __device__ __forceinline__ void dft_small(cpx<float>* a) {
+  if (R == 8) dft8<float, DIR>(a);
+  if (R == 4) dft4<float, DIR>(a);
+  if (R == 2) dft2<float, DIR>(a[0], a[1]);
+}
+
+// Ex: struct with  void st(int i, cpx<float>) const;  cpx<float> ld(int i) const;  void sync() const;
+template <int N, int DIR, class Ex>
+__device__ __forceinline__ void fft8_run(cpx<float> (&v)[8], const Ex& ex, int j, const cpx<float>* __restrict__ tw) {
+  constexpr int P = N / 8;
+  constexpr int R3 = N / 64;  // radix of the third pass (1: none)
+  static_assert(N == 64 || N == 128 || N == 256 || N == 512, "fft8_run: unsupported N");
+  // ---- pass 1: radix 8, Ns = 1 ----
+  dft8<float, DIR>(v);
+  ex.sync();
+#pragma unroll
+  for (int r = 0; r < 8; ++r) ex.st(8 * j + r, v[r]);
+  ex.sync();
+#pragma unroll
+  for (int q = 0; q < 8; ++q) v[q] = ex.ld(j + P * q);
+  // ---- pass 2: radix 8, Ns = 8 ----
+  {
+    const int k = j & 7;
+    const int ts = (N / 64) * k;
+#pragma unroll
+    for (int r = 1; r < 8; ++r) v[r] = v[r] * twd<float, DIR>(tw[ts * r]);
+    dft8<float, DIR>(v);
+    if (R3 == 1) return;  // N = 64: outputs already at j + 8*r
+    const int j0 = (j - k) * 8 + k;
+    ex.sync();
+#pragma unroll
+    for (int r = 0; r < 8; ++r) ex.st(j0 + 8 * r, v[r]);
+    ex.sync();
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = ex.ld(j + P * q);
+  }
+  // ---- pass 3: radix R3, Ns = 64; 8/R3 butterflies per thread, results stay in registers ----
+  if (R3 > 1) {
+    constexpr int NB = 8 / (R3 > 1 ? R3 : 8);
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+      const int b = j + P * i;
+      cpx<float> a[R3 > 1 ? R3 : 1];
+#pragma unroll
+      for (int r = 0; r < R3; ++r) {
+        a[r] = v[i + NB * r];
+        if (r > 0) a[r] = a[r] * twd<float, DIR>(tw[b * r]);
+      }
+      dft_small<DIR, R3>(a);
+#pragma unroll
+      for (int r = 0; r < R3; ++r) v[i + NB * r] = a[r];
+    }
+  }
+}
+
+// exchange through a contiguous, padded line buffer (row kernels): element i at i + i/8
+struct ExLine {
+  cpx<float>* base;
+  int sync_kind;  // 0: __syncwarp, otherwise named barrier id
+  int nthreads;
+  __device__ __forceinline__ void st(int i, cpx<float> x) const { base[i + (i >> 3)] = x; }
+  __device__ __forceinline__ cpx<float> ld(int i) const { return base[i + (i >> 3)]; }
+  __device__ __forceinline__ void sync() const {
+    if (sync_kind == 0) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(sync_kind), "r"(nthreads) : "memory");
+  }
+};
+
+// exchange through column w of a [N][TW] tile (column kernels): element i at i*TW + w
+template <int TW> struct ExTile {
+  cpx<float>* base;  // tile + w
+  __device__ __forceinline__ void st(int i, cpx<float> x) const { base[i * TW] = x; }
+  __device__ __forceinline__ cpx<float> ld(int i) const { return base[i * TW]; }
+  __device__ __forceinline__ void sync() const { __syncthreads(); }
+};
+
+}  // namespace exb

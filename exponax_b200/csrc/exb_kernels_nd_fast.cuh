@@ -1,0 +1,245 @@
+// Fast 2-D / 3-D pass kernels (f32, N in {64,128,256,512}) built on the register FFT core
+// exb_fft8.cuh.  Same pass structure and fusion as the generic kernels (exb_kernels_nd.cuh):
+//   col_fast<MODE>:  strided axis; a CTA owns a [N x TW] tile; thread (j, w) holds 8 points of
+//                    column w in registers, global loads/stores are coalesced across w, the
+//                    shared-memory tile is only the exchange buffer between radix passes;
+//                    COL_INV_PRO fuses mask / i*k / inverse Laplacian / curl, COL_FWD_EPI fuses
+//                    mask / scale / Leray / injection and the ETDRK stage update.
+//   row_fast<MODE>:  contiguous last axis; a group of N/8 threads owns a PAIR of rows
+//                    (two-for-one), runs the n_inv inverse transforms, the pointwise
+//                    nonlinearity in registers and the n_fwd forward transforms.
+// The nonlinear function is a compile-time descriptor S (NlS<...>).
+#pragma once
+#include "exb_fft8.cuh"
+#include "exb_kernels_nd.cuh"
+
+namespace exb {
+
+// ------------------------------------------------------------------------------- column pass
+template <int N, int TW, class S, int NFWD, int MODE, int DIR>
+__global__ void __launch_bounds__((N / 8) * TW) col_fast_kernel(const ColParams<float> p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int P = N / 8;
+  cpx<float>* tw = reinterpret_cast<cpx<float>*>(smem_raw);
+  cpx<float>* tile = tw + N;
+  for (int q = threadIdx.x; q < N; q += blockDim.x) tw[q] = p.tw[q];
+  const int w = threadIdx.x % TW, j = threadIdx.x / TW;
+  const long long ntiles = (p.inner + TW - 1) / TW;
+  long long bid = blockIdx.x;
+  const long long t = bid % ntiles;
+  bid /= ntiles;
+  const long long w0 = t * TW;
+  const bool act = w0 + w < p.inner;
+  const cpx<float> zero(0.f, 0.f);
+  ExTile<TW> ex{tile + w};
+  const long long ls = p.line_stride;
+  __syncthreads();
+
+  if (MODE == COL_PLAIN) {
+    const long long o = bid % p.n_outer;
+    bid /= p.n_outer;
+    const size_t base = (size_t)bid * p.M + (size_t)o * p.outer_stride + w0 + w;
+    cpx<float> v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = act ? p.in[base + (size_t)(j + P * q) * ls] : zero;
+    fft8_run<N, DIR>(v, ex, j, tw);
+    if (act) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) p.out[base + (size_t)(j + P * q) * ls] = v[q];
+    }
+    return;
+  }
+
+  const NlParams<float>& Pn = p.P;
+  constexpr int C = S::C;
+  const long long b = bid;
+  const long long iw = w0 + w;
+  // spatial indices of this thread's 8 modes: axis-0 index i = j + P*q; the rest from iw
+  int i1 = (int)iw, i2 = 0;
+  if (S::D == 3) {
+    i1 = (int)(iw / Pn.Nh);
+    i2 = (int)(iw - (long long)i1 * Pn.Nh);
+  }
+
+  if (MODE == COL_INV_PRO) {
+    cpx<float> uh[C][8];
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        uh[c][q] = act ? p.in[((size_t)b * C + c) * p.M + (size_t)(j + P * q) * ls + iw] : zero;
+    for (int f = 0; f < Pn.n_inv; ++f) {
+      cpx<float> v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        ModeK<float> m = make_mode<float, S>(Pn, j + P * q, i1, i2);
+        cpx<float> u[EXB_MAXC];
+#pragma unroll
+        for (int c = 0; c < EXB_MAXC; ++c) u[c] = c < C ? uh[c][q] : zero;
+        v[q] = nl_inv_field<float, S>(Pn, f, u, m);
+      }
+      fft8_run<N, DIR>(v, ex, j, tw);
+      if (act) {
+        const size_t obase = ((size_t)b * Pn.n_inv + f) * p.M + iw;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) p.out[obase + (size_t)(j + P * q) * ls] = v[q];
+      }
+    }
+    return;
+  }
+
+  // COL_FWD_EPI / COL_FWD_NL
+  cpx<float> W[NFWD][8];
+#pragma unroll
+  for (int g = 0; g < NFWD; ++g) {
+    const size_t ibase = ((size_t)b * NFWD + g) * p.M + iw;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) W[g][q] = act ? p.in[ibase + (size_t)(j + P * q) * ls] : zero;
+  }
+#pragma unroll
+  for (int g = 0; g < NFWD; ++g) fft8_run<N, DIR>(W[g], ex, j, tw);
+  if (!act) return;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int i0 = j + P * q;
+    ModeK<float> m = make_mode<float, S>(Pn, i0, i1, i2);
+    cpx<float> wq[NFWD], n[EXB_MAXC];
+#pragma unroll
+    for (int g = 0; g < NFWD; ++g) wq[g] = W[g][q];
+    nl_from_fwd<float, S>(Pn, wq, m, n);
+    const long long mode = (long long)i0 * ls + iw;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const size_t off = ((size_t)b * C + c) * p.M + mode;
+      if (MODE == COL_FWD_NL) {
+        p.out[off] = n[c];
+      } else {
+        const long long ci = (long long)(p.K.E == 1 ? 0 : c) * p.K.M + mode;
+        etdrk_update(p.K, p.stage, ci, off, n[c], p.sb);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------- row pass
+// GROUPS row pairs per CTA, N/8 threads each.
+template <int N, class S, int NINV, int NFWD, int MODE, int GROUPS>
+__global__ void __launch_bounds__((N / 8) * GROUPS) row_fast_kernel(const RowParams<float> p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int P = N / 8, Nh = N / 2 + 1, XB = N + N / 8;
+  cpx<float>* tw = reinterpret_cast<cpx<float>*>(smem_raw);
+  for (int q = threadIdx.x; q < N; q += blockDim.x) tw[q] = p.tw[q];
+  const int g = threadIdx.x / P, j = threadIdx.x % P;
+  ExLine ex{tw + N + (size_t)g * XB, P <= 32 ? 0 : 1 + g, P};
+  __syncthreads();
+  const NlParams<float>& Pn = p.P;
+  const long long npairs = (p.rows + 1) / 2;
+  const long long gp = (long long)blockIdx.x * GROUPS + g;   // global pair index
+  const bool live = gp < npairs * p.batch;
+  const long long b = live ? gp / npairs : 0;
+  const long long rp = live ? gp - b * npairs : 0;
+  const long long r1 = 2 * rp, r2 = r1 + 1;
+  const bool has1 = live, has2 = live && r2 < p.rows;
+  const cpx<float> zero(0.f, 0.f);
+
+  // two-for-one split of a forward line in registers; calls fn(k, X1, X2) for owned modes
+  auto unpack_store = [&](cpx<float> (&v)[8], cpx<float>* o1, cpx<float>* o2) {
+    ex.sync();
+#pragma unroll
+    for (int q = 4; q < 8; ++q) ex.st(j + P * q, v[q]);
+    ex.sync();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int k = j + P * q;
+      cpx<float> zk = v[q];
+      cpx<float> zp = (k == 0) ? zk : ex.ld(N - k);
+      if (has1) o1[k] = cpx<float>(0.5f * (zk.x + zp.x), 0.5f * (zk.y - zp.y));
+      if (has2) o2[k] = cpx<float>(0.5f * (zk.y + zp.y), -0.5f * (zk.x - zp.x));
+    }
+    if (j == 0) {
+      if (has1) o1[N / 2] = cpx<float>(v[4].x, 0.f);
+      if (has2) o2[N / 2] = cpx<float>(v[4].y, 0.f);
+    }
+  };
+  // packed inverse line from the half-complex rows i1p, i2p (irfft semantics at DC / Nyquist)
+  auto load_packed = [&](const cpx<float>* i1p, const cpx<float>* i2p, cpx<float> (&v)[8]) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int n = j + P * q;
+      const bool upper = n > N / 2;
+      const int k = upper ? N - n : n;
+      cpx<float> F1 = has1 ? i1p[k] : zero;
+      cpx<float> F2 = has2 ? i2p[k] : zero;
+      cpx<float> z;
+      if (k == 0 || 2 * k == N) z = cpx<float>(F1.x, F2.x);
+      else if (!upper) z = cpx<float>(F1.x - F2.y, F1.y + F2.x);
+      else z = cpx<float>(F1.x + F2.y, F2.x - F1.y);
+      v[q] = z;
+    }
+  };
+
+  if (MODE == ROW_R2C) {
+    const float* in = (const float*)p.in + (size_t)b * p.in_batch_stride;
+    cpx<float>* out = (cpx<float>*)p.out + (size_t)b * p.out_batch_stride;
+    for (int f = 0; f < p.nin; ++f) {
+      cpx<float> v[8];
+      const float* a = in + ((size_t)f * p.rows + r1) * N;
+      const float* c = in + ((size_t)f * p.rows + r2) * N;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = cpx<float>(has1 ? a[j + P * q] : 0.f, has2 ? c[j + P * q] : 0.f);
+      fft8_run<N, -1>(v, ex, j, tw);
+      unpack_store(v, out + ((size_t)f * p.rows + r1) * Nh, out + ((size_t)f * p.rows + r2) * Nh);
+    }
+    return;
+  }
+  if (MODE == ROW_C2R) {
+    const cpx<float>* in = (const cpx<float>*)p.in + (size_t)b * p.in_batch_stride;
+    float* out = (float*)p.out + (size_t)b * p.out_batch_stride;
+    for (int f = 0; f < p.nin; ++f) {
+      cpx<float> v[8];
+      load_packed(in + ((size_t)f * p.rows + r1) * Nh, in + ((size_t)f * p.rows + r2) * Nh, v);
+      fft8_run<N, +1>(v, ex, j, tw);
+      float* a = out + ((size_t)f * p.rows + r1) * N;
+      float* c = out + ((size_t)f * p.rows + r2) * N;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (has1) a[j + P * q] = v[q].x * Pn.inv_norm;
+        if (has2) c[j + P * q] = v[q].y * Pn.inv_norm;
+      }
+    }
+    return;
+  }
+
+  // ROW_NL
+  const cpx<float>* in = (const cpx<float>*)p.in + (size_t)b * p.in_batch_stride;
+  cpx<float>* out = (cpx<float>*)p.out + (size_t)b * p.out_batch_stride;
+  cpx<float> wl[NFWD][8];
+  {
+    cpx<float> z[NINV][8];
+#pragma unroll
+    for (int f = 0; f < NINV; ++f) {
+      load_packed(in + ((size_t)f * p.rows + r1) * Nh, in + ((size_t)f * p.rows + r2) * Nh, z[f]);
+      fft8_run<N, +1>(z[f], ex, j, tw);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float a1[NINV], a2[NINV], o1[NFWD], o2[NFWD];
+#pragma unroll
+      for (int f = 0; f < NINV; ++f) {
+        a1[f] = z[f][q].x * Pn.inv_norm;
+        a2[f] = z[f][q].y * Pn.inv_norm;
+      }
+      nl_pointwise<float, S>(Pn, a1, o1);
+      nl_pointwise<float, S>(Pn, a2, o2);
+#pragma unroll
+      for (int gg = 0; gg < NFWD; ++gg) wl[gg][q] = cpx<float>(o1[gg], o2[gg]);
+    }
+  }
+#pragma unroll
+  for (int gg = 0; gg < NFWD; ++gg) {
+    fft8_run<N, -1>(wl[gg], ex, j, tw);
+    unpack_store(wl[gg], out + ((size_t)gg * p.rows + r1) * Nh, out + ((size_t)gg * p.rows + r2) * Nh);
+  }
+}
+
+}  // namespace exb
