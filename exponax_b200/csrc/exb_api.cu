@@ -391,9 +391,11 @@ template <class T> struct PlanImpl : exb_plan {
   }
 
   template <int DIR>
-  int col_plain(cudaStream_t st, int axis, long long batch, int nfields, const cpx<T>* in, cpx<T>* out) {
+  int col_plain(cudaStream_t st, int axis, long long batch, int nfields, const cpx<T>* in, cpx<T>* out,
+                int prune = 0) {
     ColParams<T> p;
     memset(&p, 0, sizeof(p));
+    p.prune = prune;
     p.P = P;
     p.K = K;
     p.fd = fd;
@@ -424,6 +426,7 @@ template <class T> struct PlanImpl : exb_plan {
     p.fd = fd;
     p.tw = d_tw;
     p.mode = COL_INV_PRO;
+    p.prune = PRUNE_COLS;
     p.TW = pick_tw(C + 2);
     p.nfields = P.n_inv;
     p.M = M;
@@ -450,6 +453,7 @@ template <class T> struct PlanImpl : exb_plan {
     p.fd = fd;
     p.tw = d_tw;
     p.mode = mode;
+    p.prune = PRUNE_COLS;
     p.TW = pick_tw(P.n_fwd + 1);
     p.nfields = P.n_fwd;
     p.stage = stage;
@@ -473,6 +477,7 @@ template <class T> struct PlanImpl : exb_plan {
                long long in_bs, void* out, long long out_bs) {
     RowParams<T> p;
     memset(&p, 0, sizeof(p));
+    p.prune = mode == ROW_NL ? (PRUNE_IN_ROWS | PRUNE_OUT_ROWS) : 0;
     p.P = P;
     p.fd = fd;
     p.tw = d_tw;
@@ -557,14 +562,14 @@ template <class T> struct PlanImpl : exb_plan {
     int rc = col_inv_pro(st, batch, state, w.Winv);
     if (rc) return rc;
     if (D == 3) {
-      rc = col_plain<+1>(st, 1, batch, P.n_inv, w.Winv, w.Winv);
+      rc = col_plain<+1>(st, 1, batch, P.n_inv, w.Winv, w.Winv, PRUNE_COLS | PRUNE_IN_ROWS);
       if (rc) return rc;
     }
     rc = row_pass(st, ROW_NL, batch, P.n_inv, P.n_fwd, w.Winv, (long long)P.n_inv * M, w.Wfwd,
                   (long long)P.n_fwd * M);
     if (rc) return rc;
     if (D == 3) {
-      rc = col_plain<-1>(st, 1, batch, P.n_fwd, w.Wfwd, w.Wfwd);
+      rc = col_plain<-1>(st, 1, batch, P.n_fwd, w.Wfwd, w.Wfwd, PRUNE_COLS | PRUNE_OUT_ROWS);
       if (rc) return rc;
     }
     return EXB_OK;

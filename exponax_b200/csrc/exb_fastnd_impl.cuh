@@ -21,7 +21,7 @@ template <class K> int set_smem(K kernel, size_t smem, const char** err) {
 
 template <int N, int TW, class S, int NFWD, int MODE, int DIR>
 int launch_col(cudaStream_t st, const ColParams<float>& p, long long grid, const char** err) {
-  const size_t smem = (size_t)(N + N * TW) * sizeof(cpx<float>);
+  const size_t smem = (size_t)(Fft8Tw<N>::SIZE + ExTile<TW>::rows(N) * TW) * sizeof(cpx<float>);
   static bool once = false;
   if (!once) {
     int rc = set_smem(col_fast_kernel<N, TW, S, NFWD, MODE, DIR>, smem, err);
@@ -42,7 +42,8 @@ int launch_col(cudaStream_t st, const ColParams<float>& p, long long grid, const
 template <int N, class S, int NINV, int NFWD, int MODE>
 int launch_row(cudaStream_t st, const RowParams<float>& p, const char** err) {
   constexpr int P = N / 8, GROUPS = 256 / P;
-  const size_t smem = (size_t)(N + GROUPS * (N + N / 8)) * sizeof(cpx<float>);
+  const bool stash = false;  // see row_fast_kernel: STASH is compiled out
+  const size_t smem = (size_t)(Fft8Tw<N>::SIZE + GROUPS * (N + N / 8 + (stash ? NINV * N : 0))) * sizeof(cpx<float>);
   static bool once = false;
   if (!once) {
     int rc = set_smem(row_fast_kernel<N, S, NINV, NFWD, MODE, GROUPS>, smem, err);

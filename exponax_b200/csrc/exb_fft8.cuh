@@ -15,6 +15,27 @@ template <int DIR, int R> __device__ __forceinline__ void dft_small(cpx<float>* 
   if (R == 2) dft2<float, DIR>(a[0], a[1]);
 }
 
+// Twiddle table (shared memory, forward sign), arranged per pass so that the lanes of a warp
+// read consecutive entries (bank-conflict free):
+//   T2[(r-1)*8 + k]        = w_64^(k*r)    r = 1..7, k = 0..7          (pass 2)
+//   T3[(r-1)*64 + b]       = w_N^(b*r)     r = 1..R3-1, b = 0..63      (pass 3), T3 = T2 + 56
+template <int N> struct Fft8Tw {
+  static constexpr int R3 = N / 64;
+  static constexpr int SIZE = 56 + (R3 > 1 ? (R3 - 1) * 64 : 0);
+  // roots: the N-th roots of unity exp(-2 pi i j / N) in global memory
+  static __device__ __forceinline__ void fill(cpx<float>* t, const cpx<float>* __restrict__ roots) {
+    for (int q = threadIdx.x; q < SIZE; q += blockDim.x) {
+      if (q < 56) {
+        int r = q / 8 + 1, k = q % 8;
+        t[q] = roots[(N / 64) * k * r];
+      } else {
+        int r = (q - 56) / 64 + 1, b = (q - 56) % 64;
+        t[q] = roots[b * r];
+      }
+    }
+  }
+};
+
 // Ex: struct with  void st(int i, cpx<float>) const;  cpx<float> ld(int i) const;  void sync() const;
 template <int N, int DIR, class Ex>
 __device__ __forceinline__ void fft8_run(cpx<float> (&v)[8], const Ex& ex, int j, const cpx<float>* __restrict__ tw) {
@@ -32,9 +53,8 @@ __device__ __forceinline__ void fft8_run(cpx<float> (&v)[8], const Ex& ex, int j
   // ---- pass 2: radix 8, Ns = 8 ----
   {
     const int k = j & 7;
-    const int ts = (N / 64) * k;
 #pragma unroll
-    for (int r = 1; r < 8; ++r) v[r] = v[r] * twd<float, DIR>(tw[ts * r]);
+    for (int r = 1; r < 8; ++r) v[r] = v[r] * twd<float, DIR>(tw[(r - 1) * 8 + k]);
     dft8<float, DIR>(v);
     if (R3 == 1) return;  // N = 64: outputs already at j + 8*r
     const int j0 = (j - k) * 8 + k;
@@ -55,7 +75,7 @@ __device__ __forceinline__ void fft8_run(cpx<float> (&v)[8], const Ex& ex, int j
 #pragma unroll
       for (int r = 0; r < R3; ++r) {
         a[r] = v[i + NB * r];
-        if (r > 0) a[r] = a[r] * twd<float, DIR>(tw[b * r]);
+        if (r > 0) a[r] = a[r] * twd<float, DIR>(tw[56 + (r - 1) * 64 + b]);
       }
       dft_small<DIR, R3>(a);
 #pragma unroll
@@ -78,10 +98,14 @@ struct ExLine {
 };
 
 // exchange through column w of a [N][TW] tile (column kernels): element i at i*TW + w
+// (rows narrower than 128 B get one pad row per 8 rows so that the stride-8-row stores of
+// pass 1 spread over all banks)
 template <int TW> struct ExTile {
+  static constexpr bool PAD = TW < 16;
+  static constexpr int rows(int n) { return PAD ? n + n / 8 : n; }
   cpx<float>* base;  // tile + w
-  __device__ __forceinline__ void st(int i, cpx<float> x) const { base[i * TW] = x; }
-  __device__ __forceinline__ cpx<float> ld(int i) const { return base[i * TW]; }
+  __device__ __forceinline__ void st(int i, cpx<float> x) const { base[(PAD ? i + (i >> 3) : i) * TW] = x; }
+  __device__ __forceinline__ cpx<float> ld(int i) const { return base[(PAD ? i + (i >> 3) : i) * TW]; }
   __device__ __forceinline__ void sync() const { __syncthreads(); }
 };
 

@@ -17,6 +17,13 @@ namespace exb {
 
 enum ColMode { COL_PLAIN = 0, COL_INV_PRO = 1, COL_FWD_EPI = 2, COL_FWD_NL = 3 };
 enum RowMode { ROW_NL = 0, ROW_R2C = 1, ROW_C2R = 2 };
+// Dealiasing-aware pruning (2/3 rule: about 1/3 of the modes per masked axis are identically
+// zero before an inverse / discarded after a forward transform):
+enum Prune {
+  PRUNE_COLS = 1,      // skip lines whose fixed wavenumbers lie outside the mask
+  PRUNE_IN_ROWS = 2,   // entries of a line outside the mask are read as zero (no load)
+  PRUNE_OUT_ROWS = 4   // entries of a line outside the mask are not stored
+};
 
 template <class T> struct ColParams {
   NlParams<T> P;
@@ -27,6 +34,7 @@ template <class T> struct ColParams {
   int TW;                  // tile width (lines per CTA)
   int nfields;             // fields per batch element (PLAIN); n_inv / n_fwd otherwise
   int stage;               // ETDRK stage (FWD_EPI)
+  int prune;               // fast kernels only: PRUNE_* bits (dealiased modes are never touched)
   long long line_stride;   // elements between successive points of a line
   long long inner;         // contiguous positions across which lines are tiled
   long long n_outer;       // independent slabs per field (3-D axis-1 pass: N)
@@ -176,6 +184,7 @@ template <class T> struct RowParams {
   int mode;
   int nin, nout;             // fields per batch element read / written
   long long rows;            // rows per field = N^(D-1)
+  int prune;                 // fast kernels only: PRUNE_IN_ROWS / PRUNE_OUT_ROWS along the last axis
   long long batch;
   long long in_batch_stride;   // elements (of the in type) between batch elements
   long long out_batch_stride;  // elements (of the out type) between batch elements

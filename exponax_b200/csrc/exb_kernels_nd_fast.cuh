@@ -17,12 +17,14 @@ namespace exb {
 
 // ------------------------------------------------------------------------------- column pass
 template <int N, int TW, class S, int NFWD, int MODE, int DIR>
-__global__ void __launch_bounds__((N / 8) * TW) col_fast_kernel(const ColParams<float> p) {
+__global__ void __launch_bounds__((N / 8) * TW, (MODE == COL_PLAIN ? 2048 / ((N / 8) * TW)
+                                                 : (MODE == COL_INV_PRO ? 2 : (NFWD == 1 ? 3 : 2))))
+col_fast_kernel(const ColParams<float> p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int P = N / 8;
   cpx<float>* tw = reinterpret_cast<cpx<float>*>(smem_raw);
-  cpx<float>* tile = tw + N;
-  for (int q = threadIdx.x; q < N; q += blockDim.x) tw[q] = p.tw[q];
+  cpx<float>* tile = tw + Fft8Tw<N>::SIZE;
+  Fft8Tw<N>::fill(tw, p.tw);
   const int w = threadIdx.x % TW, j = threadIdx.x / TW;
   const long long ntiles = (p.inner + TW - 1) / TW;
   long long bid = blockIdx.x;
@@ -33,19 +35,43 @@ __global__ void __launch_bounds__((N / 8) * TW) col_fast_kernel(const ColParams<
   const cpx<float> zero(0.f, 0.f);
   ExTile<TW> ex{tile + w};
   const long long ls = p.line_stride;
+  const int kmax = p.P.kmax;
+  const bool prune_rows_in = (p.prune & PRUNE_IN_ROWS) && kmax >= 0;
+  const bool prune_rows_out = (p.prune & PRUNE_OUT_ROWS) && kmax >= 0;
+  // is entry i of a line inside the dealiasing mask (lines run along a full, fftfreq-ordered axis)
+  auto row_keep = [&](int i) {
+    int k = wavenumber_of(i, N);
+    return (k < 0 ? -k : k) <= kmax;
+  };
+  // are the fixed wavenumbers of this thread's column inside the mask
+  bool col_keep = act;
+  if ((p.prune & PRUNE_COLS) && kmax >= 0 && act) {
+    const long long iwc = w0 + w;
+    if (p.inner == p.P.Nh) {            // 2-D axis 0 or 3-D axis 1: inner index = last-axis wavenumber
+      col_keep = iwc <= kmax;
+    } else {                            // 3-D axis 0: inner = (i1, i2)
+      int a1 = (int)(iwc / p.P.Nh), a2 = (int)(iwc - (long long)a1 * p.P.Nh);
+      int k1 = wavenumber_of(a1, N);
+      col_keep = (k1 < 0 ? -k1 : k1) <= kmax && a2 <= kmax;
+    }
+  }
   __syncthreads();
+  const bool any_keep = __syncthreads_or(col_keep);
 
   if (MODE == COL_PLAIN) {
     const long long o = bid % p.n_outer;
     bid /= p.n_outer;
     const size_t base = (size_t)bid * p.M + (size_t)o * p.outer_stride + w0 + w;
+    if (!any_keep) return;
     cpx<float> v[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) v[q] = act ? p.in[base + (size_t)(j + P * q) * ls] : zero;
+    for (int q = 0; q < 8; ++q)
+      v[q] = (col_keep && (!prune_rows_in || row_keep(j + P * q))) ? p.in[base + (size_t)(j + P * q) * ls] : zero;
     fft8_run<N, DIR>(v, ex, j, tw);
-    if (act) {
+    if (col_keep) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) p.out[base + (size_t)(j + P * q) * ls] = v[q];
+      for (int q = 0; q < 8; ++q)
+        if (!prune_rows_out || row_keep(j + P * q)) p.out[base + (size_t)(j + P * q) * ls] = v[q];
     }
     return;
   }
@@ -62,24 +88,37 @@ __global__ void __launch_bounds__((N / 8) * TW) col_fast_kernel(const ColParams<
   }
 
   if (MODE == COL_INV_PRO) {
-    cpx<float> uh[C][8];
-#pragma unroll
-    for (int c = 0; c < C; ++c)
+    if (!any_keep) return;  // every column of this tile is dealiased away: nothing is written,
+                            // the consumers never read masked columns (PRUNE_* contract)
+    // the stage input is re-read for every field (L1/L2 hits: same thread, same addresses)
+    // instead of being held in registers across the field loop: keeps the kernel at <= 64
+    // registers, i.e. two 512-thread CTAs per SM
+    // (single-channel inputs are cheap enough to keep in registers: measured faster, r01g)
+    const cpx<float>* ubase = p.in + (size_t)b * C * p.M + iw;
+    cpx<float> u0[8];
+    if (C == 1) {
 #pragma unroll
       for (int q = 0; q < 8; ++q)
-        uh[c][q] = act ? p.in[((size_t)b * C + c) * p.M + (size_t)(j + P * q) * ls + iw] : zero;
+        u0[q] = (col_keep && (kmax < 0 || row_keep(j + P * q))) ? ubase[(size_t)(j + P * q) * ls] : zero;
+    }
     for (int f = 0; f < Pn.n_inv; ++f) {
       cpx<float> v[8];
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        ModeK<float> m = make_mode<float, S>(Pn, j + P * q, i1, i2);
-        cpx<float> u[EXB_MAXC];
+        const int i0 = j + P * q;
+        cpx<float> val = zero;
+        if (col_keep && (kmax < 0 || row_keep(i0))) {
+          ModeK<float> m = make_mode<float, S>(Pn, i0, i1, i2);
+          cpx<float> u[EXB_MAXC];
 #pragma unroll
-        for (int c = 0; c < EXB_MAXC; ++c) u[c] = c < C ? uh[c][q] : zero;
-        v[q] = nl_inv_field<float, S>(Pn, f, u, m);
+          for (int c = 0; c < EXB_MAXC; ++c)
+            u[c] = c < C ? (C == 1 ? u0[q] : ubase[(size_t)c * p.M + (size_t)i0 * ls]) : zero;
+          val = nl_inv_field<float, S>(Pn, f, u, m);
+        }
+        v[q] = val;
       }
       fft8_run<N, DIR>(v, ex, j, tw);
-      if (act) {
+      if (col_keep) {
         const size_t obase = ((size_t)b * Pn.n_inv + f) * p.M + iw;
 #pragma unroll
         for (int q = 0; q < 8; ++q) p.out[obase + (size_t)(j + P * q) * ls] = v[q];
@@ -94,10 +133,12 @@ __global__ void __launch_bounds__((N / 8) * TW) col_fast_kernel(const ColParams<
   for (int g = 0; g < NFWD; ++g) {
     const size_t ibase = ((size_t)b * NFWD + g) * p.M + iw;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) W[g][q] = act ? p.in[ibase + (size_t)(j + P * q) * ls] : zero;
+    for (int q = 0; q < 8; ++q) W[g][q] = col_keep ? p.in[ibase + (size_t)(j + P * q) * ls] : zero;
   }
+  if (any_keep) {  // masked columns only need the N = 0 update below
 #pragma unroll
-  for (int g = 0; g < NFWD; ++g) fft8_run<N, DIR>(W[g], ex, j, tw);
+    for (int g = 0; g < NFWD; ++g) fft8_run<N, DIR>(W[g], ex, j, tw);
+  }
   if (!act) return;
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
@@ -124,13 +165,21 @@ __global__ void __launch_bounds__((N / 8) * TW) col_fast_kernel(const ColParams<
 // ---------------------------------------------------------------------------------- row pass
 // GROUPS row pairs per CTA, N/8 threads each.
 template <int N, class S, int NINV, int NFWD, int MODE, int GROUPS>
-__global__ void __launch_bounds__((N / 8) * GROUPS) row_fast_kernel(const RowParams<float> p) {
+__global__ void __launch_bounds__((N / 8) * GROUPS, (MODE == ROW_NL ? (NINV <= 4 ? 2 : 1) : 4))
+row_fast_kernel(const RowParams<float> p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int P = N / 8, Nh = N / 2 + 1, XB = N + N / 8;
+  // ROW_NL with several inverse lines: the physical-space results of each line are parked in a
+  // thread-private slice of shared memory (conflict-free, no synchronisation) instead of
+  // NINV * 16 registers, which keeps the kernel at 2-3 CTAs per SM.
+  constexpr bool STASH = false && (MODE == ROW_NL) && NINV >= 2;  // measured slower on B200 (r01g): off
+  constexpr int SLOT = XB + (STASH ? NINV * N : 0);  // complex elements per group
   cpx<float>* tw = reinterpret_cast<cpx<float>*>(smem_raw);
-  for (int q = threadIdx.x; q < N; q += blockDim.x) tw[q] = p.tw[q];
+  Fft8Tw<N>::fill(tw, p.tw);
   const int g = threadIdx.x / P, j = threadIdx.x % P;
-  ExLine ex{tw + N + (size_t)g * XB, P <= 32 ? 0 : 1 + g, P};
+  cpx<float>* gbase = tw + Fft8Tw<N>::SIZE + (size_t)g * SLOT;
+  ExLine ex{gbase, P <= 32 ? 0 : 1 + g, P};
+  cpx<float>* stash = gbase + XB;
   __syncthreads();
   const NlParams<float>& Pn = p.P;
   const long long npairs = (p.rows + 1) / 2;
@@ -141,6 +190,8 @@ __global__ void __launch_bounds__((N / 8) * GROUPS) row_fast_kernel(const RowPar
   const long long r1 = 2 * rp, r2 = r1 + 1;
   const bool has1 = live, has2 = live && r2 < p.rows;
   const cpx<float> zero(0.f, 0.f);
+  const int kin = ((p.prune & PRUNE_IN_ROWS) && p.P.kmax >= 0) ? p.P.kmax : N;    // load k <= kin only
+  const int kout = ((p.prune & PRUNE_OUT_ROWS) && p.P.kmax >= 0) ? p.P.kmax : N;  // store k <= kout only
 
   // two-for-one split of a forward line in registers; calls fn(k, X1, X2) for owned modes
   auto unpack_store = [&](cpx<float> (&v)[8], cpx<float>* o1, cpx<float>* o2) {
@@ -153,10 +204,10 @@ __global__ void __launch_bounds__((N / 8) * GROUPS) row_fast_kernel(const RowPar
       const int k = j + P * q;
       cpx<float> zk = v[q];
       cpx<float> zp = (k == 0) ? zk : ex.ld(N - k);
-      if (has1) o1[k] = cpx<float>(0.5f * (zk.x + zp.x), 0.5f * (zk.y - zp.y));
-      if (has2) o2[k] = cpx<float>(0.5f * (zk.y + zp.y), -0.5f * (zk.x - zp.x));
+      if (has1 && k <= kout) o1[k] = cpx<float>(0.5f * (zk.x + zp.x), 0.5f * (zk.y - zp.y));
+      if (has2 && k <= kout) o2[k] = cpx<float>(0.5f * (zk.y + zp.y), -0.5f * (zk.x - zp.x));
     }
-    if (j == 0) {
+    if (j == 0 && N / 2 <= kout) {
       if (has1) o1[N / 2] = cpx<float>(v[4].x, 0.f);
       if (has2) o2[N / 2] = cpx<float>(v[4].y, 0.f);
     }
@@ -168,8 +219,8 @@ __global__ void __launch_bounds__((N / 8) * GROUPS) row_fast_kernel(const RowPar
       const int n = j + P * q;
       const bool upper = n > N / 2;
       const int k = upper ? N - n : n;
-      cpx<float> F1 = has1 ? i1p[k] : zero;
-      cpx<float> F2 = has2 ? i2p[k] : zero;
+      cpx<float> F1 = (has1 && k <= kin) ? i1p[k] : zero;
+      cpx<float> F2 = (has2 && k <= kin) ? i2p[k] : zero;
       cpx<float> z;
       if (k == 0 || 2 * k == N) z = cpx<float>(F1.x, F2.x);
       else if (!upper) z = cpx<float>(F1.x - F2.y, F1.y + F2.x);
@@ -214,7 +265,29 @@ __global__ void __launch_bounds__((N / 8) * GROUPS) row_fast_kernel(const RowPar
   const cpx<float>* in = (const cpx<float>*)p.in + (size_t)b * p.in_batch_stride;
   cpx<float>* out = (cpx<float>*)p.out + (size_t)b * p.out_batch_stride;
   cpx<float> wl[NFWD][8];
-  {
+  if (STASH) {
+    for (int f = 0; f < NINV; ++f) {
+      cpx<float> z[8];
+      load_packed(in + ((size_t)f * p.rows + r1) * Nh, in + ((size_t)f * p.rows + r2) * Nh, z);
+      fft8_run<N, +1>(z, ex, j, tw);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) stash[(size_t)f * N + j + P * q] = z[q];
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float a1[NINV], a2[NINV], o1[NFWD], o2[NFWD];
+#pragma unroll
+      for (int f = 0; f < NINV; ++f) {
+        cpx<float> zz = stash[(size_t)f * N + j + P * q];
+        a1[f] = zz.x * Pn.inv_norm;
+        a2[f] = zz.y * Pn.inv_norm;
+      }
+      nl_pointwise<float, S>(Pn, a1, o1);
+      nl_pointwise<float, S>(Pn, a2, o2);
+#pragma unroll
+      for (int gg = 0; gg < NFWD; ++gg) wl[gg][q] = cpx<float>(o1[gg], o2[gg]);
+    }
+  } else {
     cpx<float> z[NINV][8];
 #pragma unroll
     for (int f = 0; f < NINV; ++f) {
