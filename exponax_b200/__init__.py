@@ -11,6 +11,7 @@ Arrays may be torch CUDA tensors, anything with `__cuda_array_interface__`/DLPac
 NumPy arrays (copied to the device and back).  There is no CPU fallback.
 """
 from . import _spectral as spectral
+from . import _distributed as distributed
 from . import etdrk, nonlin_fun, stepper
 from ._base_stepper import BaseStepper
 from ._config import config
@@ -26,6 +27,7 @@ __all__ = [
     "ForcedStepper",
     "RepeatedStepper",
     "config",
+    "distributed",
     "etdrk",
     "fft",
     "ifft",
