@@ -17,6 +17,7 @@ from ._base_stepper import BaseStepper
 from ._config import config
 from ._forced_stepper import ForcedStepper
 from ._repeated_stepper import RepeatedStepper
+from ._slab import SlabStepper
 from ._spectral import fft, ifft
 from ._utils import make_grid, repeat, rollout, vmap
 
@@ -26,6 +27,7 @@ __all__ = [
     "BaseStepper",
     "ForcedStepper",
     "RepeatedStepper",
+    "SlabStepper",
     "config",
     "distributed",
     "etdrk",

@@ -16,6 +16,8 @@ LIB_PATH = os.path.join(_HERE, "libexb.so")
 EXB_F32, EXB_F64 = 0, 1
 NL_ZERO, NL_CONVECTION, NL_GRADIENT_NORM, NL_POLYNOMIAL, NL_VORTICITY_2D, NL_PROJECTED_3D, NL_GENERAL = range(7)
 ROLLOUT_INCLUDE_INIT, ROLLOUT_LAYOUT_TB, ROLLOUT_FINAL_ONLY, ROLLOUT_SPECTRAL_CARRY = 1, 2, 4, 8
+(SLAB_ROW_R2C, SLAB_ROW_C2R, SLAB_COL1_FWD, SLAB_COL1_INV, SLAB_COL0_FWD, SLAB_COL0_INV, SLAB_COL0_INV_PRO,
+ SLAB_ROW_NL, SLAB_COL0_FWD_EPI, SLAB_COL1_INV_NL, SLAB_COL1_FWD_NL) = range(11)
 EXB_MAX_POLY = 8
 
 
@@ -45,6 +47,8 @@ class ExbDesc(C.Structure):
         ("exp_term", C.c_void_p),
         ("half_exp_term", C.c_void_p),
         ("coef", C.c_void_p * 6),
+        ("slab_nranks", C.c_int32),
+        ("slab_rank", C.c_int32),
     ]
 
 
@@ -66,6 +70,9 @@ SYMBOLS = {
     "exb_rollout": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_uint32,
                               C.c_void_p, C.c_void_p, C.c_void_p]),
     "exb_launch_count": (C.c_int64, [C.c_void_p]),
+    "exb_slab_pass": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "exb_plan_nl_fields": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
 }
 
 
@@ -106,7 +113,8 @@ def check(rc: int):
 class Plan:
     """Owns one exb_plan (device tables live until the object is garbage collected)."""
 
-    def __init__(self, *, D, N, C_, E, order, dtype, L, kmax, nl, exp_term, half_exp_term=None, coefs=()):
+    def __init__(self, *, D, N, C_, E, order, dtype, L, kmax, nl, exp_term, half_exp_term=None, coefs=(),
+                 slab=(1, 0)):
         rd = np.float32 if dtype == np.float32 else np.float64
         cd = np.complex64 if rd == np.float32 else np.complex128
         d = ExbDesc()
@@ -136,6 +144,7 @@ class Plan:
             for i in range(3):
                 d.injection_index[i] = int(idx[i])
             d.injection_value = float(inj[1])
+        d.slab_nranks, d.slab_rank = int(slab[0]), int(slab[1])
         self._keep = []
 
         def host(a, dt):

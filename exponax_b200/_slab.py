@@ -1,0 +1,199 @@
+"""
+Slab-decomposed 3-D ETDRK stepping of ONE field that is sharded over several GPUs
+(BASELINE config c5).  One process per GPU (`torchrun`):
+
+  physical slab  A: (F, N/P, N, N)        x-planes   [rank*N/P, (rank+1)*N/P)
+  spectral slab  B: (F, N, N/P, N/2+1)    k1-indices [rank*N/P, (rank+1)*N/P)
+
+A 3-D transform = local last-axis pass + local axis-1 pass on layout A, ONE all-to-all transpose
+(NCCL over NVLink, `torch.distributed.all_to_all_single`), local axis-0 pass on layout B.  All
+nonlinear / ETDRK arithmetic is per mode or per point and therefore local; the passes are the same
+fused sm_100a kernels as on one GPU, driven through `exb_slab_pass` (include/exb.h).
+
+The reference has no multi-device code at all: it cannot even construct the dense
+operator arrays of a 2048^3 problem on one device.  Here every rank only ever holds its
+own slab of the state, of the intermediates and of the ETDRK coefficient tables.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _array as A
+from . import _native as nat
+from ._base_stepper import BaseStepper
+from .csrc_meta import etdrk_stage_input
+
+
+def _group_info(group):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def transpose_a_to_b(x: torch.Tensor, group=None) -> torch.Tensor:
+    """(F, n, N, K) split over x-planes  ->  (F, N, n, K) split over axis-1 indices (n = N/P)."""
+    rank, P = _group_info(group)
+    F, n, N, K = x.shape
+    if P == 1:
+        return x
+    send = x.view(F, n, P, n, K).permute(2, 0, 1, 3, 4).contiguous()        # [dest][F][x][k1][K]
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send, group=group)                        # [src][F][x_src][k1][K]
+    return recv.permute(1, 0, 2, 3, 4).reshape(F, N, n, K)                  # x_global = src*n + x
+
+
+def transpose_b_to_a(x: torch.Tensor, group=None) -> torch.Tensor:
+    """(F, N, n, K) split over axis-1 indices  ->  (F, n, N, K) split over x-planes."""
+    rank, P = _group_info(group)
+    F, N, n, K = x.shape
+    if P == 1:
+        return x
+    send = x.view(F, P, n, n, K).permute(1, 0, 2, 3, 4).contiguous()        # [dest][F][x][k1][K]
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send, group=group)                        # [src][F][x][k1_src][K]
+    return recv.permute(1, 2, 0, 3, 4).reshape(F, n, N, K)                  # k1_global = src*n + k1
+
+
+class SlabStepper:
+    """Distributed counterpart of a 3-D `BaseStepper` for a single, slab-sharded field."""
+
+    def __init__(self, stepper: BaseStepper, group=None):
+        if stepper.num_spatial_dims != 3:
+            raise ValueError("SlabStepper needs a 3-D stepper")
+        if not stepper._plan_available():
+            raise NotImplementedError("SlabStepper needs a stepper with a native nonlinear function")
+        self.stepper = stepper
+        self.group = group
+        self.rank, self.P = _group_info(group)
+        N = stepper.num_points
+        if N % self.P:
+            raise ValueError(f"num_points={N} must be divisible by the number of ranks ({self.P})")
+        self.N, self.n, self.Nh, self.Cn = N, N // self.P, N // 2 + 1, stepper.num_channels
+        self._plan = None
+        self._bufs = {}
+
+    # ---- plan with the LOCAL slices of the coefficient tables --------------------------------
+    def _local(self, arr):
+        lo, hi = self.rank * self.n, (self.rank + 1) * self.n
+        return np.ascontiguousarray(arr[:, :, lo:hi, :])
+
+    def plan(self):
+        if self._plan is None:
+            st, it = self.stepper, self.stepper._integrator
+            nl = st._nonlinear_fun
+            order = it.order
+            desc = nl._native_desc(st.num_channels) if order > 0 else {"kind": nat.NL_ZERO}
+            half = it._half_exp()
+            self._plan = nat.Plan(
+                D=3, N=self.N, C_=self.Cn, E=it._linear_operator.shape[0], order=order, dtype=st._dtype,
+                L=st.domain_extent, kmax=nl._kmax if order > 0 else -1, nl=desc,
+                exp_term=self._local(it._exp_term), half_exp_term=None if half is None else self._local(half),
+                coefs=[self._local(c) for c in it._coef_list()], slab=(max(self.P, 1), self.rank))
+            ni, nf = C.c_int32(), C.c_int32()
+            nat.check(nat.lib().exb_plan_nl_fields(self._plan.handle, C.byref(ni), C.byref(nf)))
+            self.n_inv, self.n_fwd = ni.value, nf.value
+            self.order = order if desc.get("kind") != nat.NL_ZERO else 0
+        return self._plan
+
+    def _buf(self, name, nfields, real=False):
+        key = (name, nfields, real)
+        b = self._bufs.get(key)
+        if b is None:
+            rd = self.stepper._dtype
+            if real:
+                b = torch.zeros((nfields, self.n, self.N, self.N), dtype=A.real_t(rd), device="cuda")
+            else:
+                b = torch.zeros((nfields, self.n, self.N, self.Nh), dtype=A.cplx_t(rd), device="cuda")
+            self._bufs[key] = b
+        return b
+
+    def _pass(self, kind, nfields, inp, out, *, stage=0, U=None, OUT=None, S=None):
+        arr = (C.c_void_p * 4)(*[A.ptr(s) if s is not None else None for s in (S or [None] * 4)])
+        nat.check(nat.lib().exb_slab_pass(self.plan().handle, A.stream_ptr(), kind, nfields, stage, A.ptr(inp),
+                                          A.ptr(out), A.ptr(U), A.ptr(OUT), arr))
+
+    # ---- data movement helpers (tests / examples) ---------------------------------------------
+    def scatter(self, u_global):
+        """Local physical slab (C, N/P, N, N) of a replicated global field (C, N, N, N)."""
+        t, _ = A.to_device(u_global, self.stepper._dtype)
+        return t[:, self.rank * self.n:(self.rank + 1) * self.n].contiguous()
+
+    def gather(self, u_local):
+        """Replicated global field from the local slabs (not on the timed path)."""
+        if self.P == 1:
+            return u_local
+        parts = [torch.empty_like(u_local) for _ in range(self.P)]
+        dist.all_gather(parts, u_local.contiguous(), group=self.group)
+        return torch.cat(parts, dim=1)
+
+    # ---- transforms ---------------------------------------------------------------------------
+    def fft(self, u_local):
+        """physical slab (F, N/P, N, N) -> spectral slab (F, N, N/P, N/2+1)."""
+        self.plan()
+        F = u_local.shape[0]
+        a = self._buf("fft_a", F)
+        self._pass(nat.SLAB_ROW_R2C, F, u_local.contiguous(), a)
+        self._pass(nat.SLAB_COL1_FWD, F, a, a)
+        b = transpose_a_to_b(a, self.group)
+        out = torch.empty((F, self.N, self.n, self.Nh), dtype=b.dtype, device="cuda")
+        self._pass(nat.SLAB_COL0_FWD, F, b.contiguous(), out)
+        return out
+
+    def ifft(self, uh_local):
+        """spectral slab -> physical slab (the input is left untouched)."""
+        self.plan()
+        F = uh_local.shape[0]
+        tmp = self._buf("ifft_b", F).view(F, self.N, self.n, self.Nh)
+        self._pass(nat.SLAB_COL0_INV, F, uh_local.contiguous(), tmp)
+        a = transpose_b_to_a(tmp, self.group).contiguous()
+        self._pass(nat.SLAB_COL1_INV, F, a, a)
+        out = torch.empty((F, self.n, self.N, self.N), dtype=A.real_t(self.stepper._dtype), device="cuda")
+        self._pass(nat.SLAB_ROW_C2R, F, a, out)
+        return out
+
+    # ---- time stepping --------------------------------------------------------------------------
+    def step_fourier(self, uh):
+        """One ETDRK step on the local spectral slab (C, N, N/P, N/2+1); returns a new tensor."""
+        self.plan()
+        uh = uh.contiguous()
+        out = torch.empty_like(uh)
+        if self.order == 0:
+            self._pass(nat.SLAB_COL0_FWD_EPI, 0, None, None, U=uh, OUT=out)
+            return out
+        S = [torch.empty_like(uh) for _ in range(self.order)] + [None] * (4 - self.order)
+        for s in range(self.order):
+            si = etdrk_stage_input(self.order, s)
+            src = uh if si < 0 else S[si]
+            winv_b = self._buf("winv_b", self.n_inv).view(self.n_inv, self.N, self.n, self.Nh)
+            self._pass(nat.SLAB_COL0_INV_PRO, self.n_inv, src, winv_b)
+            winv_a = transpose_b_to_a(winv_b, self.group).contiguous()
+            self._pass(nat.SLAB_COL1_INV_NL, self.n_inv, winv_a, winv_a)
+            wfwd_a = self._buf("wfwd_a", self.n_fwd)
+            self._pass(nat.SLAB_ROW_NL, self.n_inv, winv_a, wfwd_a)
+            self._pass(nat.SLAB_COL1_FWD_NL, self.n_fwd, wfwd_a, wfwd_a)
+            wfwd_b = transpose_a_to_b(wfwd_a, self.group).contiguous()
+            self._pass(nat.SLAB_COL0_FWD_EPI, self.n_fwd, wfwd_b, None, stage=s, U=uh, OUT=out, S=S)
+        return out
+
+    def step(self, u_local):
+        """One step of the physical slab (C, N/P, N, N): fft -> step_fourier -> ifft
+        (exponax/_base_stepper.py:201-220, distributed)."""
+        return self.ifft(self.step_fourier(self.fft(u_local)))
+
+    def repeat(self, u_local, n: int, *, spectral_carry: bool = True):
+        """n steps; with `spectral_carry` (default for the distributed path) the carry stays in
+        Fourier space: 2 all-to-alls per step are saved."""
+        if not spectral_carry:
+            for _ in range(n):
+                u_local = self.step(u_local)
+            return u_local
+        uh = self.fft(u_local)
+        for _ in range(n):
+            uh = self.step_fourier(uh)
+        return self.ifft(uh)
+
+    __call__ = step

@@ -47,6 +47,9 @@ struct exb_plan {
   virtual int step(cudaStream_t st, int64_t batch, const void* in, void* out, void* ws) = 0;
   virtual int rollout(cudaStream_t st, int64_t batch, int64_t n_saved, int substeps, unsigned flags,
                       const void* u0, void* out, void* ws) = 0;
+  virtual int slab_pass(cudaStream_t st, int pass, int nfields, int stage, const void* in, void* out,
+                        const void* U, void* OUT, void* const* S) = 0;
+  virtual void nl_fields(int* ni, int* nf) const = 0;
 };
 
 static void factorize(int N, FftDesc& fd) {
@@ -95,6 +98,8 @@ template <class T> struct PlanImpl : exb_plan {
   long long M;     // modes per channel
   long long G;     // grid points per channel
   int nscr;        // ETDRK scratch states
+  int nranks = 1;  // slab decomposition (3-D): number of ranks, local extent of the split axis
+  int nloc = 0;
   int max_smem = 0;
   int sm_count = 148;
 
@@ -127,6 +132,16 @@ template <class T> struct PlanImpl : exb_plan {
       M *= N;
       G *= N;
     }
+    nranks = desc.slab_nranks > 1 ? desc.slab_nranks : 1;
+    nloc = N;
+    if (nranks > 1) {
+      if (D != 3) return fail(EXB_EINVAL, "slab decomposition needs num_spatial_dims = 3");
+      if (N % nranks != 0) return fail(EXB_EINVAL, "num_points must be divisible by slab_nranks");
+      if (desc.slab_rank < 0 || desc.slab_rank >= nranks) return fail(EXB_EINVAL, "slab_rank out of range");
+      nloc = N / nranks;
+      M = (long long)N * nloc * Nh;  // local spectral slab (N, N/P, Nh) == local half-complex physical slab
+      G = (long long)nloc * N * N;   // local physical slab (N/P, N, N)
+    }
     factorize(N, fd);
     if (fd.nst > EXB_MAX_STAGES) return fail(EXB_EUNSUPPORTED, "too many FFT stages");
 
@@ -152,6 +167,7 @@ template <class T> struct PlanImpl : exb_plan {
     P.inj_val = (T)desc.injection_value;
     P.dscale = (T)(2.0 * M_PI / desc.domain_extent);
     P.scale = (T)desc.nl_scale;
+    P.i1_off = nranks > 1 ? desc.slab_rank * (N / nranks) : 0;
     for (int i = 0; i < EXB_MAX_POLY; ++i) P.poly[i] = (T)desc.poly[i];
     for (int i = 0; i < 3; ++i) P.gen[i] = (T)desc.general_scales[i];
     {
@@ -382,10 +398,10 @@ template <class T> struct PlanImpl : exb_plan {
       p.inner = M / N;
       p.n_outer = 1;
       p.outer_stride = 0;
-    } else {  // 3-D axis 1
+    } else {  // 3-D axis 1 (slab mode: the local physical slab has N/P planes)
       p.line_stride = Nh;
       p.inner = Nh;
-      p.n_outer = N;
+      p.n_outer = nranks > 1 ? nloc : N;
       p.outer_stride = (long long)N * Nh;
     }
   }
@@ -599,6 +615,56 @@ template <class T> struct PlanImpl : exb_plan {
     return EXB_OK;
   }
 
+  // ------------------------------------------------------------------ slab passes
+  void nl_fields(int* ni, int* nf) const override {
+    *ni = P.n_inv;
+    *nf = P.n_fwd;
+  }
+  int slab_pass(cudaStream_t st, int pass, int nfields, int stage, const void* in, void* out, const void* U,
+                void* OUT, void* const* S) override {
+    if (D != 3) return fail(EXB_EINVAL, "exb_slab_pass needs a 3-D plan");
+    const long long rows_stride_c = M;  // per-field stride, half-complex
+    switch (pass) {
+      case EXB_SLAB_ROW_R2C:
+        return row_pass(st, ROW_R2C, 1, nfields, nfields, in, (long long)nfields * G, out, (long long)nfields * rows_stride_c);
+      case EXB_SLAB_ROW_C2R:
+        return row_pass(st, ROW_C2R, 1, nfields, nfields, in, (long long)nfields * rows_stride_c, out, (long long)nfields * G);
+      case EXB_SLAB_COL1_FWD:
+        return col_plain<-1>(st, 1, 1, nfields, (const cpx<T>*)in, (cpx<T>*)out);
+      case EXB_SLAB_COL1_INV:
+        return col_plain<+1>(st, 1, 1, nfields, (const cpx<T>*)in, (cpx<T>*)out);
+      case EXB_SLAB_COL1_FWD_NL:
+        return col_plain<-1>(st, 1, 1, nfields, (const cpx<T>*)in, (cpx<T>*)out, PRUNE_COLS | PRUNE_OUT_ROWS);
+      case EXB_SLAB_COL1_INV_NL:
+        return col_plain<+1>(st, 1, 1, nfields, (const cpx<T>*)in, (cpx<T>*)out, PRUNE_COLS | PRUNE_IN_ROWS);
+      case EXB_SLAB_COL0_FWD:
+        return col_plain<-1>(st, 0, 1, nfields, (const cpx<T>*)in, (cpx<T>*)out);
+      case EXB_SLAB_COL0_INV:
+        return col_plain<+1>(st, 0, 1, nfields, (const cpx<T>*)in, (cpx<T>*)out);
+      case EXB_SLAB_COL0_INV_PRO:
+        return col_inv_pro(st, 1, (const cpx<T>*)in, (cpx<T>*)out);
+      case EXB_SLAB_ROW_NL:
+        return row_pass(st, ROW_NL, 1, P.n_inv, P.n_fwd, in, (long long)P.n_inv * M, out, (long long)P.n_fwd * M);
+      case EXB_SLAB_COL0_FWD_EPI: {
+        if (K.order == 0) {
+          long long total = (long long)C * M;
+          int grid = (int)((total + 255) / 256 < (long long)sm_count * 16 ? (total + 255) / 256 : (long long)sm_count * 16);
+          etdrk0_kernel<T><<<grid, 256, 0, st>>>(K, C, total, (const cpx<T>*)U, (cpx<T>*)OUT);
+          ++launches;
+          CUDA_OK(cudaGetLastError());
+          return EXB_OK;
+        }
+        StateBufs<T> sb;
+        sb.U = (const cpx<T>*)U;
+        sb.OUT = (cpx<T>*)OUT;
+        for (int i = 0; i < 4; ++i) sb.S[i] = S ? (cpx<T>*)S[i] : nullptr;
+        return col_fwd(st, 1, COL_FWD_EPI, stage, (const cpx<T>*)in, nullptr, sb);
+      }
+      default:
+        return fail(EXB_EINVAL, "unknown slab pass %d", pass);
+    }
+  }
+
   // ------------------------------------------------------------------ entry points
   int need_ws(void* ws, int64_t batch) {
     if (workspace_bytes(batch) > 0 && !ws) return fail(EXB_EINVAL, "workspace is NULL but %zu bytes are required", workspace_bytes(batch));
@@ -606,12 +672,14 @@ template <class T> struct PlanImpl : exb_plan {
   }
 
   int fft(cudaStream_t st, int64_t batch, int channels, const void* u, void* uh, void* ws) override {
+    if (nranks > 1) return fail(EXB_EINVAL, "slab plans only support exb_slab_pass");
     if (channels < 1) return fail(EXB_EINVAL, "channels must be >= 1");
     if (D == 1) return launch_1d(st, OP1_FFT, batch * channels, 1, u, uh, 0, 0, 0);
     return fft_nd(st, batch, channels, (const T*)u, (long long)channels * G, (cpx<T>*)uh);
   }
 
   int ifft(cudaStream_t st, int64_t batch, int channels, const void* uh, void* u, void* ws) override {
+    if (nranks > 1) return fail(EXB_EINVAL, "slab plans only support exb_slab_pass");
     if (channels < 1) return fail(EXB_EINVAL, "channels must be >= 1");
     if (D == 1) return launch_1d(st, OP1_IFFT, batch * channels, 1, uh, u, 0, 0, 0);
     if (channels > winv_fields()) return fail(EXB_EUNSUPPORTED, "ifft supports at most %d channels with this plan", winv_fields());
@@ -622,6 +690,7 @@ template <class T> struct PlanImpl : exb_plan {
   }
 
   int nonlinear(cudaStream_t st, int64_t batch, const void* uh, void* out, void* ws) override {
+    if (nranks > 1) return fail(EXB_EINVAL, "slab plans only support exb_slab_pass");
     if (P.kind == EXB_NL_ZERO) {
       CUDA_OK(cudaMemsetAsync(out, 0, (size_t)batch * C * M * sizeof(cpx<T>), st));
       return EXB_OK;
@@ -638,6 +707,7 @@ template <class T> struct PlanImpl : exb_plan {
   }
 
   int step_fourier(cudaStream_t st, int64_t batch, const void* in, void* out, void* ws) override {
+    if (nranks > 1) return fail(EXB_EINVAL, "slab plans only support exb_slab_pass");
     if (D == 1) return launch_1d(st, OP1_STEP_FOURIER, batch, C, in, out, 0, 1, 0);
     int rc = need_ws(ws, batch);
     if (rc) return rc;
@@ -651,6 +721,7 @@ template <class T> struct PlanImpl : exb_plan {
 
   int rollout(cudaStream_t st, int64_t batch, int64_t n_saved, int substeps, unsigned flags, const void* u0,
               void* out, void* ws) override {
+    if (nranks > 1) return fail(EXB_EINVAL, "slab plans only support exb_slab_pass");
     if (n_saved < 0 || substeps < 1) return fail(EXB_EINVAL, "n_saved must be >= 0 and substeps >= 1");
     const bool include_init = flags & EXB_ROLLOUT_INCLUDE_INIT;
     const bool layout_tb = flags & EXB_ROLLOUT_LAYOUT_TB;
@@ -785,5 +856,15 @@ int exb_rollout(exb_plan* plan, void* stream, int64_t batch, int64_t n_saved, in
   return plan->rollout((cudaStream_t)stream, batch, n_saved, substeps, flags, u0, out, ws);
 }
 int64_t exb_launch_count(const exb_plan* plan) { return plan ? plan->launches : 0; }
+int exb_slab_pass(exb_plan* plan, void* stream, int32_t pass, int32_t nfields, int32_t stage, const void* in,
+                  void* out, const void* U, void* OUT, void* const* S) {
+  if (!plan) return fail(EXB_EINVAL, "null plan");
+  return plan->slab_pass((cudaStream_t)stream, pass, nfields, stage, in, out, U, OUT, S);
+}
+int exb_plan_nl_fields(const exb_plan* plan, int32_t* n_inv, int32_t* n_fwd) {
+  if (!plan || !n_inv || !n_fwd) return fail(EXB_EINVAL, "null argument");
+  plan->nl_fields(n_inv, n_fwd);
+  return EXB_OK;
+}
 
 }  // extern "C"

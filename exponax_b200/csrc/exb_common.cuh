@@ -57,6 +57,7 @@ template <class T> struct NlParams {
   T poly[8];
   T gen[3];
   T inv_norm;         // 1/N^D
+  int i1_off;         // slab decomposition (3-D): global axis-1 index of local index 0
 };
 
 // ETDRK coefficient tables (device pointers); E = 1 or C leading extent, M modes each.

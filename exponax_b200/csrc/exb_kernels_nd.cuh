@@ -53,7 +53,7 @@ __device__ __forceinline__ ModeK<T> col_mode(const NlParams<T>& P, int i, long l
   if (P.D == 2) return make_mode(P, i, (int)iw, 0);
   int i1 = (int)(iw / P.Nh);
   int i2 = (int)(iw - (long long)i1 * P.Nh);
-  return make_mode(P, i, i1, i2);
+  return make_mode(P, i, i1 + P.i1_off, i2);
 }
 
 template <class T, int DIR> __global__ void col_pass_kernel(const ColParams<T> p) {

@@ -51,7 +51,7 @@ col_fast_kernel(const ColParams<float> p) {
       col_keep = iwc <= kmax;
     } else {                            // 3-D axis 0: inner = (i1, i2)
       int a1 = (int)(iwc / p.P.Nh), a2 = (int)(iwc - (long long)a1 * p.P.Nh);
-      int k1 = wavenumber_of(a1, N);
+      int k1 = wavenumber_of(a1 + p.P.i1_off, N);
       col_keep = (k1 < 0 ? -k1 : k1) <= kmax && a2 <= kmax;
     }
   }
@@ -85,6 +85,7 @@ col_fast_kernel(const ColParams<float> p) {
   if (S::D == 3) {
     i1 = (int)(iw / Pn.Nh);
     i2 = (int)(iw - (long long)i1 * Pn.Nh);
+    i1 += Pn.i1_off;
   }
 
   if (MODE == COL_INV_PRO) {

@@ -100,6 +100,12 @@ typedef struct exb_desc {
   const void *exp_term;
   const void *half_exp_term;
   const void *coef[6];
+  /* slab decomposition of ONE 3-D field over slab_nranks processes (0/1: none).  Physical slab:
+     (C, N/P, N, N), x-planes [rank*N/P, (rank+1)*N/P); spectral slab: (C, N, N/P, N/2+1), axis-1
+     wavenumber indices [rank*N/P, (rank+1)*N/P).  Coefficient tables are the LOCAL spectral
+     slices (E, N, N/P, N/2+1).  Only exb_slab_pass may be used with such a plan. */
+  int32_t slab_nranks;
+  int32_t slab_rank;
 } exb_desc;
 
 /* thread-local description of the last error on this thread */
@@ -141,6 +147,26 @@ int exb_step(exb_plan *plan, void *stream, int64_t batch, const void *u_in, void
      FINAL_ONLY     out (batch, C, N..N)         (ex.repeat) */
 int exb_rollout(exb_plan *plan, void *stream, int64_t batch, int64_t n_saved, int32_t substeps,
                 uint32_t flags, const void *u0, void *out, void *workspace);
+
+/* ---- slab-decomposed 3-D transforms (one field too large for one GPU) ----
+   One local pass of the distributed step; the caller (exponax_b200/_slab.py) performs the
+   all-to-all transposes between passes with NCCL.  Layout A = physical slab (F, N/P, N, N/2+1 | N),
+   layout B = spectral slab (F, N, N/P, N/2+1).  All buffers are caller-owned device memory. */
+#define EXB_SLAB_ROW_R2C 0      /* in: real (nfields, N/P, N, N)       -> out: A half-complex        */
+#define EXB_SLAB_ROW_C2R 1      /* in: A half-complex                  -> out: real                   */
+#define EXB_SLAB_COL1_FWD 2     /* A, FFT along axis 1, in place when in == out                       */
+#define EXB_SLAB_COL1_INV 3
+#define EXB_SLAB_COL0_FWD 4     /* B, FFT along axis 0                                                */
+#define EXB_SLAB_COL0_INV 5
+#define EXB_SLAB_COL0_INV_PRO 6 /* in: stage input state B (C fields) -> out: n_inv fields B          */
+#define EXB_SLAB_ROW_NL 7       /* in: n_inv fields A                  -> out: n_fwd fields A         */
+#define EXB_SLAB_COL0_FWD_EPI 8 /* in: n_fwd fields B; ETDRK stage update on (U, OUT, S[0..3])        */
+#define EXB_SLAB_COL1_INV_NL 9  /* COL1_INV with dealiasing-aware pruning (inside N(u) only)          */
+#define EXB_SLAB_COL1_FWD_NL 10 /* COL1_FWD with dealiasing-aware pruning (inside N(u) only)          */
+int exb_slab_pass(exb_plan *plan, void *stream, int32_t pass, int32_t nfields, int32_t stage,
+                  const void *in, void *out, const void *U, void *OUT, void *const *S);
+/* number of single-field inverse / forward transforms per N(u) evaluation of this plan */
+int exb_plan_nl_fields(const exb_plan *plan, int32_t *n_inv, int32_t *n_fwd);
 
 /* number of kernel launches issued through this plan so far (bench bookkeeping) */
 int64_t exb_launch_count(const exb_plan *plan);

@@ -80,3 +80,38 @@ def test_single_process_passthrough():
     out = D.sharded_apply(lambda u: u * 2, u0, gather=True)
     np.testing.assert_array_equal(out, u0 * 2)
     assert D.max_over_ranks(3.5) == 3.5
+
+
+# ---------------------------------------------------------------- slab transposes (config c5)
+def _slab_worker(rank, ws, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(ws))
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    try:
+        from exponax_b200._slab import transpose_a_to_b, transpose_b_to_a
+        F, N, K = 3, 8, 5
+        n = N // ws
+        g = torch.arange(F * N * N * K, dtype=torch.float32).reshape(F, N, N, K)
+        g = torch.complex(g, -g)
+        a = g[:, rank * n:(rank + 1) * n].contiguous()       # physical slab: split over axis 0
+        b = g[:, :, rank * n:(rank + 1) * n].contiguous()    # spectral slab: split over axis 1
+        assert torch.equal(transpose_a_to_b(a), b)
+        assert torch.equal(transpose_b_to_a(b), a)
+        assert torch.equal(transpose_b_to_a(transpose_a_to_b(a)), a)
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_slab_transposes_gloo_world2():
+    ws, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_slab_worker, args=(r, ws, port, q)) for r in range(ws)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(ws)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(0, "ok"), (1, "ok")], results

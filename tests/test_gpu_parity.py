@@ -479,3 +479,21 @@ def test_full_size_c4_navier_stokes_128():
     gh = ox.fft(got, num_spatial_dims=3)
     div = np.sum(ox.build_derivative_operator(3, L, N) * gh, axis=0)
     assert np.abs(div).max() / np.abs(gh).max() < 1e-4
+
+
+# ------------------------------------------------------------------ slab-decomposed path (c5)
+@pytest.mark.parametrize("name,N,order", [("NavierStokesVelocity", 16, 2), ("KolmogorovFlowVelocity", 12, 4),
+                                          ("NavierStokesVelocity", 256 // 8, 3)])
+def test_slab_stepper_single_rank_equals_plain(name, N, order):
+    """World size 1: the slab pass sequence (exb_slab_pass) must reproduce the fused single-GPU step."""
+    L, dt = 2 * np.pi, 0.01
+    u0 = ic(3, N, [0], C=3)[0]
+    st = getattr(ex.stepper, name)(3, L, N, dt, order=order)
+    ost = getattr(ox, name)(3, L, N, dt, order=order)
+    slab = ex.SlabStepper(st)
+    got = host(slab.step(slab.scatter(u0)))
+    assert rel(got, ost(u0)) < F32_STEP
+    got3 = host(slab.repeat(slab.scatter(u0), 3))
+    assert rel(got3, ox.repeat(ost, 3)(u0)) < 5e-5
+    uh = host(slab.fft(slab.scatter(u0)))
+    assert rel(uh, ox.fft(u0, num_spatial_dims=3)) < 2e-6

@@ -199,3 +199,15 @@ def test_rollout_generic_callable_cpu():
     assert np.allclose(ex.repeat(g, 3, takes_aux=True, constant_aux=False)(u0, aux), 1 + 0 + 1 + 2)
     b = ex.vmap(ex.rollout(f, 2))(np.ones((5, 1, 4), np.float32))
     assert b.shape == (5, 2, 1, 4)
+
+
+def test_stage_input_table_matches_cuda_source():
+    """exponax_b200/csrc_meta.py mirrors etdrk_stage_input of exb_nl.cuh."""
+    from exponax_b200.csrc_meta import etdrk_stage_input
+    src = open(os.path.join(ROOT, "exponax_b200", "csrc", "exb_nl.cuh")).read()
+    body = src[src.index("inline int etdrk_stage_input"):]
+    body = body[:body.index("}") + 1]
+    assert "if (s == 0) return -1;" in body and "if (order == 4 && s >= 2) return 2;" in body and "return 0;" in body
+    assert [etdrk_stage_input(4, s) for s in range(4)] == [-1, 0, 2, 2]
+    assert [etdrk_stage_input(3, s) for s in range(3)] == [-1, 0, 0]
+    assert [etdrk_stage_input(2, s) for s in range(2)] == [-1, 0]
