@@ -292,8 +292,14 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     abytes = algorithmic_bytes_per_call(w, spectral_carry=args.spectral_carry)
     achieved = abytes / (ms_per_step * 1e-3) / 1e9
+    traffic = None
+    try:  # DRAM bytes per launch/call measured once with `ncu --set full` (profiles/traffic.json)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[args.workload]
+        traffic = tr["bytes_per_trajectory_step"] * B * T
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None,
+                "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json (measured copy bandwidth)" if peaks else "fallback 6.65 TB/s",
                 "algorithmic_bytes_per_call": abytes, "kernel_launches_per_call": launches / args.steps}
     if D == 1:
