@@ -50,7 +50,94 @@ WORKLOADS = {
     "c4": dict(stepper="NavierStokesVelocity", D=3, L=2 * np.pi, N=256, dt=0.005, kw=dict(diffusivity=0.01), C=3,
                B=16, T=2, final_only=True,
                desc="NavierStokesVelocity 3-D 256^3 Taylor-Green ETDRK2, batch 16 per GPU, repeat"),
+    "c5": dict(stepper="KolmogorovFlowVelocity", D=3, L=2 * np.pi, N=2048, dt=1e-3, kw=dict(diffusivity=0.01), C=3,
+               B=1, T=1, final_only=True,
+               desc="KolmogorovFlowVelocity 3-D single field, slab-decomposed FFT with NCCL all-to-all (needs --gpus >= 2)"),
 }
+
+
+def run_c5(args, w, rank, world, local_rank):
+    """Config c5: ONE 3-D field sharded over all ranks (strong scaling by construction)."""
+    import torch
+    import torch.distributed as dist
+
+    import exponax_b200 as ex
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    N, L = w["N"], w["L"]
+    t0 = time.time()
+    with ex.spectral.slab_context(rank, world):
+        stepper = ex.stepper.KolmogorovFlowVelocity(3, L, N, w["dt"], **w["kw"])
+    slab = ex.SlabStepper(stepper)
+    slab.plan()
+    t_ctor = time.time() - t0
+    # Taylor-Green + small-mode perturbation generated on the device, slab by slab (never on the host)
+    n = N // world
+    x = (torch.arange(rank * n, (rank + 1) * n, device="cuda", dtype=torch.float32) * (L / N)).view(n, 1, 1)
+    y = (torch.arange(N, device="cuda", dtype=torch.float32) * (L / N)).view(1, N, 1)
+    z = (torch.arange(N, device="cuda", dtype=torch.float32) * (L / N)).view(1, 1, N)
+    u = torch.empty((3, n, N, N), dtype=torch.float32, device="cuda")
+    u[0] = torch.sin(x) * torch.cos(y) * torch.cos(z)
+    u[1] = -torch.cos(x) * torch.sin(y) * torch.cos(z)
+    u[2] = 0.05 * torch.sin(2 * x) * torch.cos(3 * y) * torch.ones_like(z)
+    uh = slab.fft(u)
+    del u
+    slab.release_buffers()
+    for _ in range(args.warmup):
+        uh = slab.step_fourier(uh, inplace=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = slab.plan().launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        uh = slab.step_fourier(uh, inplace=True)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    finite = bool(torch.isfinite(torch.view_as_real(uh)).all())
+    energy = torch.tensor([float((uh.abs() ** 2).sum())], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(energy)
+    launches = slab.plan().launch_count() - launches0
+    mem_gb = torch.cuda.max_memory_allocated() / 1e9
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        F = 4 * N**3
+        abytes = 90 * F                       # pass model per ETDRK2 step (SURVEY 8d), whole field
+        per_gpu = abytes / world / (total_ms / args.steps * 1e-3) / 1e9
+        # all-to-all: 2 stages x (6 inverse + 3 forward) field transposes, (P-1)/P of each slab leaves the GPU
+        a2a = 2 * 9 * (N * n * (N // 2 + 1) * 8) * (world - 1) / max(world, 1)
+        line = {"metric": "ETDRK grid-point*steps/s", "value": N**3 * args.steps / (total_ms * 1e-3),
+                "unit": "grid-point*steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"c5: {w['desc']}", "N": N, "D": 3, "order": 2, "channels": 3,
+                           "parallelism": f"slab decomposition x{world}, all_to_all_single (NCCL)",
+                           "carry": "spectral (step_fourier loop)"},
+                "roofline": {"bound": "hbm", "achieved": per_gpu, "peak": peak, "unit": "GB/s", "frac": per_gpu / peak,
+                             "traffic": None, "algorithmic_bytes_per_step_all_gpus": abytes,
+                             "alltoall_bytes_per_gpu_per_step": a2a,
+                             "alltoall_GBs_per_gpu": a2a / (total_ms / args.steps * 1e-3) / 1e9},
+                "cpu_baseline": None, "e2e": None, "gpu_launches": int(launches), "finite": finite,
+                "spectral_energy": float(energy.item()), "ctor_seconds": t_ctor, "max_mem_gb_rank0": mem_gb}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def algorithmic_bytes_per_call(w, itemsize=4, spectral_carry=False):
@@ -189,6 +276,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--spectral-carry", action="store_true")
+    ap.add_argument("--N", type=int, default=None, help="override the grid size (c5)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -199,6 +287,10 @@ def main():
         w["B"] = args.batch
     if args.T:
         w["T"] = args.T
+    if args.N:
+        w["N"] = args.N
+    if args.workload == "c5" and args.impl == "exb":
+        return run_c5(args, w, rank, world, local_rank)
     args.warmup = max(args.warmup, 3) if args.impl == "exb" else args.warmup
     N, D, C, B, T = w["N"], w["D"], w["C"], w["B"], w["T"]
     config = {"workload": f"{args.workload}: {w['desc']}", "stepper": w["stepper"], "N": N, "D": D,

@@ -40,6 +40,7 @@ class BaseStepper(ABC):
         self.num_channels = num_channels
         self.dx = domain_extent / num_points
         self._dtype = real_dtype()
+        self._slab = sp.current_slab()  # (rank, nranks) when built inside ex.spectral.slab_context
 
         derivative_operator = sp.build_derivative_operator(num_spatial_dims, domain_extent, num_points,
                                                            dtype=self._dtype)
@@ -85,6 +86,8 @@ class BaseStepper(ABC):
         """The libexb plan of this stepper, or None when the nonlinear function is user code."""
         if self._native is False:
             return None
+        if self._slab is not None:
+            raise RuntimeError("this stepper was built inside a slab_context: use it through ex.SlabStepper")
         p = self._integrator._plan(self.num_channels, self.num_points, self.domain_extent)
         self._native = p is not None
         return p

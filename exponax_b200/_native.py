@@ -49,6 +49,8 @@ class ExbDesc(C.Structure):
         ("coef", C.c_void_p * 6),
         ("slab_nranks", C.c_int32),
         ("slab_rank", C.c_int32),
+        ("tables_on_device", C.c_int32),
+        ("reserved1", C.c_int32),
     ]
 
 
@@ -94,6 +96,11 @@ def lib():
                     fn.argtypes = args
                 _lib = l
     return _lib
+
+
+def _torch():
+    import torch
+    return torch
 
 
 class ExbError(RuntimeError):
@@ -147,7 +154,16 @@ class Plan:
         d.slab_nranks, d.slab_rank = int(slab[0]), int(slab[1])
         self._keep = []
 
+        on_device = hasattr(exp_term, "is_cuda") and exp_term.is_cuda
+        d.tables_on_device = int(on_device)
+
         def host(a, dt):
+            if on_device:  # torch CUDA tensors: passed by device pointer, kept alive by the plan
+                t = a.contiguous()
+                assert t.is_cuda and t.dtype == {np.complex64: _torch().complex64, np.complex128: _torch().complex128,
+                                                 np.float32: _torch().float32, np.float64: _torch().float64}[dt]
+                self._keep.append(t)
+                return t.data_ptr()
             a = np.ascontiguousarray(np.asarray(a), dtype=dt)
             self._keep.append(a)
             return a.ctypes.data
@@ -159,7 +175,8 @@ class Plan:
             d.coef[i] = host(c, rd)
         self.handle = C.c_void_p()
         check(lib().exb_plan_create(C.byref(d), C.byref(self.handle)))
-        self._keep = None  # tables are on the device now
+        if not on_device:
+            self._keep = None  # tables were copied to the device
         self.dtype = rd
         self.D, self.N, self.C, self.order = D, N, C_, order
 

@@ -34,28 +34,41 @@ def _group_info(group):
     return 0, 1
 
 
-def transpose_a_to_b(x: torch.Tensor, group=None) -> torch.Tensor:
-    """(F, n, N, K) split over x-planes  ->  (F, N, n, K) split over axis-1 indices (n = N/P)."""
+def transpose_a_to_b(x: torch.Tensor, group=None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """(F, n, N, K) split over x-planes  ->  (F, N, n, K) split over axis-1 indices (n = N/P).
+    Field by field (bounded temporaries): one pack copy + one all-to-all, received in place."""
     rank, P = _group_info(group)
     F, n, N, K = x.shape
     if P == 1:
-        return x
-    send = x.view(F, n, P, n, K).permute(2, 0, 1, 3, 4).contiguous()        # [dest][F][x][k1][K]
-    recv = torch.empty_like(send)
-    dist.all_to_all_single(recv, send, group=group)                        # [src][F][x_src][k1][K]
-    return recv.permute(1, 0, 2, 3, 4).reshape(F, N, n, K)                  # x_global = src*n + x
+        if out is None:
+            return x
+        out.view(-1).copy_(x.reshape(-1))
+        return out
+    if out is None:
+        out = torch.empty((F, N, n, K), dtype=x.dtype, device=x.device)
+    for f in range(F):
+        send = x[f].view(n, P, n, K).permute(1, 0, 2, 3).contiguous()      # [dest][x][k1][K]
+        dist.all_to_all_single(out[f].view(P, n, n, K), send, group=group)  # [src][x_src][k1][K]: x_global = src*n + x
+    return out
 
 
-def transpose_b_to_a(x: torch.Tensor, group=None) -> torch.Tensor:
-    """(F, N, n, K) split over axis-1 indices  ->  (F, n, N, K) split over x-planes."""
+def transpose_b_to_a(x: torch.Tensor, group=None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """(F, N, n, K) split over axis-1 indices  ->  (F, n, N, K) split over x-planes.
+    Field by field: the send side is already contiguous per destination, one unpack copy."""
     rank, P = _group_info(group)
     F, N, n, K = x.shape
     if P == 1:
-        return x
-    send = x.view(F, P, n, n, K).permute(1, 0, 2, 3, 4).contiguous()        # [dest][F][x][k1][K]
-    recv = torch.empty_like(send)
-    dist.all_to_all_single(recv, send, group=group)                        # [src][F][x][k1_src][K]
-    return recv.permute(1, 2, 0, 3, 4).reshape(F, n, N, K)                  # k1_global = src*n + k1
+        if out is None:
+            return x
+        out.view(-1).copy_(x.reshape(-1))
+        return out
+    if out is None:
+        out = torch.empty((F, n, N, K), dtype=x.dtype, device=x.device)
+    recv = torch.empty((P, n, n, K), dtype=x.dtype, device=x.device)
+    for f in range(F):
+        dist.all_to_all_single(recv, x[f].view(P, n, n, K), group=group)   # [src][x][k1_src][K]
+        out[f].view(n, P, n, K).copy_(recv.permute(1, 0, 2, 3))             # k1_global = src*n + k1
+    return out
 
 
 class SlabStepper:
@@ -78,6 +91,13 @@ class SlabStepper:
 
     # ---- plan with the LOCAL slices of the coefficient tables --------------------------------
     def _local(self, arr):
+        if self.stepper._slab is not None:  # built inside ex.spectral.slab_context: already local
+            if tuple(self.stepper._slab) != (self.rank, self.P):
+                raise ValueError(f"stepper was built for slab {self.stepper._slab}, process group says "
+                                 f"{(self.rank, self.P)}")
+            return arr if hasattr(arr, "is_cuda") else np.ascontiguousarray(arr)
+        if hasattr(arr, "is_cuda"):
+            return arr[:, :, self.rank * self.n:(self.rank + 1) * self.n, :].contiguous()
         lo, hi = self.rank * self.n, (self.rank + 1) * self.n
         return np.ascontiguousarray(arr[:, :, lo:hi, :])
 
@@ -98,6 +118,11 @@ class SlabStepper:
             self.n_inv, self.n_fwd = ni.value, nf.value
             self.order = order if desc.get("kind") != nat.NL_ZERO else 0
         return self._plan
+
+    def release_buffers(self):
+        """Drop the cached work buffers (they are re-created on demand)."""
+        self._bufs.clear()
+        torch.cuda.empty_cache()
 
     def _buf(self, name, nfields, real=False):
         key = (name, nfields, real)
@@ -156,26 +181,33 @@ class SlabStepper:
         return out
 
     # ---- time stepping --------------------------------------------------------------------------
-    def step_fourier(self, uh):
-        """One ETDRK step on the local spectral slab (C, N, N/P, N/2+1); returns a new tensor."""
+    def step_fourier(self, uh, *, inplace: bool = False):
+        """One ETDRK step on the local spectral slab (C, N, N/P, N/2+1).  `inplace=True` overwrites
+        `uh` (each mode is read before it is written) -- what long runs use to save memory."""
         self.plan()
         uh = uh.contiguous()
-        out = torch.empty_like(uh)
+        out = uh if inplace else torch.empty_like(uh)
         if self.order == 0:
             self._pass(nat.SLAB_COL0_FWD_EPI, 0, None, None, U=uh, OUT=out)
             return out
-        S = [torch.empty_like(uh) for _ in range(self.order)] + [None] * (4 - self.order)
+        S = [self._buf(f"S{i}", self.Cn).view(self.Cn, self.N, self.n, self.Nh) for i in range(self.order)]
+        S += [None] * (4 - self.order)
+        # the B-layout buffer is shared by the inverse fields and (later in the stage) the forward fields
+        nb = max(self.n_inv, self.n_fwd)
+        wb = self._buf("w_b", nb)
+        winv_b = wb[:self.n_inv].view(self.n_inv, self.N, self.n, self.Nh)
+        wfwd_b = wb[:self.n_fwd].view(self.n_fwd, self.N, self.n, self.Nh)
+        winv_a = self._buf("winv_a", self.n_inv)
+        wfwd_a = self._buf("wfwd_a", self.n_fwd)
         for s in range(self.order):
             si = etdrk_stage_input(self.order, s)
             src = uh if si < 0 else S[si]
-            winv_b = self._buf("winv_b", self.n_inv).view(self.n_inv, self.N, self.n, self.Nh)
             self._pass(nat.SLAB_COL0_INV_PRO, self.n_inv, src, winv_b)
-            winv_a = transpose_b_to_a(winv_b, self.group).contiguous()
+            transpose_b_to_a(winv_b, self.group, out=winv_a)
             self._pass(nat.SLAB_COL1_INV_NL, self.n_inv, winv_a, winv_a)
-            wfwd_a = self._buf("wfwd_a", self.n_fwd)
             self._pass(nat.SLAB_ROW_NL, self.n_inv, winv_a, wfwd_a)
             self._pass(nat.SLAB_COL1_FWD_NL, self.n_fwd, wfwd_a, wfwd_a)
-            wfwd_b = transpose_a_to_b(wfwd_a, self.group).contiguous()
+            transpose_a_to_b(wfwd_a, self.group, out=wfwd_b)
             self._pass(nat.SLAB_COL0_FWD_EPI, self.n_fwd, wfwd_b, None, stage=s, U=uh, OUT=out, S=S)
         return out
 
@@ -193,7 +225,7 @@ class SlabStepper:
             return u_local
         uh = self.fft(u_local)
         for _ in range(n):
-            uh = self.step_fourier(uh)
+            uh = self.step_fourier(uh, inplace=True)
         return self.ifft(uh)
 
     __call__ = step

@@ -16,12 +16,54 @@ from . import _native as nat
 from ._config import complex_dtype, real_dtype
 
 
+# ---- slab context (config c5): constructors build only the LOCAL spectral slab -------------------
+_SLAB = None  # (rank, nranks): 3-D spectral arrays are restricted to axis-1 indices of this rank
+
+
+class slab_context:
+    """`with ex.spectral.slab_context(rank, nranks): stepper = ex.stepper.X(3, L, N, dt)` builds
+    every spectral array of the stepper (operators, masks, ETDRK tables, injection) only on the
+    local spectral slab (N, N/nranks, N/2+1) -- all of them are elementwise in the mode index, so
+    restricting the wavenumber grid is enough.  The reference cannot construct 2048^3 operators on
+    one device at all."""
+
+    def __init__(self, rank: int, nranks: int):
+        self.slab = (int(rank), int(nranks))
+
+    def __enter__(self):
+        global _SLAB
+        self._prev, _SLAB = _SLAB, self.slab
+        return self
+
+    def __exit__(self, *exc):
+        global _SLAB
+        _SLAB = self._prev
+        return False
+
+
+def current_slab():
+    return _SLAB
+
+
+def _slab_slice(vec, num_spatial_dims, num_points):
+    """restrict the axis-1 grid vector of a 3-D array to the local slab"""
+    if _SLAB is None or num_spatial_dims != 3:
+        return vec
+    rank, nranks = _SLAB
+    if num_points % nranks:
+        raise ValueError(f"num_points={num_points} must be divisible by the number of slab ranks ({nranks})")
+    n = num_points // nranks
+    return vec[rank * n:(rank + 1) * n]
+
+
 def build_wavenumbers(num_spatial_dims: int, num_points: int, *, indexing: str = "ij", dtype=None):
     """exponax/_spectral.py:13-49."""
     dtype = real_dtype() if dtype is None else dtype
     right = np.fft.rfftfreq(num_points, 1 / num_points).astype(dtype)
     other = np.fft.fftfreq(num_points, 1 / num_points).astype(dtype)
     grids = [other] * (num_spatial_dims - 1) + [right]
+    if num_spatial_dims == 3:
+        grids[1] = _slab_slice(other, 3, num_points)
     return np.stack(np.meshgrid(*grids, indexing=indexing))
 
 
@@ -73,7 +115,9 @@ def spatial_shape(num_spatial_dims: int, num_points: int):
 
 
 def wavenumber_shape(num_spatial_dims: int, num_points: int):
-    """exponax/_spectral.py:254-275."""
+    """exponax/_spectral.py:254-275 (the local slab shape inside a `slab_context`)."""
+    if _SLAB is not None and num_spatial_dims == 3:
+        return (num_points, num_points // _SLAB[1], num_points // 2 + 1)
     return (num_points,) * (num_spatial_dims - 1) + (num_points // 2 + 1,)
 
 
@@ -117,6 +161,8 @@ def build_scaling_array(num_spatial_dims, num_points, *,
         right = np.where(right_wn == num_points // 2, num_points, right)
         other = np.where(other_wn == -num_points // 2, num_points, other)
     grids = [other] * (num_spatial_dims - 1) + [right]
+    if num_spatial_dims == 3:
+        grids[1] = _slab_slice(other, 3, num_points)
     return np.prod(np.stack(np.meshgrid(*grids, indexing=indexing)), axis=0, keepdims=True).astype(dtype)
 
 

@@ -102,12 +102,18 @@ template <class T> struct PlanImpl : exb_plan {
   int nloc = 0;
   int max_smem = 0;
   int sm_count = 148;
+  const void* twiddle_host_tmp = nullptr;
 
   ~PlanImpl() override {
     for (void* p : d_allocs) cudaFree(p);
   }
 
+  bool tables_on_device = false;
   int upload(const void* host, size_t bytes, void** dev) {
+    if (tables_on_device && host != (const void*)twiddle_host_tmp) {  // caller-owned device table
+      *dev = const_cast<void*>(host);
+      return EXB_OK;
+    }
     CUDA_OK(cudaMalloc(dev, bytes));
     d_allocs.push_back(*dev);
     CUDA_OK(cudaMemcpy(*dev, host, bytes, cudaMemcpyHostToDevice));
@@ -116,6 +122,7 @@ template <class T> struct PlanImpl : exb_plan {
 
   int init(const exb_desc& desc) {
     d = desc;
+    tables_on_device = desc.tables_on_device != 0;
     D = desc.num_spatial_dims;
     N = desc.num_points;
     C = desc.num_channels;
@@ -240,7 +247,9 @@ template <class T> struct PlanImpl : exb_plan {
         long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)j / (long double)N;
         tw[j] = cpx<T>((T)cosl(a), (T)sinl(a));
       }
+      twiddle_host_tmp = tw.data();
       int rc = upload(tw.data(), sizeof(cpx<T>) * N, (void**)&d_tw);
+      twiddle_host_tmp = nullptr;
       if (rc) return rc;
     }
     // ---- ETDRK coefficients ----

@@ -18,6 +18,8 @@ from .. import _native as nat
 from .. import _spectral as sp
 from ._utils import roots_of_unity
 
+GPU_TABLE_THRESHOLD = 1 << 26  # modes; above this the ETDRK tables are built on the GPU
+
 
 class BaseETDRK(ABC):
     dt: float
@@ -32,7 +34,14 @@ class BaseETDRK(ABC):
         self._cd = linear_operator.dtype
         self._rd = linear_operator.real.dtype.type
         self._linear_operator = linear_operator
-        self._exp_term = np.exp(self._rd(dt) * linear_operator).astype(self._cd)
+        # Grids whose tables take minutes in NumPy (config c5: > 1e8 modes per rank) build them with
+        # the same formulas on the GPU; the tables then stay on the device (tables_on_device).
+        self._on_gpu = linear_operator.size >= GPU_TABLE_THRESHOLD and A.torch.cuda.is_available()
+        if self._on_gpu:
+            self._L_dev = A.torch.as_tensor(linear_operator, device="cuda")
+            self._exp_term = A.torch.exp(self._rd(dt) * self._L_dev)
+        else:
+            self._exp_term = np.exp(self._rd(dt) * linear_operator).astype(self._cd)
         self._nonlinear_fun = None
         self._plans = {}
         self._dev_coefs = {}
@@ -43,6 +52,19 @@ class BaseETDRK(ABC):
         over the roots (exponax/etdrk/_etdrk_2.py:74-89)."""
         rd, cd = self._rd, self._cd
         roots = roots_of_unity(num_circle_points, rd)
+        if self._on_gpu:
+            t = A.torch
+            L_dt = self._L_dev * rd(self.dt)
+            accs = [t.zeros_like(L_dt.real) for _ in fns]
+            need_half = getattr(self, "_needs_half_exp", True)
+            for root in roots:
+                lr = L_dt + complex(rd(circle_radius) * root)
+                exp_lr = t.exp(lr)
+                exp_lr_half = t.exp(lr / 2) if need_half else None
+                for i, f in enumerate(fns):
+                    accs[i] += f(lr, exp_lr, exp_lr_half).real
+                del lr, exp_lr, exp_lr_half
+            return [(a / rd(num_circle_points)) * rd(self.dt) for a in accs]
         L_dt = (self._linear_operator * rd(self.dt)).astype(cd)
         accs = [np.zeros_like(L_dt.real) for _ in fns]
         for root in roots:

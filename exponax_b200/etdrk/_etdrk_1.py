@@ -10,6 +10,7 @@ class ETDRK1(BaseETDRK):
                  circle_radius: float = 1.0):
         super().__init__(dt, linear_operator)
         self._nonlinear_fun = nonlinear_fun
+        self._needs_half_exp = False
         (self._coef_1,) = self._contour_means([lambda lr, e, eh: (e - 1) / lr], num_circle_points, circle_radius)
 
     def _coef_list(self):

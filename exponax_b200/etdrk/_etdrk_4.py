@@ -1,5 +1,6 @@
 import numpy as np
 
+from .. import _array as A
 from ._base_etdrk import BaseETDRK
 
 
@@ -12,7 +13,10 @@ class ETDRK4(BaseETDRK):
                  circle_radius: float = 1.0):
         super().__init__(dt, linear_operator)
         self._nonlinear_fun = nonlinear_fun
-        self._half_exp_term = np.exp(self._rd(0.5) * self._rd(dt) * self._linear_operator).astype(self._cd)
+        if self._on_gpu:
+            self._half_exp_term = A.torch.exp(self._rd(0.5) * self._rd(dt) * self._L_dev)
+        else:
+            self._half_exp_term = np.exp(self._rd(0.5) * self._rd(dt) * self._linear_operator).astype(self._cd)
         (self._coef_1, self._coef_4, self._coef_5, self._coef_6) = self._contour_means(
             [
                 lambda lr, e, eh: (eh - 1) / lr,

@@ -41,6 +41,7 @@ class ProjectedConvection3dKolmogorov(ProjectedConvection3d):
                          dealiasing_fraction=dealiasing_fraction)
         self.injection_mode = injection_mode
         self.injection_scale = injection_scale
+        self._slab = sp.current_slab()
         wavenumbers = sp.build_wavenumbers(num_spatial_dims, num_points, dtype=self._dtype)
         injection_mask = (wavenumbers[0] == 0) & (wavenumbers[1] == injection_mode) & (wavenumbers[2] == 0)
         injection_single = np.where(
@@ -55,7 +56,11 @@ class ProjectedConvection3dKolmogorov(ProjectedConvection3d):
     def _injection(self):
         nz = np.argwhere(self.injection[0] != 0)
         if len(nz) == 0:
-            return None
+            return None  # (inside a slab_context: the forced mode lives on another rank)
         assert len(nz) == 1
         idx = tuple(int(i) for i in nz[0])
-        return idx, float(self.injection[0][idx])
+        val = float(self.injection[0][idx])
+        slab = sp.current_slab() if self._slab is None else self._slab
+        if slab is not None:  # the kernels compare GLOBAL mode indices
+            idx = (idx[0], idx[1] + slab[0] * (self.num_points // slab[1]), idx[2])
+        return idx, val

@@ -106,6 +106,10 @@ typedef struct exb_desc {
      slices (E, N, N/P, N/2+1).  Only exb_slab_pass may be used with such a plan. */
   int32_t slab_nranks;
   int32_t slab_rank;
+  /* non-zero: exp_term / half_exp_term / coef[] are DEVICE pointers that stay valid for the life of
+     the plan (tables built on the GPU for grids whose tables do not fit the host comfortably) */
+  int32_t tables_on_device;
+  int32_t reserved1;
 } exb_desc;
 
 /* thread-local description of the last error on this thread */
