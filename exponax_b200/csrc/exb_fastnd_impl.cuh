@@ -61,38 +61,54 @@ int launch_row(cudaStream_t st, const RowParams<float>& p, const char** err) {
   return EXB_OK;
 }
 
-template <int N, int TW> int col_n(cudaStream_t st, const ColParams<float>& p, int dir, long long grid, const char** err) {
+template <int N, int TW, bool VORT = true, bool PROJ = true> int col_n(cudaStream_t st, const ColParams<float>& p, int dir, long long grid, const char** err) {
   const int kind = p.P.kind;
   switch (p.mode) {
     case COL_PLAIN:
       return dir < 0 ? launch_col<N, TW, SPlain, 1, COL_PLAIN, -1>(st, p, grid, err)
                      : launch_col<N, TW, SPlain, 1, COL_PLAIN, +1>(st, p, grid, err);
     case COL_INV_PRO:
-      if (kind == EXB_NL_VORTICITY_2D) return launch_col<N, TW, SVort, 1, COL_INV_PRO, +1>(st, p, grid, err);
-      if (kind == EXB_NL_PROJECTED_3D) return launch_col<N, TW, SProj, 3, COL_INV_PRO, +1>(st, p, grid, err);
+      if constexpr (VORT) {
+        if (kind == EXB_NL_VORTICITY_2D) return launch_col<N, TW, SVort, 1, COL_INV_PRO, +1>(st, p, grid, err);
+      }
+      if constexpr (PROJ) {
+        if (kind == EXB_NL_PROJECTED_3D) return launch_col<N, TW, SProj, 3, COL_INV_PRO, +1>(st, p, grid, err);
+      }
       break;
     case COL_FWD_EPI:
-      if (kind == EXB_NL_VORTICITY_2D) return launch_col<N, TW, SVort, 1, COL_FWD_EPI, -1>(st, p, grid, err);
-      if (kind == EXB_NL_PROJECTED_3D) return launch_col<N, TW, SProj, 3, COL_FWD_EPI, -1>(st, p, grid, err);
+      if constexpr (VORT) {
+        if (kind == EXB_NL_VORTICITY_2D) return launch_col<N, TW, SVort, 1, COL_FWD_EPI, -1>(st, p, grid, err);
+      }
+      if constexpr (PROJ) {
+        if (kind == EXB_NL_PROJECTED_3D) return launch_col<N, TW, SProj, 3, COL_FWD_EPI, -1>(st, p, grid, err);
+      }
       break;
     case COL_FWD_NL:
-      if (kind == EXB_NL_VORTICITY_2D) return launch_col<N, TW, SVort, 1, COL_FWD_NL, -1>(st, p, grid, err);
-      if (kind == EXB_NL_PROJECTED_3D) return launch_col<N, TW, SProj, 3, COL_FWD_NL, -1>(st, p, grid, err);
+      if constexpr (VORT) {
+        if (kind == EXB_NL_VORTICITY_2D) return launch_col<N, TW, SVort, 1, COL_FWD_NL, -1>(st, p, grid, err);
+      }
+      if constexpr (PROJ) {
+        if (kind == EXB_NL_PROJECTED_3D) return launch_col<N, TW, SProj, 3, COL_FWD_NL, -1>(st, p, grid, err);
+      }
       break;
   }
   *err = "fast N-D column pass: unsupported configuration";
   return EXB_EUNSUPPORTED;
 }
 
-template <int N> int row_n(cudaStream_t st, const RowParams<float>& p, const char** err) {
+template <int N, bool VORT = true, bool PROJ = true> int row_n(cudaStream_t st, const RowParams<float>& p, const char** err) {
   switch (p.mode) {
     case ROW_R2C:
       return launch_row<N, SPlain, 1, 1, ROW_R2C>(st, p, err);
     case ROW_C2R:
       return launch_row<N, SPlain, 1, 1, ROW_C2R>(st, p, err);
     case ROW_NL:
-      if (p.P.kind == EXB_NL_VORTICITY_2D) return launch_row<N, SVort, 4, 1, ROW_NL>(st, p, err);
-      if (p.P.kind == EXB_NL_PROJECTED_3D) return launch_row<N, SProj, 6, 3, ROW_NL>(st, p, err);
+      if constexpr (VORT) {
+        if (p.P.kind == EXB_NL_VORTICITY_2D) return launch_row<N, SVort, 4, 1, ROW_NL>(st, p, err);
+      }
+      if constexpr (PROJ) {
+        if (p.P.kind == EXB_NL_PROJECTED_3D) return launch_row<N, SProj, 6, 3, ROW_NL>(st, p, err);
+      }
       break;
   }
   *err = "fast N-D row pass: unsupported configuration";

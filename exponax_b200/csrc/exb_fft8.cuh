@@ -15,33 +15,69 @@ template <int DIR, int R> __device__ __forceinline__ void dft_small(cpx<float>* 
   if (R == 2) dft2<float, DIR>(a[0], a[1]);
 }
 
+// Pass structure: N = 64: 8 x 8;  N = 128/256/512: 8 x 8 x (N/64);  N = 1024/2048: 8 x 8 x 8 x (N/512).
+template <int N> struct Fft8Cfg {
+  static constexpr int P = N / 8;
+  static constexpr int NP = N == 64 ? 2 : (N <= 512 ? 3 : 4);          // number of passes
+  static constexpr int RL = N == 64 ? 8 : (N <= 512 ? N / 64 : N / 512);  // radix of the last pass
+};
+
 // Twiddle table (shared memory, forward sign), arranged per pass so that the lanes of a warp
 // read consecutive entries (bank-conflict free):
-//   T2[(r-1)*8 + k]        = w_64^(k*r)    r = 1..7, k = 0..7          (pass 2)
-//   T3[(r-1)*64 + b]       = w_N^(b*r)     r = 1..R3-1, b = 0..63      (pass 3), T3 = T2 + 56
+//   T2[(r-1)*8 + k]    = w_64^(k*r)        r = 1..7, k = 0..7                     (pass 2)
+//   3 passes: T3[(r-1)*64 + b]  = w_N^(b*r)    r = 1..RL-1, b = 0..63             (pass 3, last)
+//   4 passes: T3[(r-1)*64 + k]  = w_512^(k*r)  r = 1..7,    k = 0..63             (pass 3)
+//             T4[(r-1)*512 + b] = w_N^(b*r)    r = 1..RL-1, b = 0..511            (pass 4, last)
 template <int N> struct Fft8Tw {
-  static constexpr int R3 = N / 64;
-  static constexpr int SIZE = 56 + (R3 > 1 ? (R3 - 1) * 64 : 0);
+  using Cfg = Fft8Cfg<N>;
+  static constexpr int T3 = 56;
+  static constexpr int N3 = Cfg::NP == 2 ? 0 : (Cfg::NP == 3 ? (Cfg::RL - 1) * 64 : 7 * 64);
+  static constexpr int T4 = T3 + N3;
+  static constexpr int N4 = Cfg::NP == 4 ? (Cfg::RL - 1) * 512 : 0;
+  static constexpr int SIZE = T4 + N4;
   // roots: the N-th roots of unity exp(-2 pi i j / N) in global memory
   static __device__ __forceinline__ void fill(cpx<float>* t, const cpx<float>* __restrict__ roots) {
     for (int q = threadIdx.x; q < SIZE; q += blockDim.x) {
-      if (q < 56) {
+      if (q < T3) {
         int r = q / 8 + 1, k = q % 8;
         t[q] = roots[(N / 64) * k * r];
+      } else if (q < T4) {
+        int r = (q - T3) / 64 + 1, b = (q - T3) % 64;
+        t[q] = roots[(Cfg::NP == 4 ? (N / 512) : 1) * b * r];
       } else {
-        int r = (q - 56) / 64 + 1, b = (q - 56) % 64;
+        int r = (q - T4) / 512 + 1, b = (q - T4) % 512;
         t[q] = roots[b * r];
       }
     }
   }
 };
 
+// last pass: radix RL with Ns = N / RL; 8/RL butterflies per thread, results stay in registers
+template <int N, int DIR, int TOFF>
+__device__ __forceinline__ void fft8_last_pass(cpx<float> (&v)[8], int j, const cpx<float>* __restrict__ tw) {
+  constexpr int P = N / 8, RL = Fft8Cfg<N>::RL, NS = N / RL, NB = 8 / RL;
+#pragma unroll
+  for (int i = 0; i < NB; ++i) {
+    const int b = j + P * i;
+    cpx<float> a[RL];
+#pragma unroll
+    for (int r = 0; r < RL; ++r) {
+      a[r] = v[i + NB * r];
+      if (r > 0) a[r] = a[r] * twd<float, DIR>(tw[TOFF + (r - 1) * NS + b]);
+    }
+    dft_small<DIR, RL>(a);
+#pragma unroll
+    for (int r = 0; r < RL; ++r) v[i + NB * r] = a[r];
+  }
+}
+
 // Ex: struct with  void st(int i, cpx<float>) const;  cpx<float> ld(int i) const;  void sync() const;
 template <int N, int DIR, class Ex>
 __device__ __forceinline__ void fft8_run(cpx<float> (&v)[8], const Ex& ex, int j, const cpx<float>* __restrict__ tw) {
-  constexpr int P = N / 8;
-  constexpr int R3 = N / 64;  // radix of the third pass (1: none)
-  static_assert(N == 64 || N == 128 || N == 256 || N == 512, "fft8_run: unsupported N");
+  using Cfg = Fft8Cfg<N>;
+  using Tw = Fft8Tw<N>;
+  constexpr int P = Cfg::P;
+  static_assert(N == 64 || N == 128 || N == 256 || N == 512 || N == 1024 || N == 2048, "fft8_run: unsupported N");
   // ---- pass 1: radix 8, Ns = 1 ----
   dft8<float, DIR>(v);
   ex.sync();
@@ -56,7 +92,7 @@ __device__ __forceinline__ void fft8_run(cpx<float> (&v)[8], const Ex& ex, int j
 #pragma unroll
     for (int r = 1; r < 8; ++r) v[r] = v[r] * twd<float, DIR>(tw[(r - 1) * 8 + k]);
     dft8<float, DIR>(v);
-    if (R3 == 1) return;  // N = 64: outputs already at j + 8*r
+    if (Cfg::NP == 2) return;  // N = 64: outputs already at j + 8*r
     const int j0 = (j - k) * 8 + k;
     ex.sync();
 #pragma unroll
@@ -65,23 +101,25 @@ __device__ __forceinline__ void fft8_run(cpx<float> (&v)[8], const Ex& ex, int j
 #pragma unroll
     for (int q = 0; q < 8; ++q) v[q] = ex.ld(j + P * q);
   }
-  // ---- pass 3: radix R3, Ns = 64; 8/R3 butterflies per thread, results stay in registers ----
-  if (R3 > 1) {
-    constexpr int NB = 8 / (R3 > 1 ? R3 : 8);
-#pragma unroll
-    for (int i = 0; i < NB; ++i) {
-      const int b = j + P * i;
-      cpx<float> a[R3 > 1 ? R3 : 1];
-#pragma unroll
-      for (int r = 0; r < R3; ++r) {
-        a[r] = v[i + NB * r];
-        if (r > 0) a[r] = a[r] * twd<float, DIR>(tw[56 + (r - 1) * 64 + b]);
-      }
-      dft_small<DIR, R3>(a);
-#pragma unroll
-      for (int r = 0; r < R3; ++r) v[i + NB * r] = a[r];
-    }
+  if (Cfg::NP == 3) {
+    fft8_last_pass<N, DIR, Tw::T3>(v, j, tw);
+    return;
   }
+  // ---- pass 3 of 4: radix 8, Ns = 64 ----
+  {
+    const int k = j & 63;
+#pragma unroll
+    for (int r = 1; r < 8; ++r) v[r] = v[r] * twd<float, DIR>(tw[Tw::T3 + (r - 1) * 64 + k]);
+    dft8<float, DIR>(v);
+    const int j0 = (j - k) * 8 + k;
+    ex.sync();
+#pragma unroll
+    for (int r = 0; r < 8; ++r) ex.st(j0 + 64 * r, v[r]);
+    ex.sync();
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = ex.ld(j + P * q);
+  }
+  fft8_last_pass<N, DIR, Tw::T4>(v, j, tw);
 }
 
 // exchange through a contiguous, padded line buffer (row kernels): element i at i + i/8

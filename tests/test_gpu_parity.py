@@ -497,3 +497,49 @@ def test_slab_stepper_single_rank_equals_plain(name, N, order):
     assert rel(got3, ox.repeat(ost, 3)(u0)) < 5e-5
     uh = host(slab.fft(slab.scatter(u0)))
     assert rel(uh, ox.fft(u0, num_spatial_dims=3)) < 2e-6
+
+
+@pytest.mark.parametrize("N,nloc", [(256, 4), (512, 4), (1024, 2), (2048, 2)])
+def test_slab_passes_large_n_vs_torch_fft(N, nloc):
+    """The register-FFT pass kernels at the c5 line lengths (3 and 4 radix passes), exercised on a THIN
+    slab (N/P = nloc planes, as rank 1 of P = N/nloc would own) against torch.fft along the same axis."""
+    import ctypes as C
+    from exponax_b200 import _native as nat
+    P = N // nloc
+    Nh = N // 2 + 1
+    M = N * nloc * Nh
+    plan = nat.Plan(D=3, N=N, C_=3, E=1, order=0, dtype=np.float32, L=2 * np.pi, kmax=-1,
+                    nl={"kind": nat.NL_PROJECTED_3D}, exp_term=np.ones(M, np.complex64), slab=(P, 1))
+    nullS = (C.c_void_p * 4)()
+
+    def run(kind, nf, inp, out):
+        nat.check(nat.lib().exb_slab_pass(plan.handle, torch.cuda.current_stream().cuda_stream, kind, nf, 0,
+                                          inp.data_ptr(), out.data_ptr(), None, None, nullS))
+        torch.cuda.synchronize()
+
+    g = torch.Generator(device="cuda").manual_seed(N)
+    u = torch.randn((2, nloc, N, N), device="cuda", generator=g)
+    a = torch.empty((2, nloc, N, Nh), dtype=torch.complex64, device="cuda")
+    run(nat.SLAB_ROW_R2C, 2, u, a)
+    ref = torch.fft.rfft(u, dim=-1)
+    assert float((a - ref).norm() / ref.norm()) < 3e-6
+    back = torch.empty_like(u)
+    run(nat.SLAB_ROW_C2R, 2, ref.contiguous(), back)
+    assert float((back * N * N - u).norm() / u.norm()) < 3e-6   # C2R applies 1/N^3, irfft only 1/N
+    z = torch.randn((2, nloc, N, Nh, 2), device="cuda", generator=g)
+    z = torch.view_as_complex(z).contiguous()
+    o = torch.empty_like(z)
+    run(nat.SLAB_COL1_FWD, 2, z, o)
+    ref = torch.fft.fft(z, dim=2)
+    assert float((o - ref).norm() / ref.norm()) < 3e-6
+    run(nat.SLAB_COL1_INV, 2, z, o)
+    ref = torch.fft.ifft(z, dim=2) * N
+    assert float((o - ref).norm() / ref.norm()) < 3e-6
+    zb = z.view(2, N, nloc, Nh)  # same memory read as spectral slab (F, N, n, Nh)
+    ob = torch.empty_like(zb)
+    run(nat.SLAB_COL0_FWD, 2, zb, ob)
+    ref = torch.fft.fft(zb, dim=1)
+    assert float((ob - ref).norm() / ref.norm()) < 3e-6
+    run(nat.SLAB_COL0_INV, 2, zb, ob)
+    ref = torch.fft.ifft(zb, dim=1) * N
+    assert float((ob - ref).norm() / ref.norm()) < 3e-6
