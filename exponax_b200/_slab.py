@@ -71,10 +71,87 @@ def transpose_b_to_a(x: torch.Tensor, group=None, out: torch.Tensor | None = Non
     return out
 
 
+class _ShapeOnly:
+    """stands in for a freed operator array where only its shape is consulted"""
+
+    def __init__(self, shape):
+        self.shape, self.ndim = shape, len(shape)
+
+
+class _LeanNonlinearFun:
+    """Descriptor-only nonlinear function (no operator / mask arrays are ever materialised)."""
+
+    def __init__(self, desc: dict, kmax: int):
+        self._desc, self._kmax = desc, kmax
+
+    def _native_desc(self, num_channels):
+        return self._desc
+
+
+class _LeanStepper:
+    """What `SlabStepper` needs of a stepper, without the dense host arrays of `BaseStepper`."""
+
+    def __init__(self, N, L, dt, num_channels, dtype, integrator, nonlinear_fun, slab):
+        self.num_spatial_dims, self.num_points, self.domain_extent, self.dt = 3, N, L, dt
+        self.num_channels, self._dtype = num_channels, dtype
+        self._integrator, self._nonlinear_fun, self._slab = integrator, nonlinear_fun, slab
+        self.dx = L / N
+
+    def _plan_available(self):
+        return True
+
+
 class SlabStepper:
     """Distributed counterpart of a 3-D `BaseStepper` for a single, slab-sharded field."""
 
-    def __init__(self, stepper: BaseStepper, group=None):
+    @classmethod
+    def navier_stokes_velocity(cls, domain_extent: float, num_points: int, dt: float, *, diffusivity: float = 0.01,
+                               drag: float = 0.0, injection_mode: int | None = None, injection_scale: float = 1.0,
+                               order: int = 2, dealiasing_fraction: float = 2 / 3, num_circle_points: int = 16,
+                               circle_radius: float = 1.0, group=None):
+        """Lean constructor for `NavierStokesVelocity` (injection_mode=None) / `KolmogorovFlowVelocity`
+        (exponax/stepper/_navier_stokes.py:330-598) on a slab: the linear operator
+        `nu * laplace + drag` is assembled ON THE GPU for the local spectral slab from the 1-D
+        wavenumber vectors (same float32 arithmetic as `build_derivative_operator` /
+        `build_laplace_operator`), the ETDRK tables are built and kept on the device, and the
+        nonlinear function is a pure descriptor.  Nothing of size N^3 ever exists on the host --
+        the only way to set up the 2048^3 problem of config c5."""
+        from . import _spectral as sp
+        from . import etdrk
+        from ._config import real_dtype
+
+        rank, P = _group_info(group)
+        rd = real_dtype()
+        N, n = num_points, num_points // max(P, 1)
+        td = A.real_t(rd)
+        scale = rd(2 * np.pi / domain_extent)
+        k_other = np.fft.fftfreq(N, 1 / N).astype(rd)
+        k_last = np.fft.rfftfreq(N, 1 / N).astype(rd)
+        d0 = torch.as_tensor(scale * k_other, device="cuda", dtype=td).view(N, 1, 1)
+        d1 = torch.as_tensor(scale * k_other[rank * n:(rank + 1) * n], device="cuda", dtype=td).view(1, n, 1)
+        d2 = torch.as_tensor(scale * k_last, device="cuda", dtype=td).view(1, 1, N // 2 + 1)
+        lap = -(d0 * d0) - (d1 * d1) - (d2 * d2)          # sum_d (i k_d)^2, real
+        lin = (rd(diffusivity) * lap + rd(drag)).to(A.cplx_t(rd)).unsqueeze(0)
+        del lap
+        cutoff = dealiasing_fraction * (N // 2) - 1         # nonlin_fun/_base.py:59-71
+        kmax = sp.dealias_kmax(N, cutoff, rd)
+        inj = None
+        if injection_mode is not None and 0 <= injection_mode - rank * n < n and 0 < injection_mode < N // 2:
+            # (0, +k_f, 0) on channel 0, value gamma * N^3 / 2 (coef_extraction scaling), SURVEY App. B.14
+            inj = ((0, int(injection_mode), 0), float(injection_scale) * N * (N / 2) * N)
+        nl = _LeanNonlinearFun({"kind": nat.NL_PROJECTED_3D, "injection": inj}, kmax)
+        cls_e = {0: etdrk.ETDRK0, 1: etdrk.ETDRK1, 2: etdrk.ETDRK2, 3: etdrk.ETDRK3, 4: etdrk.ETDRK4}[order]
+        if order == 0:
+            integ = cls_e(dt, lin)
+        else:
+            integ = cls_e(dt, lin, nl, num_circle_points=num_circle_points, circle_radius=circle_radius)
+        integ._L_dev = None  # the operator itself is not needed after the tables exist
+        integ._linear_operator = _ShapeOnly(tuple(lin.shape))
+        del lin
+        torch.cuda.empty_cache()
+        return cls(_LeanStepper(N, domain_extent, dt, 3, rd, integ, nl, (rank, max(P, 1))), group=group)
+
+    def __init__(self, stepper, group=None):
         if stepper.num_spatial_dims != 3:
             raise ValueError("SlabStepper needs a 3-D stepper")
         if not stepper._plan_available():

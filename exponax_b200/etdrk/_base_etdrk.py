@@ -27,6 +27,18 @@ class BaseETDRK(ABC):
 
     def __init__(self, dt: float, linear_operator):
         self.dt = dt
+        self._nonlinear_fun = None
+        self._plans = {}
+        self._dev_coefs = {}
+        if isinstance(linear_operator, A.torch.Tensor):
+            # operator assembled directly on the GPU (lean slab constructors, config c5)
+            self._cd = np.dtype(np.complex64 if linear_operator.dtype == A.torch.complex64 else np.complex128)
+            self._rd = np.float32 if linear_operator.dtype == A.torch.complex64 else np.float64
+            self._linear_operator = linear_operator
+            self._on_gpu = True
+            self._L_dev = linear_operator
+            self._exp_term = A.torch.exp(self._rd(dt) * self._L_dev)
+            return
         linear_operator = np.asarray(linear_operator)
         if not np.iscomplexobj(linear_operator):
             linear_operator = linear_operator.astype(np.complex128 if linear_operator.dtype == np.float64

@@ -543,3 +543,24 @@ def test_slab_passes_large_n_vs_torch_fft(N, nloc):
     run(nat.SLAB_COL0_INV, 2, zb, ob)
     ref = torch.fft.ifft(zb, dim=1) * N
     assert float((ob - ref).norm() / ref.norm()) < 3e-6
+
+
+def test_lean_slab_constructor_matches_reference_constructor():
+    """SlabStepper.navier_stokes_velocity (tables assembled on the GPU, nothing N^3-sized on the host)
+    against the stepper built the reference way: same tables, same step."""
+    L, N, dt = 2 * np.pi, 32, 0.01
+    u0 = ic(3, N, [0], C=3)[0]
+    for order, inj in ((2, 4), (4, None)):
+        if inj is None:
+            st = ex.stepper.NavierStokesVelocity(3, L, N, dt, order=order, drag=-0.1)
+            ost = ox.NavierStokesVelocity(3, L, N, dt, order=order, drag=-0.1)
+            lean = ex.SlabStepper.navier_stokes_velocity(L, N, dt, order=order, drag=-0.1)
+        else:
+            st = ex.stepper.KolmogorovFlowVelocity(3, L, N, dt, order=order, injection_mode=inj)
+            ost = ox.KolmogorovFlowVelocity(3, L, N, dt, order=order, injection_mode=inj)
+            lean = ex.SlabStepper.navier_stokes_velocity(L, N, dt, order=order, injection_mode=inj)
+        it, lt = st._integrator, lean.stepper._integrator
+        assert rel(lt._exp_term.cpu().numpy(), it._exp_term) < 1e-6
+        assert rel(lt._coef_1.cpu().numpy(), it._coef_1) < 1e-5
+        got = host(lean.step(lean.scatter(u0)))
+        assert rel(got, ost(u0)) < F32_STEP
