@@ -1,4 +1,5 @@
 """Concrete PDE steppers (mirrors exponax/stepper/__init__.py for the hot-path scope)."""
+from . import generic as generic
 from . import reaction as reaction
 from ._burgers import Burgers
 from ._korteweg_de_vries import KortewegDeVries
@@ -26,4 +27,5 @@ __all__ = [
     "NavierStokesVelocity",
     "KolmogorovFlowVelocity",
     "reaction",
+    "generic",
 ]

@@ -564,3 +564,33 @@ def test_lean_slab_constructor_matches_reference_constructor():
         assert rel(lt._coef_1.cpu().numpy(), it._coef_1) < 1e-5
         got = host(lean.step(lean.scatter(u0)))
         assert rel(got, ost(u0)) < F32_STEP
+
+
+def test_generic_steppers_on_gpu():
+    """specific == generic == normalized == difficulty on the GPU (tests/test_builtin_solvers.py:70-388)."""
+    g = ex.stepper.generic
+    L, N, dt, nu, b = 5.0, 64, 0.02, 0.03, 1.7
+    u0 = ic(1, N, range(3))
+    ref = per_sample(ox.Burgers(1, L, N, dt, diffusivity=nu, convection_scale=b), u0)
+    phys = g.GeneralConvectionStepper(1, L, N, dt, linear_coefficients=(0.0, 0.0, nu), convection_scale=b)
+    assert rel(host(ex.vmap(phys)(dev(u0))), ref) < F32_STEP
+    alphas = g.normalize_coefficients((0.0, 0.0, nu), domain_extent=L, dt=dt)
+    bn = g.normalize_convection_scale(b, domain_extent=L, dt=dt)
+    norm = g.NormalizedConvectionStepper(1, N, normalized_linear_coefficients=alphas, normalized_convection_scale=bn)
+    assert rel(host(ex.vmap(norm)(dev(u0))), ref) < 1e-4
+    diff = g.DifficultyConvectionStepper(
+        1, N, linear_difficulties=g.reduce_normalized_coefficients_to_difficulty(alphas, num_spatial_dims=1, num_points=N),
+        convection_difficulty=g.reduce_normalized_convection_scale_to_difficulty(bn, num_spatial_dims=1, num_points=N,
+                                                                                 maximum_absolute=1.0))
+    assert rel(host(ex.vmap(diff)(dev(u0))), ref) < 1e-4
+    # general nonlinear stepper with only the convection coefficient == Burgers (single channel, conservative form)
+    gn = g.GeneralNonlinearStepper(1, L, N, dt, linear_coefficients=(0.0, 0.0, nu), nonlinear_coefficients=(0.0, -b, 0.0))
+    refc = per_sample(ox.Burgers(1, L, N, dt, diffusivity=nu, convection_scale=b, conservative=True,
+                                 single_channel=True), u0)
+    assert rel(host(ex.vmap(gn)(dev(u0))), refc) < F32_STEP
+    ks = g.GeneralGradientNormStepper(1, 60.0, N, 0.1)
+    assert rel(host(ex.vmap(ks)(dev(u0))), per_sample(ox.KuramotoSivashinsky(1, 60.0, N, 0.1), u0)) < F32_STEP
+    lin = g.DifficultyLinearStepperSimple(2, 32, difficulty=-2.0, order=1)
+    u2 = ic(2, 32, range(2))
+    out = host(ex.vmap(lin)(dev(u2)))
+    assert np.all(np.isfinite(out)) and out.shape == u2.shape

@@ -211,3 +211,86 @@ def test_stage_input_table_matches_cuda_source():
     assert [etdrk_stage_input(4, s) for s in range(4)] == [-1, 0, 2, 2]
     assert [etdrk_stage_input(3, s) for s in range(3)] == [-1, 0, 0]
     assert [etdrk_stage_input(2, s) for s in range(2)] == [-1, 0]
+
+
+# ---- generic steppers: specific == generic (tests/test_builtin_solvers.py:70-299, 878-895) --------
+def _tables(st):
+    it = st._integrator
+    out = [it._exp_term]
+    for nm in ("_coef_1", "_coef_2"):
+        if hasattr(it, nm):
+            out.append(getattr(it, nm))
+    return out
+
+
+def _same_tables(a, b, tol=2e-6):
+    for x, y in zip(_tables(a), _tables(b)):
+        assert x.shape == y.shape
+        assert np.max(np.abs(x - y)) <= tol * max(1.0, np.max(np.abs(y)))
+
+
+def test_generic_steppers_reduce_to_specific_ones():
+    g = ex.stepper.generic
+    L, N, dt = 3.0, 48, 0.01
+    _same_tables(g.GeneralLinearStepper(1, L, N, dt, linear_coefficients=(0.0, -0.7)),
+                 ex.stepper.Advection(1, L, N, dt, velocity=0.7))
+    _same_tables(g.GeneralLinearStepper(2, L, 16, dt, linear_coefficients=(0.0, 0.0, 0.03)),
+                 ex.stepper.Diffusion(2, L, 16, dt, diffusivity=0.03))
+    _same_tables(g.GeneralLinearStepper(1, L, N, dt, linear_coefficients=(0.0, 0.0, 0.0, 0.2)),
+                 ex.stepper.Dispersion(1, L, N, dt, dispersivity=0.2))
+    _same_tables(g.GeneralLinearStepper(1, L, N, dt, linear_coefficients=(0.0, 0.0, 0.0, 0.0, -0.001)),
+                 ex.stepper.HyperDiffusion(1, L, N, dt, hyper_diffusivity=0.001))
+    b = g.GeneralConvectionStepper(1, L, N, dt, linear_coefficients=(0.0, 0.0, 0.05), convection_scale=1.3)
+    _same_tables(b, ex.stepper.Burgers(1, L, N, dt, diffusivity=0.05, convection_scale=1.3))
+    assert b._nonlinear_fun._native_desc(1) == ex.stepper.Burgers(1, L, N, dt, diffusivity=0.05,
+                                                                 convection_scale=1.3)._nonlinear_fun._native_desc(1)
+    _same_tables(g.GeneralConvectionStepper(1, 20.0, N, 0.001, linear_coefficients=(0.0, 0.0, 0.0, -1.0, -0.01),
+                                            convection_scale=-6.0),
+                 ex.stepper.KortewegDeVries(1, 20.0, N, 0.001))
+    _same_tables(g.GeneralGradientNormStepper(1, 60.0, N, 0.1), ex.stepper.KuramotoSivashinsky(1, 60.0, N, 0.1))
+    _same_tables(g.GeneralConvectionStepper(1, 60.0, N, 0.1, linear_coefficients=(0.0, 0.0, -1.0, 0.0, -1.0),
+                                            conservative=True),
+                 ex.stepper.KuramotoSivashinskyConservative(1, 60.0, N, 0.1))
+    _same_tables(g.GeneralPolynomialStepper(1, 10.0, N, 0.001, linear_coefficients=(5.0, 0.0, 0.01),
+                                            polynomial_coefficients=(0.0, 0.0, -5.0)),
+                 ex.stepper.reaction.FisherKPP(1, 10.0, N, 0.001, diffusivity=0.01, reactivity=5.0))
+    _same_tables(g.GeneralVorticityConvectionStepper(2, 2 * np.pi, 16, 0.01, linear_coefficients=(0.0, 0.0, 0.01)),
+                 ex.stepper.NavierStokesVorticity(2, 2 * np.pi, 16, 0.01, diffusivity=0.01))
+    k = g.GeneralVorticityConvectionStepper(2, 2 * np.pi, 16, 0.01, linear_coefficients=(-0.05, 0.0, 0.001),
+                                            injection_mode=4, injection_scale=1.0)
+    _same_tables(k, ex.stepper.KolmogorovFlowVorticity(2, 2 * np.pi, 16, 0.01))  # drag -0.1 = 2 * (-0.05) in 2-D
+    assert k._nonlinear_fun._injection() == ex.stepper.KolmogorovFlowVorticity(2, 2 * np.pi, 16, 0.01)._nonlinear_fun._injection()
+    with pytest.raises(ValueError, match="exactly 3 elements"):
+        g.GeneralNonlinearStepper(1, L, N, dt, nonlinear_coefficients=(1.0, 2.0))
+    with pytest.raises(ValueError, match="Expected num_spatial_dims = 2"):
+        g.GeneralVorticityConvectionStepper(3, L, 8, dt)
+
+
+def test_normalized_and_difficulty_reparametrisations():
+    g = ex.stepper.generic
+    L, N, dt, nu, b = 5.0, 48, 0.02, 0.03, 1.7
+    phys = g.GeneralConvectionStepper(1, L, N, dt, linear_coefficients=(0.0, 0.0, nu), convection_scale=b)
+    norm = g.NormalizedConvectionStepper(
+        1, N, normalized_linear_coefficients=g.normalize_coefficients((0.0, 0.0, nu), domain_extent=L, dt=dt),
+        normalized_convection_scale=g.normalize_convection_scale(b, domain_extent=L, dt=dt))
+    # same exp(dt L) table; the phi-tables differ by the factor dt that the normalized nonlinear scale absorbs
+    # (tests/test_builtin_solvers.py:302-388 compare the steps; done on the GPU in test_gpu_parity.py)
+    assert np.max(np.abs(norm._integrator._exp_term - phys._integrator._exp_term)) < 2e-5
+    assert np.max(np.abs(norm._integrator._coef_1 * norm.convection_scale * L
+                         - phys._integrator._coef_1 * phys.convection_scale)) < 2e-6
+    alphas = g.normalize_coefficients((0.0, 0.0, nu), domain_extent=L, dt=dt)
+    gammas = g.reduce_normalized_coefficients_to_difficulty(alphas, num_spatial_dims=1, num_points=N)
+    back = g.extract_normalized_coefficients_from_difficulty(gammas, num_spatial_dims=1, num_points=N)
+    assert back == pytest.approx(alphas)
+    assert g.denormalize_coefficients(alphas, domain_extent=L, dt=dt) == pytest.approx((0.0, 0.0, nu))
+    d = g.DifficultyConvectionStepper(1, N, linear_difficulties=gammas,
+                                      convection_difficulty=g.reduce_normalized_convection_scale_to_difficulty(
+                                          g.normalize_convection_scale(b, domain_extent=L, dt=dt),
+                                          num_spatial_dims=1, num_points=N, maximum_absolute=1.0))
+    assert np.max(np.abs(d._integrator._exp_term - phys._integrator._exp_term)) < 2e-5
+    for cls in (g.DifficultyLinearStepper, g.DifficultyLinearStepperSimple, g.DifficultyGradientNormStepper,
+                g.DifficultyPolynomialStepper, g.DifficultyNonlinearStepper, g.NormalizedLinearStepper):
+        st = cls(1, 48) if cls is not g.NormalizedLinearStepper else cls(1, 48)
+        assert st.num_points == 48 and st.domain_extent == 1.0 and st.dt == 1.0
+    with pytest.warns(DeprecationWarning):
+        g.DiffultyLinearStepperSimple()
