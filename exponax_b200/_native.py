@@ -14,7 +14,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libexb.so")
 
 EXB_F32, EXB_F64 = 0, 1
-NL_ZERO, NL_CONVECTION, NL_GRADIENT_NORM, NL_POLYNOMIAL, NL_VORTICITY_2D, NL_PROJECTED_3D, NL_GENERAL = range(7)
+(NL_ZERO, NL_CONVECTION, NL_GRADIENT_NORM, NL_POLYNOMIAL, NL_VORTICITY_2D, NL_PROJECTED_3D, NL_GENERAL,
+ NL_GRAY_SCOTT, NL_CAHN_HILLIARD) = range(9)
 ROLLOUT_INCLUDE_INIT, ROLLOUT_LAYOUT_TB, ROLLOUT_FINAL_ONLY, ROLLOUT_SPECTRAL_CARRY = 1, 2, 4, 8
 (SLAB_ROW_R2C, SLAB_ROW_C2R, SLAB_COL1_FWD, SLAB_COL1_INV, SLAB_COL0_FWD, SLAB_COL0_INV, SLAB_COL0_INV_PRO,
  SLAB_ROW_NL, SLAB_COL0_FWD_EPI, SLAB_COL1_INV_NL, SLAB_COL1_FWD_NL) = range(11)

@@ -235,6 +235,16 @@ template <class T> struct PlanImpl : exb_plan {
         P.n_inv = C * (1 + D);
         P.n_fwd = 2 * C;
         break;
+      case EXB_NL_GRAY_SCOTT:
+        if (C != 2) return fail(EXB_EINVAL, "num_channels must be 2");
+        P.n_inv = 2;
+        P.n_fwd = 2;
+        break;
+      case EXB_NL_CAHN_HILLIARD:
+        if (C != 1) return fail(EXB_EINVAL, "Cahn-Hilliard needs 1 channel");
+        P.n_inv = 1;
+        P.n_fwd = 1;
+        break;
       default:
         return fail(EXB_EINVAL, "unknown nl_kind %d", P.kind);
     }

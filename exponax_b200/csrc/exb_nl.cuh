@@ -87,6 +87,8 @@ __device__ __forceinline__ cpx<T> nl_inv_field(const NlParams<T>& P, int f, cons
       return mul_i(pick3(m.kd, d) * pick3c(uh, c));
     }
     case EXB_NL_POLYNOMIAL:
+    case EXB_NL_GRAY_SCOTT:
+    case EXB_NL_CAHN_HILLIARD:
       return pick3c(uh, f);
     case EXB_NL_VORTICITY_2D: {                   // (_vorticity_convection.py:78-99)
       // laplacian = (i kd0)^2 + (i kd1)^2 ; inv = where(lap == 0, 1, 1/lap)
@@ -186,6 +188,15 @@ __device__ __forceinline__ void nl_pointwise(const NlParams<T>& P, const T* in, 
     case EXB_NL_VORTICITY_2D:
       out[0] = in[0] * in[2] + in[1] * in[3];
       break;
+    case EXB_NL_GRAY_SCOTT: {  // feed = gen[0], kill = gen[1]   (_gray_scott.py:36-43)
+      T uvv = in[0] * (in[1] * in[1]);
+      out[0] = P.gen[0] * ((T)1 - in[0]) - uvv;
+      out[1] = -(P.gen[0] + P.gen[1]) * in[1] + uvv;
+      break;
+    }
+    case EXB_NL_CAHN_HILLIARD:  // (_cahn_hilliard.py:33)
+      out[0] = in[0] * in[0] * in[0];
+      break;
     case EXB_NL_PROJECTED_3D: {
       // convection = velocity x curl   (in[0..2] = curl, in[3..5] = velocity)
       out[0] = in[4] * in[2] - in[5] * in[1];
@@ -268,6 +279,18 @@ __device__ __forceinline__ void nl_from_fwd(const NlParams<T>& P, const cpx<T>* 
       case EXB_NL_VORTICITY_2D:
         out[0] = (-P.scale) * W[0];
         break;
+      case EXB_NL_GRAY_SCOTT:
+        out[0] = W[0];
+        out[1] = W[1];
+        break;
+      case EXB_NL_CAHN_HILLIARD: {  // scale * laplace * F[u^3]   (_cahn_hilliard.py:34-36)
+        T lap = (T)0;
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+          if (d < D) lap -= m.kd[d] * m.kd[d];
+        out[0] = P.scale * (lap * W[0]);
+        break;
+      }
       case EXB_NL_PROJECTED_3D: {  // Leray projection (_leray.py:114-136)
         cpx<T> div = mul_i(m.kd[0] * W[0] + m.kd[1] * W[1] + m.kd[2] * W[2]);
         T lap = -(m.kd[0] * m.kd[0]) - (m.kd[1] * m.kd[1]) - (m.kd[2] * m.kd[2]);

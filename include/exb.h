@@ -56,6 +56,8 @@ extern "C" {
 #define EXB_NL_VORTICITY_2D 4    /* _vorticity_convection.py:78-99, 166-182 */
 #define EXB_NL_PROJECTED_3D 5    /* _projected_convection.py:114-136, 202-226 (+ _leray.py:114-136) */
 #define EXB_NL_GENERAL 6         /* _general_nonlinear.py:78-119 */
+#define EXB_NL_GRAY_SCOTT 7      /* stepper/reaction/_gray_scott.py:30-45   (general_scales = feed, kill) */
+#define EXB_NL_CAHN_HILLIARD 8   /* stepper/reaction/_cahn_hilliard.py:29-37 (nl_scale * laplace * F[u^3]) */
 
 #define EXB_MAX_POLY 8
 

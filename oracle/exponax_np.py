@@ -1098,3 +1098,82 @@ def gaussian_random_field(D, N, *, L=1.0, powerlaw_exponent=3.0, seed=0, max_one
     if max_one:
         u = u / np.max(np.abs(u))
     return u.astype(dtype)
+
+
+# --------------------------------------------------------------------------
+# stepper/reaction/_gray_scott.py, _cahn_hilliard.py
+# --------------------------------------------------------------------------
+class GrayScottNonlinearFun(BaseNonlinearFun):
+    """exponax/stepper/reaction/_gray_scott.py:12-45 (the mask is applied twice there; idempotent)."""
+
+    def __init__(self, D, N, *, dealiasing_fraction, feed_rate, kill_rate, dtype=np.float32):
+        super().__init__(D, N, dealiasing_fraction=dealiasing_fraction, dtype=dtype)
+        self.feed_rate, self.kill_rate = feed_rate, kill_rate
+
+    def __call__(self, u_hat):
+        if u_hat.shape[0] != 2:
+            raise ValueError("num_channels must be 2")
+        t = self.dtype
+        u = self.ifft(self.dealias(u_hat))
+        f, k = t(self.feed_rate), t(self.kill_rate)
+        up = np.stack([f * (1 - u[0]) - u[0] * u[1] ** 2, -(f + k) * u[1] + u[0] * u[1] ** 2])
+        return self.fft(up)
+
+
+class GrayScott(BaseStepper):
+    """exponax/stepper/reaction/_gray_scott.py:48-180."""
+
+    def __init__(self, D, L, N, dt, *, diffusivity_1=2e-5, diffusivity_2=1e-5, feed_rate=0.04, kill_rate=0.06,
+                 order=2, dealiasing_fraction=1 / 2, num_circle_points=16, circle_radius=1.0, dtype=np.float32):
+        self.diffusivity_1, self.diffusivity_2 = diffusivity_1, diffusivity_2
+        self.feed_rate, self.kill_rate = feed_rate, kill_rate
+        self.dealiasing_fraction = dealiasing_fraction
+        super().__init__(D, L, N, dt, num_channels=2, order=order, num_circle_points=num_circle_points,
+                         circle_radius=circle_radius, dtype=dtype)
+
+    def _build_linear_operator(self, dop):
+        t = self.dtype
+        lap = build_laplace_operator(dop, order=2)
+        return np.concatenate([t(self.diffusivity_1) * lap, t(self.diffusivity_2) * lap])
+
+    def _build_nonlinear_fun(self, dop):
+        return GrayScottNonlinearFun(self.num_spatial_dims, self.num_points, feed_rate=self.feed_rate,
+                                     kill_rate=self.kill_rate, dealiasing_fraction=self.dealiasing_fraction,
+                                     dtype=self.dtype)
+
+
+class CahnHilliardNonlinearFun(BaseNonlinearFun):
+    """exponax/stepper/reaction/_cahn_hilliard.py:12-37."""
+
+    def __init__(self, D, N, *, derivative_operator, scale, dealiasing_fraction, dtype=np.float32):
+        super().__init__(D, N, dealiasing_fraction=dealiasing_fraction, dtype=dtype)
+        self.laplace_operator = build_laplace_operator(derivative_operator)
+        self.scale = scale
+
+    def __call__(self, u_hat):
+        u = self.ifft(self.dealias(u_hat))
+        up_hat = self.fft(u[0:1] ** 3)
+        return self.laplace_operator * up_hat * self.dtype(self.scale)
+
+
+class CahnHilliard(BaseStepper):
+    """exponax/stepper/reaction/_cahn_hilliard.py:40-158."""
+
+    def __init__(self, D, L, N, dt, *, diffusivity=1e-2, gamma=1e-3, first_order_coefficient=-1.0,
+                 third_order_coefficient=1.0, order=2, dealiasing_fraction=1 / 2, num_circle_points=16,
+                 circle_radius=1.0, dtype=np.float32):
+        self.diffusivity, self.gamma = diffusivity, gamma
+        self.first_order_coefficient, self.third_order_coefficient = first_order_coefficient, third_order_coefficient
+        self.dealiasing_fraction = dealiasing_fraction
+        super().__init__(D, L, N, dt, num_channels=1, order=order, num_circle_points=num_circle_points,
+                         circle_radius=circle_radius, dtype=dtype)
+
+    def _build_linear_operator(self, dop):
+        t = self.dtype
+        lap = build_laplace_operator(dop, order=2)
+        return t(self.diffusivity) * lap * (t(self.first_order_coefficient) - t(self.gamma) * lap)
+
+    def _build_nonlinear_fun(self, dop):
+        return CahnHilliardNonlinearFun(self.num_spatial_dims, self.num_points, derivative_operator=dop,
+                                        dealiasing_fraction=self.dealiasing_fraction,
+                                        scale=self.diffusivity * self.third_order_coefficient, dtype=self.dtype)

@@ -594,3 +594,23 @@ def test_generic_steppers_on_gpu():
     u2 = ic(2, 32, range(2))
     out = host(ex.vmap(lin)(dev(u2)))
     assert np.all(np.isfinite(out)) and out.shape == u2.shape
+
+
+@pytest.mark.parametrize("D,N", [(1, 64), (1, 50), (2, 24), (3, 12)])
+@pytest.mark.parametrize("order", [2, 4])
+def test_gray_scott_and_cahn_hilliard(D, N, order):
+    """stepper/reaction/_gray_scott.py (2 species, per-channel linear operator E = C) and
+    _cahn_hilliard.py (laplace of u^3) -- tests/test_builtin_solvers.py:1034-1110."""
+    L, dt = 2.0, 0.5
+    u = 0.5 + 0.3 * ic(D, N, range(3), C=2)
+    gs = ex.stepper.reaction.GrayScott(D, L, N, dt, order=order)
+    ogs = ox.GrayScott(D, L, N, dt, order=order)
+    assert rel(host(ex.vmap(gs)(dev(u))), per_sample(ogs, u)) < F32_STEP
+    uh = ox.fft(u[0], num_spatial_dims=D)
+    assert rel(host(gs._nonlinear_fun(dev(uh))), ogs._integrator._nonlinear_fun(uh)) < 5e-6
+    with pytest.raises(ValueError, match="num_channels must be 2"):
+        gs._nonlinear_fun(dev(uh[:1]))
+    w = 0.4 * ic(D, N, range(3))
+    ch = ex.stepper.reaction.CahnHilliard(D, L, N, 0.001, order=order)
+    och = ox.CahnHilliard(D, L, N, 0.001, order=order)
+    assert rel(host(ex.vmap(ch)(dev(w))), per_sample(och, w)) < F32_STEP
