@@ -45,11 +45,17 @@ WORKLOADS = {
                final_only=False,
                desc="Burgers 1-D ETDRK2 N=256, 16384 trajectories x 1000 steps per GPU, every step saved"),
     "c3": dict(stepper="KolmogorovFlowVorticity", D=2, L=2 * np.pi, N=512, dt=0.01, kw=dict(diffusivity=0.001), C=1,
-               B=512, T=20, final_only=True,
-               desc="KolmogorovFlowVorticity 2-D 512x512 ETDRK2 2/3-dealiased, batch 512 per GPU, repeat"),
+               B=512, T=20, final_only=True, substeps=10,
+               desc="KolmogorovFlowVorticity 2-D 512x512 ETDRK2 2/3-dealiased, batch 512 per GPU, "
+                    "ex.repeat(ex.RepeatedStepper(stepper, 10), 2) = 20 ETDRK steps"),
     "c4": dict(stepper="NavierStokesVelocity", D=3, L=2 * np.pi, N=256, dt=0.005, kw=dict(diffusivity=0.01), C=3,
-               B=16, T=2, final_only=True,
-               desc="NavierStokesVelocity 3-D 256^3 Taylor-Green ETDRK2, batch 16 per GPU, repeat"),
+               B=16, T=4, final_only=True, substeps=2,
+               desc="NavierStokesVelocity 3-D 256^3 Taylor-Green ETDRK2, batch 16 per GPU, "
+                    "ex.repeat(ex.RepeatedStepper(stepper, 2), 2) = 4 ETDRK steps"),
+    "readme": dict(stepper="KuramotoSivashinsky", D=2, L=30.0, N=128, dt=0.1, kw={}, C=1, B=50, T=200,
+                   final_only=False,
+                   desc="README.md:187-189 claim: 50 trajectories of 2-D Kuramoto-Sivashinsky, 128x128, 200 steps "
+                        "('under a second on a modern GPU'); every step saved"),
     "c5": dict(stepper="KolmogorovFlowVelocity", D=3, L=2 * np.pi, N=2048, dt=1e-3, kw=dict(diffusivity=0.01), C=3,
                B=1, T=1, final_only=True,
                desc="KolmogorovFlowVelocity 3-D single field, slab-decomposed FFT with NCCL all-to-all (needs --gpus >= 2)"),
@@ -148,10 +154,13 @@ def algorithmic_bytes_per_call(w, itemsize=4, spectral_carry=False):
         saved = 1 if w["final_only"] else T
         return B * C * F * (1 + saved)
     # pass model per ETDRK2 step: stage = [2C + 2(D-1)(n_inv+n_fwd) + n_op] F, n_op = 0 / 2C
-    n_inv, n_fwd = {"KolmogorovFlowVorticity": (4, 1), "NavierStokesVelocity": (6, 3)}[w["stepper"]]
+    n_inv, n_fwd = {"KolmogorovFlowVorticity": (4, 1), "NavierStokesVelocity": (6, 3),
+                    "KuramotoSivashinsky": (2, 1)}[w["stepper"]]
     per_stage = 2 * C + 2 * (D - 1) * (n_inv + n_fwd)
     step = (2 * per_stage + 2 * C) * F          # c3: 26 F, c4: 90 F
-    carry = 0 if spectral_carry else 4 * C * F  # physical carry: the step's own ifft + fft (+4 F per channel)
+    # physical carry (the step's own ifft + fft, +4 F per channel) once per SAVED step: sub-steps of a
+    # RepeatedStepper carry the state in Fourier space (exponax/_repeated_stepper.py:56-102)
+    carry = 0 if spectral_carry else 4 * C * F / w.get("substeps", 1)
     return B * T * (step + carry)
 
 
@@ -170,6 +179,9 @@ def synth_ic(w, B, seed0=0):
         u /= np.abs(u).max(axis=-1, keepdims=True)
         return u.astype(np.float32)
     if D == 2:
+        if w["stepper"] == "KuramotoSivashinsky":
+            return np.stack([ox.random_truncated_fourier_series(2, N, cutoff=5, seed=seed0 + i, max_one=True)
+                             for i in range(B)]).astype(np.float32)
         base = np.stack([ox.gaussian_random_field(2, N, powerlaw_exponent=3.5, seed=seed0 + i) for i in range(8)])
         reps = (B + 7) // 8
         amp = (1.0 + 0.01 * (np.arange(reps * 8, dtype=np.float32) % 16))[:B]
@@ -232,12 +244,12 @@ def cpu_reference_run(w, steps, warmup, budget_s=20.0):
     cores = os.cpu_count() or 1
     ox.set_fft_workers(cores)
     N, D = w["N"], w["D"]
-    Bs = {"c1": 1, "c2": 1024, "c3": 4, "c4": 1}[w["name"]]
-    Ts = {"c1": 500, "c2": 50, "c3": 5, "c4": 1}[w["name"]]
+    Bs = {"c1": 1, "c2": 1024, "c3": 4, "c4": 1, "readme": 50}[w["name"]]
+    Ts = {"c1": 500, "c2": 50, "c3": 5, "c4": 1, "readme": 20}[w["name"]]
     st = getattr(ox, w["stepper"])(D, w["L"], N, w["dt"], **w["kw"])
     u0 = synth_ic(w, Bs)
     # oracle classes broadcast over a batch axis placed between channel and space for C == 1
-    if w["C"] == 1:
+    if w["C"] == 1 and w["stepper"] in ("Burgers", "KolmogorovFlowVorticity", "KuramotoSivashinskyConservative"):
         x0 = np.ascontiguousarray(np.moveaxis(u0, 0, 1))  # (1, B, N..)
         fn = ox.repeat(st.step, Ts)
         run = lambda: fn(x0)  # noqa: E731
@@ -326,7 +338,10 @@ def main():
     stepper = getattr(ex.stepper, w["stepper"])(D, w["L"], N, w["dt"], **w["kw"])
     u0_host = synth_ic(w, B, seed0=1000 * rank)
     u0 = torch.as_tensor(u0_host, device="cuda")
-    if w["final_only"]:
+    sub = w.get("substeps", 1)
+    if w["final_only"] and sub > 1:
+        fn = ex.vmap(ex.repeat(ex.RepeatedStepper(stepper, sub), T // sub, spectral_carry=args.spectral_carry))
+    elif w["final_only"]:
         fn = ex.vmap(ex.repeat(stepper, T, spectral_carry=args.spectral_carry))
     else:
         fn = ex.vmap(ex.rollout(stepper, T, spectral_carry=args.spectral_carry))

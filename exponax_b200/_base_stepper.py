@@ -99,6 +99,11 @@ class BaseStepper(ABC):
             self._native = self._order == 0 or nl._native_desc(self.num_channels) is not None
         return bool(self._native)
 
+    def _step_fourier_generic(self, u_hat):
+        """Array-level step in Fourier space used when no fused plan applies (user-defined nonlinear
+        functions, steppers overriding `step_fourier` such as `Wave`)."""
+        return self._integrator.step_fourier(u_hat)
+
     def _state_shape(self):
         return (self.num_channels,) + sp.spatial_shape(self.num_spatial_dims, self.num_points)
 
@@ -123,7 +128,7 @@ class BaseStepper(ABC):
         if plan is None:
             u_hat = sp.fft(t, num_spatial_dims=self.num_spatial_dims)
             for _ in range(substeps):
-                u_hat = self._integrator.step_fourier(u_hat)
+                u_hat = self._step_fourier_generic(u_hat)
             out = sp.ifft(u_hat, num_spatial_dims=self.num_spatial_dims, num_points=self.num_points)
             return A.from_device(out, kind)
         out = A.torch.empty_like(t)
@@ -138,7 +143,7 @@ class BaseStepper(ABC):
         plan = self._plan()
         if plan is None:
             for _ in range(substeps):
-                t = self._integrator.step_fourier(t)
+                t = self._step_fourier_generic(t)
             return A.from_device(t, kind)
         out = A.torch.empty_like(t)
         ws = sp.workspace(plan.workspace_bytes(batch))

@@ -5,6 +5,7 @@ from ._burgers import Burgers
 from ._korteweg_de_vries import KortewegDeVries
 from ._kuramoto_sivashinsky import KuramotoSivashinsky, KuramotoSivashinskyConservative
 from ._linear import Advection, AdvectionDiffusion, Diffusion, Dispersion, HyperDiffusion
+from ._wave import Wave
 from ._navier_stokes import (
     KolmogorovFlowVelocity,
     KolmogorovFlowVorticity,
@@ -18,6 +19,7 @@ __all__ = [
     "AdvectionDiffusion",
     "Dispersion",
     "HyperDiffusion",
+    "Wave",
     "Burgers",
     "KortewegDeVries",
     "KuramotoSivashinsky",

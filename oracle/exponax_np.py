@@ -1177,3 +1177,35 @@ class CahnHilliard(BaseStepper):
         return CahnHilliardNonlinearFun(self.num_spatial_dims, self.num_points, derivative_operator=dop,
                                         dealiasing_fraction=self.dealiasing_fraction,
                                         scale=self.diffusivity * self.third_order_coefficient, dtype=self.dtype)
+
+
+class Wave(BaseStepper):
+    """exponax/stepper/_wave.py:14-197."""
+
+    def __init__(self, D, L, N, dt, *, speed_of_sound=1.0, dtype=np.float32):
+        self.speed_of_sound = speed_of_sound
+        self.wavenumber_norm = np.linalg.norm(build_scaled_wavenumbers(D, L, N, dtype), axis=0,
+                                              keepdims=True).astype(dtype)
+        super().__init__(D, L, N, dt, num_channels=2, order=0, dtype=dtype)
+
+    def _build_linear_operator(self, dop):
+        val = 1j * self.dtype(self.speed_of_sound) * self.wavenumber_norm
+        return np.concatenate((val, -val), axis=0)
+
+    def _build_nonlinear_fun(self, dop):
+        return ZeroNonlinearFun(self.num_spatial_dims, self.num_points, dtype=self.dtype)
+
+    def step_fourier(self, u_hat):
+        t = self.dtype
+        c = t(self.speed_of_sound)
+        kg = np.where(self.wavenumber_norm == 0, t(1.0), self.wavenumber_norm)
+        s = t(1 / np.sqrt(2))
+        w = 1j * c * kg * u_hat[0:1]
+        waves = np.concatenate([s * (w + u_hat[1:2]), s * (w - u_hat[1:2])], axis=0)
+        nxt = self._integrator.step_fourier(waves)
+        w2 = s * (nxt[0:1] + nxt[1:2])
+        v2 = s * (nxt[0:1] - nxt[1:2])
+        out = np.concatenate([w2 / (1j * c * kg), v2], axis=0)
+        dc = (0,) * self.num_spatial_dims
+        out[(0,) + dc] += t(self.dt) * u_hat[(1,) + dc]
+        return out

@@ -614,3 +614,28 @@ def test_gray_scott_and_cahn_hilliard(D, N, order):
     ch = ex.stepper.reaction.CahnHilliard(D, L, N, 0.001, order=order)
     och = ox.CahnHilliard(D, L, N, 0.001, order=order)
     assert rel(host(ex.vmap(ch)(dev(w))), per_sample(och, w)) < F32_STEP
+
+
+@pytest.mark.parametrize("D,N", [(1, 64), (2, 32), (3, 12)])
+def test_wave_stepper(D, N):
+    """exponax/stepper/_wave.py; analytic single mode (tests/test_wave.py:70-86) and DC drift (:146-158)."""
+    L, dt, c = 2 * np.pi, 0.01, 1.3
+    st = ex.stepper.Wave(D, L, N, dt, speed_of_sound=c)
+    ost = ox.Wave(D, L, N, dt, speed_of_sound=c)
+    assert st.num_channels == 2
+    u0 = ic(D, N, range(2), C=2)
+    assert rel(host(ex.vmap(st)(dev(u0))), per_sample(ost, u0)) < F32_STEP
+    trj = host(ex.rollout(st, 5, include_init=True)(dev(u0[0])))
+    assert trj.shape == (6, 2) + (N,) * D
+    if D == 1:
+        k0 = 3
+        x = np.linspace(0, L, N, endpoint=False)
+        u = dev(np.stack([np.cos(k0 * x), np.zeros(N)]).astype(np.float32))
+        for _ in range(10):
+            u = st(u)
+        u = host(u)
+        t = 10 * dt
+        assert u[0] == pytest.approx(np.cos(k0 * x) * np.cos(c * k0 * t), abs=1e-4)
+        assert u[1] == pytest.approx(-c * k0 * np.cos(k0 * x) * np.sin(c * k0 * t), abs=1e-3)
+        w = dev(np.stack([np.zeros(N), np.full(N, 0.5)]).astype(np.float32))
+        assert float(host(st(w))[0].mean()) == pytest.approx(0.5 * dt, abs=1e-5)
