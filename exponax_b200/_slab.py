@@ -34,6 +34,17 @@ def _group_info(group):
     return 0, 1
 
 
+def init_process_group_nccl(local_rank: int):
+    """NCCL process group whose internal stream has high priority, so that the all-to-all kernels are
+    scheduled ahead of the grid-filling pass kernels they overlap with."""
+    opts = None
+    try:
+        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+    except Exception:
+        pass
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=opts)
+
+
 def transpose_a_to_b(x: torch.Tensor, group=None, out: torch.Tensor | None = None) -> torch.Tensor:
     """(F, n, N, K) split over x-planes  ->  (F, N, n, K) split over axis-1 indices (n = N/P).
     Field by field (bounded temporaries): one pack copy + one all-to-all, received in place."""
@@ -165,6 +176,7 @@ class SlabStepper:
         self.N, self.n, self.Nh, self.Cn = N, N // self.P, N // 2 + 1, stepper.num_channels
         self._plan = None
         self._bufs = {}
+        self.overlap = True   # pipeline the all-to-all transposes against the passes (two streams)
 
     # ---- plan with the LOCAL slices of the coefficient tables --------------------------------
     def _local(self, arr):
@@ -276,17 +288,65 @@ class SlabStepper:
         wfwd_b = wb[:self.n_fwd].view(self.n_fwd, self.N, self.n, self.Nh)
         winv_a = self._buf("winv_a", self.n_inv)
         wfwd_a = self._buf("wfwd_a", self.n_fwd)
+        overlap = self.overlap and self.P > 1
         for s in range(self.order):
             si = etdrk_stage_input(self.order, s)
             src = uh if si < 0 else S[si]
-            self._pass(nat.SLAB_COL0_INV_PRO, self.n_inv, src, winv_b)
-            transpose_b_to_a(winv_b, self.group, out=winv_a)
-            self._pass(nat.SLAB_COL1_INV_NL, self.n_inv, winv_a, winv_a)
-            self._pass(nat.SLAB_ROW_NL, self.n_inv, winv_a, wfwd_a)
-            self._pass(nat.SLAB_COL1_FWD_NL, self.n_fwd, wfwd_a, wfwd_a)
-            transpose_a_to_b(wfwd_a, self.group, out=wfwd_b)
+            if not overlap:
+                self._pass(nat.SLAB_COL0_INV_PRO, self.n_inv, src, winv_b)
+                transpose_b_to_a(winv_b, self.group, out=winv_a)
+                self._pass(nat.SLAB_COL1_INV_NL, self.n_inv, winv_a, winv_a)
+                self._pass(nat.SLAB_ROW_NL, self.n_inv, winv_a, wfwd_a)
+                self._pass(nat.SLAB_COL1_FWD_NL, self.n_fwd, wfwd_a, wfwd_a)
+                transpose_a_to_b(wfwd_a, self.group, out=wfwd_b)
+            else:
+                # field-by-field pipeline on two streams: the all-to-all of field f (comm stream, NVLink)
+                # runs while the compute stream works on the prologue of field f+1 / the axis-1 pass of
+                # field f-1; events order producer -> transpose -> consumer per field.
+                main, comm = torch.cuda.current_stream(), self._comm_stream()
+                arrived = []
+                for f in range(self.n_inv):
+                    nat.check(nat.lib().exb_slab_inv_pro_fields(self.plan().handle, main.cuda_stream, f, 1,
+                                                                A.ptr(src), A.ptr(winv_b)))
+                    ready = torch.cuda.Event()
+                    ready.record(main)
+                    with torch.cuda.stream(comm):
+                        comm.wait_event(ready)
+                        transpose_b_to_a(winv_b[f:f + 1], self.group, out=winv_a[f:f + 1])
+                        ev = torch.cuda.Event()
+                        ev.record(comm)
+                    arrived.append(ev)
+                for f in range(self.n_inv):
+                    main.wait_event(arrived[f])
+                    self._pass(nat.SLAB_COL1_INV_NL, 1, winv_a[f], winv_a[f])
+                self._pass(nat.SLAB_ROW_NL, self.n_inv, winv_a, wfwd_a)
+                arrived = []
+                for g in range(self.n_fwd):
+                    self._pass(nat.SLAB_COL1_FWD_NL, 1, wfwd_a[g], wfwd_a[g])
+                    ready = torch.cuda.Event()
+                    ready.record(main)
+                    with torch.cuda.stream(comm):
+                        comm.wait_event(ready)
+                        transpose_a_to_b(wfwd_a[g:g + 1], self.group, out=wfwd_b[g:g + 1])
+                        ev = torch.cuda.Event()
+                        ev.record(comm)
+                    arrived.append(ev)
+                for ev in arrived:
+                    main.wait_event(ev)
             self._pass(nat.SLAB_COL0_FWD_EPI, self.n_fwd, wfwd_b, None, stage=s, U=uh, OUT=out, S=S)
+            if overlap:
+                # the next stage's prologue overwrites w_b: the comm stream must be done reading it (it is:
+                # every transpose was awaited above), and must not start before this epilogue finished
+                done = torch.cuda.Event()
+                done.record(torch.cuda.current_stream())
+                self._comm_stream().wait_event(done)
         return out
+
+    def _comm_stream(self):
+        if getattr(self, "_comm", None) is None:
+            # high priority: the (small) NCCL / pack kernels must not queue behind the grid-filling pass kernels
+            self._comm = torch.cuda.Stream(priority=-1)
+        return self._comm
 
     def step(self, u_local):
         """One step of the physical slab (C, N/P, N, N): fft -> step_fourier -> ifft

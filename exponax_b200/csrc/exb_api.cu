@@ -50,6 +50,7 @@ struct exb_plan {
   virtual int slab_pass(cudaStream_t st, int pass, int nfields, int stage, const void* in, void* out,
                         const void* U, void* OUT, void* const* S) = 0;
   virtual void nl_fields(int* ni, int* nf) const = 0;
+  virtual int slab_inv_pro_fields(cudaStream_t st, int f0, int nf, const void* in, void* out) = 0;
 };
 
 static void factorize(int N, FftDesc& fd) {
@@ -453,9 +454,11 @@ template <class T> struct PlanImpl : exb_plan {
     return EXB_OK;
   }
 
-  int col_inv_pro(cudaStream_t st, long long batch, const cpx<T>* state, cpx<T>* winv) {
+  int col_inv_pro(cudaStream_t st, long long batch, const cpx<T>* state, cpx<T>* winv, int f0 = 0, int fcount = 0) {
     ColParams<T> p;
     memset(&p, 0, sizeof(p));
+    p.f0 = f0;
+    p.fcount = fcount;
     p.P = P;
     p.K = K;
     p.fd = fd;
@@ -635,6 +638,11 @@ template <class T> struct PlanImpl : exb_plan {
   }
 
   // ------------------------------------------------------------------ slab passes
+  int slab_inv_pro_fields(cudaStream_t st, int f0, int nf, const void* in, void* out) override {
+    if (D != 3) return fail(EXB_EINVAL, "exb_slab_inv_pro_fields needs a 3-D plan");
+    if (f0 < 0 || nf < 1 || f0 + nf > P.n_inv) return fail(EXB_EINVAL, "field range out of bounds");
+    return col_inv_pro(st, 1, (const cpx<T>*)in, (cpx<T>*)out, f0, nf);
+  }
   void nl_fields(int* ni, int* nf) const override {
     *ni = P.n_inv;
     *nf = P.n_fwd;
@@ -879,6 +887,10 @@ int exb_slab_pass(exb_plan* plan, void* stream, int32_t pass, int32_t nfields, i
                   void* out, const void* U, void* OUT, void* const* S) {
   if (!plan) return fail(EXB_EINVAL, "null plan");
   return plan->slab_pass((cudaStream_t)stream, pass, nfields, stage, in, out, U, OUT, S);
+}
+int exb_slab_inv_pro_fields(exb_plan* plan, void* stream, int32_t field0, int32_t nfields, const void* in, void* out) {
+  if (!plan) return fail(EXB_EINVAL, "null plan");
+  return plan->slab_inv_pro_fields((cudaStream_t)stream, field0, nfields, in, out);
 }
 int exb_plan_nl_fields(const exb_plan* plan, int32_t* n_inv, int32_t* n_fwd) {
   if (!plan || !n_inv || !n_fwd) return fail(EXB_EINVAL, "null argument");

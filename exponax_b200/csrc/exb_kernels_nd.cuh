@@ -35,6 +35,7 @@ template <class T> struct ColParams {
   int nfields;             // fields per batch element (PLAIN); n_inv / n_fwd otherwise
   int stage;               // ETDRK stage (FWD_EPI)
   int prune;               // fast kernels only: PRUNE_* bits (dealiased modes are never touched)
+  int f0, fcount;          // COL_INV_PRO: inverse fields [f0, f0 + fcount) (fcount <= 0: all)
   long long line_stride;   // elements between successive points of a line
   long long inner;         // contiguous positions across which lines are tiled
   long long n_outer;       // independent slabs per field (3-D axis-1 pass: N)
@@ -104,7 +105,8 @@ template <class T, int DIR> __global__ void col_pass_kernel(const ColParams<T> p
       Ust[q] = w < wv ? p.in[((size_t)b * C + ch) * p.M + (size_t)i * p.line_stride + w0 + w] : zero;
     }
     __syncthreads();
-    for (int f = 0; f < P.n_inv; ++f) {
+    const int f_begin = p.fcount > 0 ? p.f0 : 0, f_end = p.fcount > 0 ? p.f0 + p.fcount : P.n_inv;
+    for (int f = f_begin; f < f_end; ++f) {
       for (int q = threadIdx.x; q < N * TW; q += blockDim.x) {
         int i = q / TW, w = q - i * TW;
         cpx<T> v = zero;

@@ -102,7 +102,8 @@ col_fast_kernel(const ColParams<float> p) {
       for (int q = 0; q < 8; ++q)
         u0[q] = (col_keep && (kmax < 0 || row_keep(j + P * q))) ? ubase[(size_t)(j + P * q) * ls] : zero;
     }
-    for (int f = 0; f < Pn.n_inv; ++f) {
+    const int f_begin = p.fcount > 0 ? p.f0 : 0, f_end = p.fcount > 0 ? p.f0 + p.fcount : Pn.n_inv;
+    for (int f = f_begin; f < f_end; ++f) {
       cpx<float> v[8];
 #pragma unroll
       for (int q = 0; q < 8; ++q) {

@@ -171,6 +171,10 @@ int exb_rollout(exb_plan *plan, void *stream, int64_t batch, int64_t n_saved, in
 #define EXB_SLAB_COL1_FWD_NL 10 /* COL1_FWD with dealiasing-aware pruning (inside N(u) only)          */
 int exb_slab_pass(exb_plan *plan, void *stream, int32_t pass, int32_t nfields, int32_t stage,
                   const void *in, void *out, const void *U, void *OUT, void *const *S);
+/* EXB_SLAB_COL0_INV_PRO restricted to the inverse fields [field0, field0 + nfields): lets the caller
+   overlap the all-to-all of field f with the prologue pass of field f+1 (out = base of ALL fields) */
+int exb_slab_inv_pro_fields(exb_plan *plan, void *stream, int32_t field0, int32_t nfields, const void *in,
+                            void *out);
 /* number of single-field inverse / forward transforms per N(u) evaluation of this plan */
 int exb_plan_nl_fields(const exb_plan *plan, int32_t *n_inv, int32_t *n_fwd);
 
