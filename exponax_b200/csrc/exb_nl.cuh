@@ -55,6 +55,11 @@ __device__ __forceinline__ ModeK<T> make_mode(const NlParams<T>& P, int i0, int 
   return m;
 }
 
+// 1/x, correctly rounded (identical to the IEEE division the reference's `1 / laplacian` performs) but
+// a single MUFU + Newton step instead of the full division sequence
+__device__ __forceinline__ float exb_rcp(float x) { return __frcp_rn(x); }
+__device__ __forceinline__ double exb_rcp(double x) { return 1.0 / x; }
+
 template <class T> __device__ __forceinline__ T pick3(const T* a, int i) {
   return i == 0 ? a[0] : (i == 1 ? a[1] : a[2]);
 }
@@ -93,7 +98,7 @@ __device__ __forceinline__ cpx<T> nl_inv_field(const NlParams<T>& P, int f, cons
     case EXB_NL_VORTICITY_2D: {                   // (_vorticity_convection.py:78-99)
       // laplacian = (i kd0)^2 + (i kd1)^2 ; inv = where(lap == 0, 1, 1/lap)
       T lap = -(m.kd[0] * m.kd[0]) - (m.kd[1] * m.kd[1]);
-      T inv = (lap == (T)0) ? (T)1 : (T)1 / lap;
+      T inv = (lap == (T)0) ? (T)1 : exb_rcp(lap);
       cpx<T> w = uh[0];
       cpx<T> psi = inv * w;
       if (f == 0) return mul_i(m.kd[1] * psi);    // u = +d_y psi
@@ -294,7 +299,7 @@ __device__ __forceinline__ void nl_from_fwd(const NlParams<T>& P, const cpx<T>* 
       case EXB_NL_PROJECTED_3D: {  // Leray projection (_leray.py:114-136)
         cpx<T> div = mul_i(m.kd[0] * W[0] + m.kd[1] * W[1] + m.kd[2] * W[2]);
         T lap = -(m.kd[0] * m.kd[0]) - (m.kd[1] * m.kd[1]) - (m.kd[2] * m.kd[2]);
-        T inv = (lap != (T)0) ? (T)1 / lap : (T)0;
+        T inv = (lap != (T)0) ? exb_rcp(lap) : (T)0;
         cpx<T> p = (-inv) * div;
 #pragma unroll
         for (int c = 0; c < 3; ++c) out[c] = W[c] + mul_i(m.kd[c] * p);
