@@ -247,8 +247,12 @@ def cpu_reference_run(w, steps, warmup, budget_s=20.0):
     cores = os.cpu_count() or 1
     ox.set_fft_workers(cores)
     N, D = w["N"], w["D"]
-    Bs = {"c1": 1, "c2": 1024, "c3": 4, "c4": 1, "readme": 50}[w["name"]]
-    Ts = {"c1": 500, "c2": 50, "c3": 5, "c4": 1, "readme": 20}[w["name"]]
+    Bs = {"c1": 1, "c2": 1024, "c3": 4, "c4": 1, "readme": 50, "c5": 1}[w["name"]]
+    Ts = {"c1": 500, "c2": 50, "c3": 5, "c4": 1, "readme": 20, "c5": 2}[w["name"]]
+    if w["name"] == "c5":
+        # the reference cannot construct 2048^3: its CPU arm is sampled at 128^3
+        N = 128
+        w = dict(w, N=N)
     st = getattr(ox, w["stepper"])(D, w["L"], N, w["dt"], **w["kw"])
     u0 = synth_ic(w, Bs)
     # oracle classes broadcast over a batch axis placed between channel and space for C == 1
@@ -304,6 +308,8 @@ def main():
         w["T"] = args.T
     if args.N:
         w["N"] = args.N
+    if args.workload == "c5" and args.impl == "exb" and world < 2:
+        raise SystemExit("workload c5 shards ONE field over the ranks: launch it with torchrun on >= 2 GPUs")
     if args.workload == "c5" and args.impl == "exb":
         return run_c5(args, w, rank, world, local_rank)
     args.warmup = max(args.warmup, 3) if args.impl == "exb" else args.warmup

@@ -94,12 +94,6 @@ class BaseETDRK(ABC):
         return None
 
     # ---- native plan ---------------------------------------------------------------------
-    def _geometry(self):
-        shp = self._linear_operator.shape
-        D = len(shp) - 1
-        N = shp[1] if D >= 2 else None
-        return D, N, shp[0]
-
     def _plan(self, num_channels: int, num_points: int, domain_extent: float):
         key = (num_channels, A.torch.cuda.current_device())
         p = self._plans.get(key)
@@ -118,15 +112,6 @@ class BaseETDRK(ABC):
                          exp_term=self._exp_term, half_exp_term=self._half_exp(), coefs=self._coef_list())
             self._plans[key] = p
         return p
-
-    def _is_native(self) -> bool:
-        nl = self._nonlinear_fun
-        if self.order == 0 or nl is None:
-            return True
-        try:
-            return nl._native_desc(getattr(nl, "_probe_channels", self._linear_operator.ndim - 1)) is not None
-        except ValueError:
-            return True  # channel mismatch is reported when the plan is built
 
     def _dev(self, name):
         """device copy of a coefficient array (generic path only)."""

@@ -639,3 +639,20 @@ def test_wave_stepper(D, N):
         assert u[1] == pytest.approx(-c * k0 * np.cos(k0 * x) * np.sin(c * k0 * t), abs=1e-3)
         w = dev(np.stack([np.zeros(N), np.full(N, 0.5)]).astype(np.float32))
         assert float(host(st(w))[0].mean()) == pytest.approx(0.5 * dt, abs=1e-5)
+
+
+@pytest.mark.parametrize("N", [1024, 2048, 4096])
+def test_large_1d_grids(N):
+    """1-D grids of a few thousand points run on the persistent shared-memory kernel."""
+    L, dt = 2 * np.pi, 1e-3
+    u0 = ic(1, N, range(3))
+    st = ex.stepper.Burgers(1, L, N, dt, diffusivity=0.05)
+    ost = ox.Burgers(1, L, N, dt, diffusivity=0.05)
+    got = host(ex.vmap(ex.repeat(st, 3))(dev(u0)))
+    assert rel(got, per_sample(ox.repeat(ost, 3), u0)) < 3e-5
+
+
+def test_1d_grid_beyond_shared_memory_is_rejected_loudly():
+    st = ex.stepper.Burgers(1, 1.0, 16384, 1e-3)
+    with pytest.raises(NotImplementedError, match="shared memory"):
+        st(dev(np.zeros((1, 16384), np.float32)))
