@@ -656,3 +656,93 @@ def test_1d_grid_beyond_shared_memory_is_rejected_loudly():
     st = ex.stepper.Burgers(1, 1.0, 16384, 1e-3)
     with pytest.raises(NotImplementedError, match="shared memory"):
         st(dev(np.zeros((1, 16384), np.float32)))
+
+
+# ------------------------------------------------------------------ fast 1-D kernel coverage (N = 64, 256)
+def _fast_1d_cases():
+    g = "generic"
+    return [
+        ("KuramotoSivashinsky", dict(), 60.0, 0.1),
+        ("KuramotoSivashinskyConservative", dict(), 60.0, 0.1),
+        ("KortewegDeVries", dict(), 20.0, 0.001),
+        ("KortewegDeVries", dict(conservative=True, single_channel=True), 20.0, 0.001),
+        ("Burgers", dict(single_channel=True), 2 * np.pi, 0.01),
+        ("FisherKPP", dict(reactivity=2.0), 10.0, 0.01),
+        ("SwiftHohenberg", dict(), 10.0, 0.01),
+        ("CahnHilliard", dict(), 2.0, 0.001),
+        (g, dict(nonlinear_coefficients=(0.3, -1.0, 0.5)), 2 * np.pi, 0.01),
+        ("Diffusion", dict(diffusivity=0.1), 10.0, 0.1),
+        ("Dispersion", dict(dispersivity=0.2), 10.0, 0.01),
+    ]
+
+
+@pytest.mark.parametrize("N", [64, 256])
+@pytest.mark.parametrize("name,kw,L,dt", _fast_1d_cases(), ids=lambda v: v if isinstance(v, str) else "")
+def test_fast_1d_kernel_all_nonlinear_functions(name, kw, L, dt, N):
+    """Every instantiation of the register-FFT persistent kernel (convection both forms, gradient
+    norm, polynomial, general; order 0) at its two grid sizes, orders 1-4, rollout + repeat."""
+    u0 = 0.6 * ic(1, N, range(5))
+    linear = name in ("Diffusion", "Dispersion")
+    for order in ([None] if linear else [1, 2, 3, 4]):
+        okw = dict(kw) if linear else dict(kw, order=order)
+        if name == "generic":
+            st = ex.stepper.generic.GeneralNonlinearStepper(1, L, N, dt, linear_coefficients=(0.0, 0.0, 0.05), **okw)
+            # oracle: same operator via the three sub-functions
+            class _O(ox.BaseStepper):
+                def __init__(s):
+                    super().__init__(1, L, N, dt, num_channels=1, order=order)
+
+                def _build_linear_operator(s, dop):
+                    return np.float32(0.05) * ox.build_laplace_operator(dop)
+
+                def _build_nonlinear_fun(s, dop):
+                    return ox.GeneralNonlinearFun(1, N, derivative_operator=dop, dealiasing_fraction=2 / 3,
+                                                  scale_list=kw["nonlinear_coefficients"])
+            ost = _O()
+        else:
+            mod = ex.stepper.reaction if hasattr(ex.stepper.reaction, name) else ex.stepper
+            st = getattr(mod, name)(1, L, N, dt, **okw)
+            ost = getattr(ox, name)(1, L, N, dt, **okw)
+        ref = per_sample(ox.rollout(ost, 3, include_init=True), u0)
+        got = host(ex.vmap(ex.rollout(st, 3, include_init=True))(dev(u0)))
+        assert rel(got, ref) < 2e-5, (name, order, rel(got, ref))
+        rep = host(ex.vmap(ex.repeat(st, 3, spectral_carry=True))(dev(u0)))
+        assert rel(rep, ref[:, -1]) < 2e-5, (name, order)
+    rs = host(ex.vmap(ex.rollout(ex.RepeatedStepper(st, 2), 2))(dev(u0)))
+    oref = per_sample(ox.rollout(ox.RepeatedStepper(ost, 2), 2), u0)
+    assert rel(rs, oref) < 2e-5
+
+
+def test_fast_and_generic_1d_kernels_agree():
+    """Same plan parameters through the generic shared-memory kernel (EXB_DISABLE_FAST_1D) and the
+    register-FFT kernel."""
+    import os
+    N, L, dt = 256, 2 * np.pi, 0.01
+    u0 = dev(ic(1, N, range(7)))
+    fast = host(ex.vmap(ex.rollout(ex.stepper.Burgers(1, L, N, dt), 20))(u0))
+    os.environ["EXB_DISABLE_FAST_1D"] = "1"
+    try:
+        slow = host(ex.vmap(ex.rollout(ex.stepper.Burgers(1, L, N, dt), 20))(u0))
+    finally:
+        del os.environ["EXB_DISABLE_FAST_1D"]
+    assert rel(fast, slow) < 5e-6
+
+
+# ------------------------------------------------------------------ size-independent properties at full size
+def test_full_size_round_trips_and_linearity():
+    """fft -> ifft round trips and linearity of the transforms at the BASELINE grid sizes."""
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for D, N, nf in ((2, 512, 4), (3, 256, 2)):
+        u = torch.randn((nf,) + (N,) * D, device="cuda", generator=g)
+        v = torch.randn((nf,) + (N,) * D, device="cuda", generator=g)
+        uh = ex.fft(u, num_spatial_dims=D)
+        back = ex.ifft(uh, num_spatial_dims=D, num_points=N)
+        assert float((back - u).norm() / u.norm()) < 3e-6
+        lin = ex.fft(2.0 * u - 0.5 * v, num_spatial_dims=D)
+        assert float((lin - (2.0 * uh - 0.5 * ex.fft(v, num_spatial_dims=D))).norm() / lin.norm()) < 3e-6
+        # Parseval (rfft layout: interior last-axis modes count twice)
+        w = torch.full((N // 2 + 1,), 2.0, device="cuda")
+        w[0] = 1.0
+        w[-1] = 1.0
+        e_spec = float(((uh.abs() ** 2) * w).sum()) / N**D
+        assert e_spec == pytest.approx(float((u**2).sum()), rel=1e-4)
