@@ -55,14 +55,12 @@ int launch_fast_t(cudaStream_t st, const K1dParams<float>& p, int nscr, int max_
     *err = "fast 1-D kernel: not enough shared memory";
     return EXB_EUNSUPPORTED;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  {  // per device attribute: set on every launch (a process may drive several devices)
     cudaError_t e = cudaFuncSetAttribute(k1d_fast_kernel<R, S, NI, NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
     if (e != cudaSuccess) {
       *err = cudaGetErrorString(e);
       return EXB_ECUDA;
     }
-    attr_set = true;
   }
   long long npairs = (p.batch + 1) / 2;
   long long grid = (npairs + groups - 1) / groups;

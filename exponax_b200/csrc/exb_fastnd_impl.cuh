@@ -22,12 +22,8 @@ template <class K> int set_smem(K kernel, size_t smem, const char** err) {
 template <int N, int TW, class S, int NFWD, int MODE, int DIR>
 int launch_col(cudaStream_t st, const ColParams<float>& p, long long grid, const char** err) {
   const size_t smem = (size_t)(Fft8Tw<N>::SIZE + ExTile<TW>::rows(N) * TW) * sizeof(cpx<float>);
-  static bool once = false;
-  if (!once) {
-    int rc = set_smem(col_fast_kernel<N, TW, S, NFWD, MODE, DIR>, smem, err);
-    if (rc) return rc;
-    once = true;
-  }
+  // (set on every launch: the attribute is per device, and a process may drive several devices)
+  if (int rc = set_smem(col_fast_kernel<N, TW, S, NFWD, MODE, DIR>, smem, err)) return rc;
   ColParams<float> q = p;
   q.TW = TW;
   col_fast_kernel<N, TW, S, NFWD, MODE, DIR><<<(unsigned)grid, (N / 8) * TW, smem, st>>>(q);
@@ -44,12 +40,7 @@ int launch_row(cudaStream_t st, const RowParams<float>& p, const char** err) {
   constexpr int P = N / 8, GROUPS = 256 / P;
   const bool stash = false;  // see row_fast_kernel: STASH is compiled out
   const size_t smem = (size_t)(Fft8Tw<N>::SIZE + GROUPS * (N + N / 8 + (stash ? NINV * N : 0))) * sizeof(cpx<float>);
-  static bool once = false;
-  if (!once) {
-    int rc = set_smem(row_fast_kernel<N, S, NINV, NFWD, MODE, GROUPS>, smem, err);
-    if (rc) return rc;
-    once = true;
-  }
+  if (int rc = set_smem(row_fast_kernel<N, S, NINV, NFWD, MODE, GROUPS>, smem, err)) return rc;
   const long long npairs = (p.rows + 1) / 2 * p.batch;
   const long long grid = (npairs + GROUPS - 1) / GROUPS;
   row_fast_kernel<N, S, NINV, NFWD, MODE, GROUPS><<<(unsigned)grid, P * GROUPS, smem, st>>>(p);

@@ -152,7 +152,7 @@ __device__ inline void stockham_bfly_generic(const cpx<T>* __restrict__ in, cpx<
 // Precondition: A is fully written and the CTA is synchronised.  Returns the buffer holding the
 // result (synchronised).
 template <class T, int DIR>
-__device__ cpx<T>* fft_lines(cpx<T>* A, cpx<T>* B, int nlines, int lstr, int istr, bool line_fastest,
+__device__ __noinline__ cpx<T>* fft_lines(cpx<T>* A, cpx<T>* B, int nlines, int lstr, int istr, bool line_fastest,
                              const FftDesc& fd, const cpx<T>* __restrict__ tw) {
   const int N = fd.N;
   int Ns = 1;
