@@ -408,16 +408,19 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     abytes = algorithmic_bytes_per_call(w, spectral_carry=args.spectral_carry)
     achieved = abytes / (ms_per_step * 1e-3) / 1e9
-    traffic = None
+    traffic, ncu_ctx = None, {}
     try:  # DRAM bytes per launch/call measured once with `ncu --set full` (profiles/traffic.json)
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[args.workload]
         traffic = tr["bytes_per_trajectory_step"] * B * T
+        ncu_ctx = {k: v for k, v in tr.items() if k.startswith("ncu_")}
     except Exception:
-        pass
+        ncu_ctx = {}
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json (measured copy bandwidth)" if peaks else "fallback 6.65 TB/s",
                 "algorithmic_bytes_per_call": abytes, "kernel_launches_per_call": launches / args.steps}
+    if ncu_ctx:
+        roofline["ncu"] = ncu_ctx  # what actually bounds the kernel (one `ncu --set full` capture, see profiles/)
     if D == 1:
         # the persistent 1-D kernel is FP32/shared-memory bound (AI ~ 40 FLOP/B): report the FLOP side too
         nfft = 8 if not args.spectral_carry else 7  # real N-point transforms per ETDRK2 rollout step (Burgers)
