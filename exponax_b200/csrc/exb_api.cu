@@ -380,7 +380,7 @@ template <class T> struct PlanImpl : exb_plan {
 
   // ------------------------------------------------------------------ N-D
   bool fast_nd = false;  // set in init(): register-FFT kernels available for this (D, N, N(u))
-  int fast_tw() const { return N == 512 ? 8 : (N == 1024 ? 4 : (N == 2048 ? 2 : 16)); }
+  int fast_tw() const { return N == 512 ? 8 : (N == 1024 ? 4 : (N == 2048 ? 2 : 16)); }  // == TW of exb_fastnd_n*.cu
   int launch_col_fast(cudaStream_t st, ColParams<T>& p, int dir, long long units) {
     if constexpr (std::is_same<T, float>::value) {
       p.TW = fast_tw();

@@ -52,55 +52,87 @@ int launch_row(cudaStream_t st, const RowParams<float>& p, const char** err) {
   return EXB_OK;
 }
 
-template <int N, int TW, bool VORT = true, bool PROJ = true> int col_n(cudaStream_t st, const ColParams<float>& p, int dir, long long grid, const char** err) {
-  const int kind = p.P.kind;
-  switch (p.mode) {
-    case COL_PLAIN:
-      return dir < 0 ? launch_col<N, TW, SPlain, 1, COL_PLAIN, -1>(st, p, grid, err)
-                     : launch_col<N, TW, SPlain, 1, COL_PLAIN, +1>(st, p, grid, err);
-    case COL_INV_PRO:
-      if constexpr (VORT) {
-        if (kind == EXB_NL_VORTICITY_2D) return launch_col<N, TW, SVort, 1, COL_INV_PRO, +1>(st, p, grid, err);
-      }
-      if constexpr (PROJ) {
-        if (kind == EXB_NL_PROJECTED_3D) return launch_col<N, TW, SProj, 3, COL_INV_PRO, +1>(st, p, grid, err);
-      }
-      break;
-    case COL_FWD_EPI:
-      if constexpr (VORT) {
-        if (kind == EXB_NL_VORTICITY_2D) return launch_col<N, TW, SVort, 1, COL_FWD_EPI, -1>(st, p, grid, err);
-      }
-      if constexpr (PROJ) {
-        if (kind == EXB_NL_PROJECTED_3D) return launch_col<N, TW, SProj, 3, COL_FWD_EPI, -1>(st, p, grid, err);
-      }
-      break;
-    case COL_FWD_NL:
-      if constexpr (VORT) {
-        if (kind == EXB_NL_VORTICITY_2D) return launch_col<N, TW, SVort, 1, COL_FWD_NL, -1>(st, p, grid, err);
-      }
-      if constexpr (PROJ) {
-        if (kind == EXB_NL_PROJECTED_3D) return launch_col<N, TW, SProj, 3, COL_FWD_NL, -1>(st, p, grid, err);
-      }
-      break;
+// kinds with fast instantiations (bit mask per translation unit)
+enum : int { K_VORT = 1, K_PROJ = 2, K_GRAD2 = 4, K_POLY2 = 8, K_CONV2 = 16 };
+using SGrad2 = NlS<EXB_NL_GRADIENT_NORM, -1, 2, 1>;   // 2-D gradient norm, 1 channel (KS 2-D): 2 inverse, 1 forward
+using SPoly2 = NlS<EXB_NL_POLYNOMIAL, -1, 2, 1>;      // 2-D polynomial, 1 channel (reaction-diffusion): 1 / 1
+using SConv2 = NlS<EXB_NL_CONVECTION, 0, 2, 2>;       // 2-D convection, 2 channels, non-conservative (Burgers): 6 / 2
+
+// which fast kind (0: none) does this nonlinear function map to
+inline int fast_kind_of(const NlParams<float>& P) {
+  if (P.D == 2) {
+    if (P.kind == EXB_NL_VORTICITY_2D) return K_VORT;
+    if (P.kind == EXB_NL_GRADIENT_NORM && P.C == 1) return K_GRAD2;
+    if (P.kind == EXB_NL_POLYNOMIAL && P.C == 1) return K_POLY2;
+    if (P.kind == EXB_NL_CONVECTION && !P.single_channel && !P.conservative && P.C == 2) return K_CONV2;
+  }
+  if (P.D == 3 && P.kind == EXB_NL_PROJECTED_3D) return K_PROJ;
+  return 0;
+}
+
+template <int N, int TW, int KINDS, int MODE, int DIR>
+int col_mode_dispatch(cudaStream_t st, const ColParams<float>& p, long long grid, const char** err) {
+  const int fk = fast_kind_of(p.P);
+  if constexpr ((KINDS & K_VORT) != 0) {
+    if (fk == K_VORT) return launch_col<N, TW, SVort, 1, MODE, DIR>(st, p, grid, err);
+  }
+  if constexpr ((KINDS & K_PROJ) != 0) {
+    if (fk == K_PROJ) return launch_col<N, TW, SProj, 3, MODE, DIR>(st, p, grid, err);
+  }
+  if constexpr ((KINDS & K_GRAD2) != 0) {
+    if (fk == K_GRAD2) return launch_col<N, TW, SGrad2, 1, MODE, DIR>(st, p, grid, err);
+  }
+  if constexpr ((KINDS & K_POLY2) != 0) {
+    if (fk == K_POLY2) return launch_col<N, TW, SPoly2, 1, MODE, DIR>(st, p, grid, err);
+  }
+  if constexpr ((KINDS & K_CONV2) != 0) {
+    if (fk == K_CONV2) return launch_col<N, TW, SConv2, 2, MODE, DIR>(st, p, grid, err);
   }
   *err = "fast N-D column pass: unsupported configuration";
   return EXB_EUNSUPPORTED;
 }
 
-template <int N, bool VORT = true, bool PROJ = true> int row_n(cudaStream_t st, const RowParams<float>& p, const char** err) {
+template <int N, int TW, int KINDS> int col_n(cudaStream_t st, const ColParams<float>& p, int dir, long long grid, const char** err) {
+  switch (p.mode) {
+    case COL_PLAIN:
+      return dir < 0 ? launch_col<N, TW, SPlain, 1, COL_PLAIN, -1>(st, p, grid, err)
+                     : launch_col<N, TW, SPlain, 1, COL_PLAIN, +1>(st, p, grid, err);
+    case COL_INV_PRO:
+      return col_mode_dispatch<N, TW, KINDS, COL_INV_PRO, +1>(st, p, grid, err);
+    case COL_FWD_EPI:
+      return col_mode_dispatch<N, TW, KINDS, COL_FWD_EPI, -1>(st, p, grid, err);
+    case COL_FWD_NL:
+      return col_mode_dispatch<N, TW, KINDS, COL_FWD_NL, -1>(st, p, grid, err);
+  }
+  *err = "fast N-D column pass: unsupported configuration";
+  return EXB_EUNSUPPORTED;
+}
+
+template <int N, int KINDS> int row_n(cudaStream_t st, const RowParams<float>& p, const char** err) {
   switch (p.mode) {
     case ROW_R2C:
       return launch_row<N, SPlain, 1, 1, ROW_R2C>(st, p, err);
     case ROW_C2R:
       return launch_row<N, SPlain, 1, 1, ROW_C2R>(st, p, err);
-    case ROW_NL:
-      if constexpr (VORT) {
-        if (p.P.kind == EXB_NL_VORTICITY_2D) return launch_row<N, SVort, 4, 1, ROW_NL>(st, p, err);
+    case ROW_NL: {
+      const int fk = fast_kind_of(p.P);
+      if constexpr ((KINDS & K_VORT) != 0) {
+        if (fk == K_VORT) return launch_row<N, SVort, 4, 1, ROW_NL>(st, p, err);
       }
-      if constexpr (PROJ) {
-        if (p.P.kind == EXB_NL_PROJECTED_3D) return launch_row<N, SProj, 6, 3, ROW_NL>(st, p, err);
+      if constexpr ((KINDS & K_PROJ) != 0) {
+        if (fk == K_PROJ) return launch_row<N, SProj, 6, 3, ROW_NL>(st, p, err);
+      }
+      if constexpr ((KINDS & K_GRAD2) != 0) {
+        if (fk == K_GRAD2) return launch_row<N, SGrad2, 2, 1, ROW_NL>(st, p, err);
+      }
+      if constexpr ((KINDS & K_POLY2) != 0) {
+        if (fk == K_POLY2) return launch_row<N, SPoly2, 1, 1, ROW_NL>(st, p, err);
+      }
+      if constexpr ((KINDS & K_CONV2) != 0) {
+        if (fk == K_CONV2) return launch_row<N, SConv2, 6, 2, ROW_NL>(st, p, err);
       }
       break;
+    }
   }
   *err = "fast N-D row pass: unsupported configuration";
   return EXB_EUNSUPPORTED;

@@ -1,9 +1,9 @@
-// N = 1024 instantiations (3-D projected convection + plain passes: config c5 at reduced size).
+// N = 1024 instantiations of the fast 2-D / 3-D pass kernels.
 #include "exb_fastnd_impl.cuh"
 
 int exb_fastnd_col_n1024(cudaStream_t st, const ColParams<float>& p, int dir, long long grid, const char** err) {
-  return col_n<1024, 4, false, true>(st, p, dir, grid, err);
+  return col_n<1024, 4, K_PROJ>(st, p, dir, grid, err);
 }
 int exb_fastnd_row_n1024(cudaStream_t st, const RowParams<float>& p, const char** err) {
-  return row_n<1024, false, true>(st, p, err);
+  return row_n<1024, K_PROJ>(st, p, err);
 }

@@ -2,6 +2,8 @@
 #include "exb_fastnd_impl.cuh"
 
 int exb_fastnd_col_n512(cudaStream_t st, const ColParams<float>& p, int dir, long long grid, const char** err) {
-  return col_n<512, 8>(st, p, dir, grid, err);
+  return col_n<512, 8, K_VORT | K_PROJ | K_GRAD2 | K_POLY2 | K_CONV2>(st, p, dir, grid, err);
 }
-int exb_fastnd_row_n512(cudaStream_t st, const RowParams<float>& p, const char** err) { return row_n<512>(st, p, err); }
+int exb_fastnd_row_n512(cudaStream_t st, const RowParams<float>& p, const char** err) {
+  return row_n<512, K_VORT | K_PROJ | K_GRAD2 | K_POLY2 | K_CONV2>(st, p, err);
+}

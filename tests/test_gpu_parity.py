@@ -746,3 +746,46 @@ def test_full_size_round_trips_and_linearity():
         w[-1] = 1.0
         e_spec = float(((uh.abs() ** 2) * w).sum()) / N**D
         assert e_spec == pytest.approx(float((u**2).sum()), rel=1e-4)
+
+
+# ------------------------------------------------------------------ fast N-D kernel coverage (N = 128, 256, 512)
+def _fast_nd_cases():
+    return [
+        ("KuramotoSivashinsky", dict(), 2, 30.0, 0.1, 1),
+        ("FisherKPP", dict(reactivity=2.0), 2, 10.0, 0.01, 1),
+        ("AllenCahn", dict(), 2, 10.0, 0.01, 1),
+        ("Burgers", dict(), 2, 1.0, 0.001, 2),
+        ("NavierStokesVorticity", dict(), 2, 2 * np.pi, 0.01, 1),
+        ("KolmogorovFlowVorticity", dict(order=4), 2, 2 * np.pi, 0.01, 1),
+    ]
+
+
+@pytest.mark.parametrize("N", [128, 256])
+@pytest.mark.parametrize("name,kw,D,L,dt,C", _fast_nd_cases(), ids=lambda v: v if isinstance(v, str) else "")
+def test_fast_nd_kernels_2d_kinds(name, kw, D, L, dt, C, N):
+    """Register-FFT pass kernels for every 2-D nonlinear function that has a fast instantiation
+    (gradient norm, polynomial, 2-channel convection, vorticity), incl. dealiasing-aware pruning."""
+    u0 = 0.7 * ic(D, N, range(3), C=C)
+    mod = ex.stepper.reaction if hasattr(ex.stepper.reaction, name) else ex.stepper
+    st = getattr(mod, name)(D, L, N, dt, **kw)
+    ost = getattr(ox, name)(D, L, N, dt, **kw)
+    assert rel(host(ex.vmap(st)(dev(u0))), per_sample(ost, u0)) < F32_STEP
+    uh = ox.fft(u0[0], num_spatial_dims=D)
+    assert rel(host(st._nonlinear_fun(dev(uh))), ost._integrator._nonlinear_fun(uh)) < 5e-6
+    got = host(ex.vmap(ex.repeat(ex.RepeatedStepper(st, 2), 2))(dev(u0)))
+    assert rel(got, per_sample(ox.repeat(ox.RepeatedStepper(ost, 2), 2), u0)) < 5e-5
+
+
+def test_fast_nd_kernel_3d_n128_and_generic_agree():
+    import os
+    L, N, dt = 2 * np.pi, 128, 0.005
+    g = ox.make_grid(3, L, N)
+    u0 = dev(np.stack([np.sin(g[0]) * np.cos(g[1]) * np.cos(g[2]), -np.cos(g[0]) * np.sin(g[1]) * np.cos(g[2]),
+                       0.2 * np.sin(3 * g[1]) * np.cos(2 * g[2])]).astype(np.float32))
+    fast = host(ex.repeat(ex.stepper.KolmogorovFlowVelocity(3, L, N, dt), 2)(u0))
+    os.environ["EXB_DISABLE_FAST_ND"] = "1"
+    try:
+        slow = host(ex.repeat(ex.stepper.KolmogorovFlowVelocity(3, L, N, dt), 2)(u0))
+    finally:
+        del os.environ["EXB_DISABLE_FAST_ND"]
+    assert rel(fast, slow) < 5e-6
