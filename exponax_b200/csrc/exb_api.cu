@@ -284,6 +284,14 @@ template <class T> struct PlanImpl : exb_plan {
       if (rc) return rc;
     }
     nscr = etdrk_num_scratch(order);
+    if (D >= 2 && nranks == 1) {
+      // chunk so that one chunk's working set fits comfortably in L2 -- only worthwhile when several
+      // trajectories fit (small fields); big fields are streamed through HBM pass by pass
+      const double per_traj = ((double)(nscr + 1) * C + (P.n_inv > C ? P.n_inv : C) + (P.n_fwd > C ? P.n_fwd : C)) *
+                              (double)M * sizeof(cpx<T>);
+      const double budget = 96.0 * 1024 * 1024;
+      nd_chunk = per_traj * 6 <= budget ? (long long)(budget / per_traj) : 0;
+    }
     if constexpr (std::is_same<T, float>::value) {
       fast_nd = D >= 2 && !getenv("EXB_DISABLE_FAST_ND") && exb_fastnd_supported(D, N, P);
     }
@@ -761,10 +769,43 @@ template <class T> struct PlanImpl : exb_plan {
     }
     int rc = need_ws(ws, batch);
     if (rc) return rc;
+    // Trajectory-major chunking: trajectories are independent, so the batch is processed a chunk at
+    // a time through ALL steps.  A chunk's intermediates (n_inv + n_fwd fields, stage buffers) are
+    // sized to stay resident in the 126 MB L2 between the passes that produce and consume them.
+    const long long cb = chunk_batch(batch);
+    const long long fsz0 = (long long)C * G;
+    const long long Tn0 = final_only ? 1 : n_saved + (include_init ? 1 : 0);
+    for (long long b0 = 0; b0 < batch; b0 += cb) {
+      const long long nb = batch - b0 < cb ? batch - b0 : cb;
+      const T* u0c = (const T*)u0 + (size_t)b0 * fsz0;
+      T* outc = (T*)out + (size_t)b0 * ((final_only || layout_tb) ? fsz0 : Tn0 * fsz0);
+      rc = rollout_nd_chunk(st, nb, batch, n_saved, substeps, flags, u0c, outc, ws);
+      if (rc) return rc;
+    }
+    return EXB_OK;
+  }
+
+  // number of trajectories processed together (N-D).  EXB_ND_CHUNK overrides (0 = whole batch).
+  long long chunk_batch(long long batch) const {
+    if (const char* e = getenv("EXB_ND_CHUNK")) {
+      long long v = atoll(e);
+      return v <= 0 ? batch : (v < batch ? v : batch);
+    }
+    return nd_chunk > 0 && nd_chunk < batch ? nd_chunk : batch;
+  }
+  long long nd_chunk = 0;  // set in init()
+
+  int rollout_nd_chunk(cudaStream_t st, long long batch, long long batch_total, int64_t n_saved, int substeps,
+                       unsigned flags, const T* u0, T* out, void* ws) {
+    const bool include_init = flags & EXB_ROLLOUT_INCLUDE_INIT;
+    const bool layout_tb = flags & EXB_ROLLOUT_LAYOUT_TB;
+    const bool final_only = flags & EXB_ROLLOUT_FINAL_ONLY;
+    const bool spectral_carry = flags & EXB_ROLLOUT_SPECTRAL_CARRY;
+    int rc;
     Ws w = carve(ws, batch);
     const long long fsz = (long long)C * G;
     const long long Tn = final_only ? 1 : n_saved + (include_init ? 1 : 0);
-    T* o = (T*)out;
+    T* o = out;
     auto slot = [&](long long s, long long& bs) -> T* {
       if (final_only) {
         bs = fsz;
@@ -772,7 +813,7 @@ template <class T> struct PlanImpl : exb_plan {
       }
       if (layout_tb) {
         bs = fsz;
-        return o + (size_t)s * batch * fsz;
+        return o + (size_t)s * batch_total * fsz;
       }
       bs = Tn * fsz;
       return o + (size_t)s * fsz;
