@@ -284,14 +284,10 @@ template <class T> struct PlanImpl : exb_plan {
       if (rc) return rc;
     }
     nscr = etdrk_num_scratch(order);
-    if (D >= 2 && nranks == 1) {
-      // chunk so that one chunk's working set fits comfortably in L2 -- only worthwhile when several
-      // trajectories fit (small fields); big fields are streamed through HBM pass by pass
-      const double per_traj = ((double)(nscr + 1) * C + (P.n_inv > C ? P.n_inv : C) + (P.n_fwd > C ? P.n_fwd : C)) *
-                              (double)M * sizeof(cpx<T>);
-      const double budget = 96.0 * 1024 * 1024;
-      nd_chunk = per_traj * 6 <= budget ? (long long)(budget / per_traj) : 0;
-    }
+    // Trajectory-major chunking (EXB_ND_CHUNK) is OFF by default: measured on B200 (c3, 512^2, B=512) the
+    // pass kernels are issue-bound, not DRAM-bound, so keeping a chunk's intermediates in L2 does not pay and the
+    // smaller grids lose occupancy (chunk 11: 0.31, chunk 48: 0.38, whole batch: 0.43 of the HBM roofline).
+    nd_chunk = 0;
     if constexpr (std::is_same<T, float>::value) {
       fast_nd = D >= 2 && !getenv("EXB_DISABLE_FAST_ND") && exb_fastnd_supported(D, N, P);
     }
@@ -769,9 +765,8 @@ template <class T> struct PlanImpl : exb_plan {
     }
     int rc = need_ws(ws, batch);
     if (rc) return rc;
-    // Trajectory-major chunking: trajectories are independent, so the batch is processed a chunk at
-    // a time through ALL steps.  A chunk's intermediates (n_inv + n_fwd fields, stage buffers) are
-    // sized to stay resident in the 126 MB L2 between the passes that produce and consume them.
+    // Optional trajectory-major chunking (EXB_ND_CHUNK=n): trajectories are independent, so the batch can
+    // be processed n at a time through ALL steps (bounds the live workspace; see init() for why it is off).
     const long long cb = chunk_batch(batch);
     const long long fsz0 = (long long)C * G;
     const long long Tn0 = final_only ? 1 : n_saved + (include_init ? 1 : 0);
