@@ -11,7 +11,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libexb.so")
+LIB_PATH = os.environ.get("EXB_LIB") or os.path.join(_HERE, "libexb.so")  # EXB_LIB: A/B experiments
 
 EXB_F32, EXB_F64 = 0, 1
 (NL_ZERO, NL_CONVECTION, NL_GRADIENT_NORM, NL_POLYNOMIAL, NL_VORTICITY_2D, NL_PROJECTED_3D, NL_GENERAL,

@@ -38,8 +38,9 @@ int launch_col(cudaStream_t st, const ColParams<float>& p, long long grid, const
 template <int N, class S, int NINV, int NFWD, int MODE>
 int launch_row(cudaStream_t st, const RowParams<float>& p, const char** err) {
   constexpr int P = N / 8, GROUPS = 256 / P;
-  const bool stash = false;  // see row_fast_kernel: STASH is compiled out
-  const size_t smem = (size_t)(Fft8Tw<N>::SIZE + GROUPS * (N + N / 8 + (stash ? NINV * N : 0))) * sizeof(cpx<float>);
+  const bool prefetch = MODE == ROW_NL && (EXB_ROW_PREFETCH != 0);  // staging rows, see row_fast_kernel
+  const int nhp = (N / 2 + 1 + 7) / 8 * 8;
+  const size_t smem = (size_t)(Fft8Tw<N>::SIZE + GROUPS * (N + N / 8 + (prefetch ? 2 * nhp : 0))) * sizeof(cpx<float>);
   if (int rc = set_smem(row_fast_kernel<N, S, NINV, NFWD, MODE, GROUPS>, smem, err)) return rc;
   const long long npairs = (p.rows + 1) / 2 * p.batch;
   const long long grid = (npairs + GROUPS - 1) / GROUPS;

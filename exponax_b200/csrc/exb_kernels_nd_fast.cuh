@@ -13,7 +13,19 @@
 #include "exb_fft8.cuh"
 #include "exb_kernels_nd.cuh"
 
+#ifndef EXB_ROW_PREFETCH
+#define EXB_ROW_PREFETCH 1
+#endif
+
 namespace exb {
+
+// 8-byte asynchronous global -> shared copy (LDGSTS) and its completion primitives
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------- column pass
 template <int N, int TW, class S, int NFWD, int MODE, int DIR>
@@ -175,13 +187,18 @@ row_fast_kernel(const RowParams<float> p) {
   // thread-private slice of shared memory (conflict-free, no synchronisation) instead of
   // NINV * 16 registers, which keeps the kernel at 2-3 CTAs per SM.
   constexpr bool STASH = false && (MODE == ROW_NL) && NINV >= 2;  // measured slower on B200 (r01g): off
-  constexpr int SLOT = XB + (STASH ? NINV * N : 0);  // complex elements per group
+  // ROW_NL: the half-complex rows of inverse line f+1 are fetched with cp.async into a small staging
+  // buffer while line f is being transformed (global-load latency off the critical path, no registers).
+  constexpr bool PREFETCH = (MODE == ROW_NL) && (EXB_ROW_PREFETCH != 0);
+  constexpr int NHP = (Nh + 7) / 8 * 8;
+  constexpr int SLOT = XB + (STASH ? NINV * N : 0) + (PREFETCH ? 2 * NHP : 0);  // complex elements per group
   cpx<float>* tw = reinterpret_cast<cpx<float>*>(smem_raw);
   Fft8Tw<N>::fill(tw, p.tw);
   const int g = threadIdx.x / P, j = threadIdx.x % P;
   cpx<float>* gbase = tw + Fft8Tw<N>::SIZE + (size_t)g * SLOT;
   ExLine ex{gbase, P <= 32 ? 0 : 1 + g, P};
   cpx<float>* stash = gbase + XB;
+  cpx<float>* stage = gbase + XB + (STASH ? NINV * N : 0);
   __syncthreads();
   const NlParams<float>& Pn = p.P;
   const long long npairs = (p.rows + 1) / 2;
@@ -291,10 +308,44 @@ row_fast_kernel(const RowParams<float> p) {
     }
   } else {
     cpx<float> z[NINV][8];
+    if (PREFETCH) {
+      auto prefetch = [&](int f) {
+        const cpx<float>* a = in + ((size_t)f * p.rows + r1) * Nh;
+        const cpx<float>* c = in + ((size_t)f * p.rows + r2) * Nh;
+        for (int k = j; k < Nh && k <= kin; k += P) {
+          if (has1) cp_async8(stage + k, a + k);
+          if (has2) cp_async8(stage + NHP + k, c + k);
+        }
+        cp_async_commit();
+      };
+      prefetch(0);
 #pragma unroll
-    for (int f = 0; f < NINV; ++f) {
-      load_packed(in + ((size_t)f * p.rows + r1) * Nh, in + ((size_t)f * p.rows + r2) * Nh, z[f]);
-      fft8_run<N, +1>(z[f], ex, j, tw);
+      for (int f = 0; f < NINV; ++f) {
+        cp_async_wait_all();
+        ex.sync();  // the staged rows are visible to the whole group
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int n = j + P * q;
+          const bool upper = n > N / 2;
+          const int k = upper ? N - n : n;
+          cpx<float> F1 = (has1 && k <= kin) ? stage[k] : zero;
+          cpx<float> F2 = (has2 && k <= kin) ? stage[NHP + k] : zero;
+          cpx<float> zz;
+          if (k == 0 || 2 * k == N) zz = cpx<float>(F1.x, F2.x);
+          else if (!upper) zz = cpx<float>(F1.x - F2.y, F1.y + F2.x);
+          else zz = cpx<float>(F1.x + F2.y, F2.x - F1.y);
+          z[f][q] = zz;
+        }
+        ex.sync();  // staging buffer consumed
+        if (f + 1 < NINV) prefetch(f + 1);
+        fft8_run<N, +1>(z[f], ex, j, tw);
+      }
+    } else {
+#pragma unroll
+      for (int f = 0; f < NINV; ++f) {
+        load_packed(in + ((size_t)f * p.rows + r1) * Nh, in + ((size_t)f * p.rows + r2) * Nh, z[f]);
+        fft8_run<N, +1>(z[f], ex, j, tw);
+      }
     }
 #pragma unroll
     for (int q = 0; q < 8; ++q) {

@@ -789,3 +789,55 @@ def test_fast_nd_kernel_3d_n128_and_generic_agree():
     finally:
         del os.environ["EXB_DISABLE_FAST_ND"]
     assert rel(fast, slow) < 5e-6
+
+
+def test_forced_stepper_and_aux_rollout():
+    """ForcedStepper == stepper(u + dt f) (tests/test_forced_stepper.py:7-81); rollout/repeat with aux."""
+    N, L, dt = 64, 2 * np.pi, 0.01
+    u0 = ic(1, N, [0])[0]
+    f = 0.3 * ic(1, N, [1])[0]
+    st = ex.stepper.Burgers(1, L, N, dt)
+    ost = ox.Burgers(1, L, N, dt)
+    fs = ex.ForcedStepper(st)
+    got = host(fs(dev(u0), dev(f)))
+    assert rel(got, ost(u0 + np.float32(dt) * f)) < F32_STEP
+    trj = host(ex.rollout(fs, 3, takes_aux=True, constant_aux=True)(dev(u0), dev(f)))
+    u = u0
+    for _ in range(3):
+        u = ost(u + np.float32(dt) * f)
+    assert trj.shape == (3, 1, N) and rel(trj[-1], u) < 5e-5
+    uh, fh = ox.fft(u0, num_spatial_dims=1), ox.fft(f, num_spatial_dims=1)
+    assert rel(host(fs.step_fourier(dev(uh), dev(fh))), ost.step_fourier(uh + np.float32(dt) * fh)) < F32_STEP
+
+
+def test_user_stepper_with_builtin_nonlinear_fun_runs_fused():
+    """A user subclass of BaseStepper that only changes the linear operator (the reference's extension
+    protocol, docs/examples/creating_your_own_solvers_1d.ipynb) still runs on the fused kernels."""
+    class DampedBurgers(ex.BaseStepper):
+        def __init__(self, D, L, N, dt):
+            super().__init__(D, L, N, dt, num_channels=1, order=2)
+
+        def _build_linear_operator(self, dop):
+            return 0.05 * ex.spectral.build_laplace_operator(dop) - 0.3
+
+        def _build_nonlinear_fun(self, dop):
+            return ex.nonlin_fun.ConvectionNonlinearFun(self.num_spatial_dims, self.num_points,
+                                                        derivative_operator=dop, dealiasing_fraction=2 / 3)
+
+    class ODamped(ox.BaseStepper):
+        def __init__(self, D, L, N, dt):
+            super().__init__(D, L, N, dt, num_channels=1, order=2)
+
+        def _build_linear_operator(self, dop):
+            return np.float32(0.05) * ox.build_laplace_operator(dop) - np.float32(0.3)
+
+        def _build_nonlinear_fun(self, dop):
+            return ox.ConvectionNonlinearFun(1, self.num_points, derivative_operator=dop, dealiasing_fraction=2 / 3)
+
+    N, L, dt = 256, 2 * np.pi, 0.01
+    u0 = ic(1, N, range(4))
+    st = DampedBurgers(1, L, N, dt)
+    assert st._plan_available()
+    got = host(ex.vmap(ex.rollout(st, 10))(dev(u0)))
+    ref = per_sample(ox.rollout(ODamped(1, L, N, dt), 10), u0)
+    assert rel(got, ref) < 2e-5
