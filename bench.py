@@ -295,6 +295,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--spectral-carry", action="store_true")
     ap.add_argument("--N", type=int, default=None, help="override the grid size (c5)")
+    ap.add_argument("--cuda-graph", action="store_true", help="replay the fused call from a captured CUDA graph")
     ap.add_argument("--no-overlap", action="store_true", help="c5: do not pipeline transposes against passes")
     args = ap.parse_args()
 
@@ -354,7 +355,7 @@ def main():
     elif w["final_only"]:
         fn = ex.vmap(ex.repeat(stepper, T, spectral_carry=args.spectral_carry))
     else:
-        fn = ex.vmap(ex.rollout(stepper, T, spectral_carry=args.spectral_carry))
+        fn = ex.vmap(ex.rollout(stepper, T, spectral_carry=args.spectral_carry, cuda_graph=args.cuda_graph))
     plan = stepper._plan()
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")  # > 126 MB L2
 

@@ -154,7 +154,7 @@ class BaseStepper(ABC):
         return A.from_device(out, kind)
 
     def _rollout_batched(self, u0, n: int, *, include_init: bool, layout_tb: bool, final_only: bool,
-                         substeps: int = 1, spectral_carry: bool = False):
+                         substeps: int = 1, spectral_carry: bool = False, cuda_graph: bool = False):
         """Fused `rollout`/`repeat` over a batch: u0 (B.., C, N..) -> (B.., T, C, N..) /
         (T, B.., C, N..) / (B.., C, N..)."""
         t, kind = A.to_device(u0, self._dtype)
@@ -176,10 +176,45 @@ class BaseStepper(ABC):
         flags |= nat.ROLLOUT_LAYOUT_TB if layout_tb else 0
         flags |= nat.ROLLOUT_FINAL_ONLY if final_only else 0
         flags |= nat.ROLLOUT_SPECTRAL_CARRY if spectral_carry else 0
+        if cuda_graph:
+            return A.from_device(self._rollout_graph(plan, t, shape, batch, n, substeps, flags), kind)
         ws = sp.workspace(plan.workspace_bytes(batch))
         nat.check(nat.lib().exb_rollout(plan.handle, A.stream_ptr(), batch, n, substeps, flags, A.ptr(t),
                                         A.ptr(out), A.ptr(ws)))
         return A.from_device(out, kind)
+
+    def _rollout_graph(self, plan, t, shape, batch, n, substeps, flags):
+        """Replay the launch sequence of one fused rollout from a captured CUDA graph (the library only
+        enqueues on the stream it is given, so the whole call is capturable).  Pays off for N-D problems
+        whose hundreds of small pass launches are launch-bound; buffers are owned by the graph entry."""
+        key = (tuple(t.shape), t.dtype, n, substeps, flags, A.torch.cuda.current_device())
+        cache = self.__dict__.setdefault("_graphs", {})
+        ent = cache.get(key)
+        if ent is None:
+            torch = A.torch
+            static_in = torch.empty_like(t)
+            static_out = torch.empty(shape, dtype=t.dtype, device="cuda")
+            nbytes = plan.workspace_bytes(batch)
+            ws = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device="cuda")
+            static_in.copy_(t)
+
+            def enqueue():
+                nat.check(nat.lib().exb_rollout(plan.handle, A.stream_ptr(), batch, n, substeps, flags,
+                                                A.ptr(static_in), A.ptr(static_out), A.ptr(ws)))
+
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                enqueue()  # warm-up outside capture (function attributes, lazy module load)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                enqueue()
+            ent = cache[key] = (graph, static_in, static_out, ws)
+        graph, static_in, static_out, _ = ent
+        static_in.copy_(t)
+        graph.replay()
+        return static_out.clone()
 
     # ---- reference API -------------------------------------------------------------------
     def step(self, u):

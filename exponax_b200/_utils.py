@@ -70,10 +70,10 @@ def _stack(xs):
 
 
 class _Rollout:
-    def __init__(self, stepper_fn, n, include_init, takes_aux, constant_aux, spectral_carry):
+    def __init__(self, stepper_fn, n, include_init, takes_aux, constant_aux, spectral_carry, cuda_graph=False):
         self.stepper_fn, self.n = stepper_fn, n
         self.include_init, self.takes_aux, self.constant_aux = include_init, takes_aux, constant_aux
-        self.spectral_carry = spectral_carry
+        self.spectral_carry, self.cuda_graph = spectral_carry, cuda_graph
 
     def _call(self, u_0, *aux, batched=False):
         tgt = None if self.takes_aux else _native_target(self.stepper_fn)
@@ -86,7 +86,8 @@ class _Rollout:
                 )
             # rollout(vmap(stepper)) stacks time first: (T, B, ...); vmap(rollout(stepper)): (B, T, ...)
             return st._rollout_batched(u_0, self.n, include_init=self.include_init, layout_tb=vm and not batched,
-                                       final_only=False, substeps=sub, spectral_carry=self.spectral_carry)
+                                       final_only=False, substeps=sub, spectral_carry=self.spectral_carry,
+                                       cuda_graph=self.cuda_graph)
         # reference loop (exponax/_utils.py:137-186) for arbitrary callables
         if batched:
             return _stack([self._call(u_0[i], *(a[i] for a in aux)) for i in range(len(u_0))])
@@ -107,10 +108,10 @@ class _Rollout:
 
 
 class _Repeat:
-    def __init__(self, stepper_fn, n, takes_aux, constant_aux, spectral_carry):
+    def __init__(self, stepper_fn, n, takes_aux, constant_aux, spectral_carry, cuda_graph=False):
         self.stepper_fn, self.n = stepper_fn, n
         self.takes_aux, self.constant_aux = takes_aux, constant_aux
-        self.spectral_carry = spectral_carry
+        self.spectral_carry, self.cuda_graph = spectral_carry, cuda_graph
 
     def _call(self, u_0, *aux, batched=False):
         tgt = None if self.takes_aux else _native_target(self.stepper_fn)
@@ -122,7 +123,7 @@ class _Repeat:
                  operation use `jax.vmap` on this function."""
                 )
             return st._rollout_batched(u_0, self.n, include_init=False, layout_tb=False, final_only=True,
-                                       substeps=sub, spectral_carry=self.spectral_carry)
+                                       substeps=sub, spectral_carry=self.spectral_carry, cuda_graph=self.cuda_graph)
         if batched:
             return _stack([self._call(u_0[i], *(a[i] for a in aux)) for i in range(len(u_0))])
         u = u_0
@@ -153,15 +154,17 @@ def _like(x, ref):
 
 
 def rollout(stepper_fn, n: int, *, include_init: bool = False, takes_aux: bool = False,
-            constant_aux: bool = True, spectral_carry: bool = False):
+            constant_aux: bool = True, spectral_carry: bool = False, cuda_graph: bool = False):
     """Autoregressive rollout returning the stacked trajectory (exponax/_utils.py:92-186).
 
     `spectral_carry=True` (extension) keeps the carry in Fourier space between saved steps
-    instead of the reference's ifft -> fft round trip (identical up to rounding)."""
-    return _Rollout(stepper_fn, n, include_init, takes_aux, constant_aux, spectral_carry)
+    instead of the reference's ifft -> fft round trip (identical up to rounding).
+    `cuda_graph=True` (extension) captures the launch sequence of the fused call once per input shape
+    and replays it (worth it for N-D grids whose many small pass launches are launch-bound)."""
+    return _Rollout(stepper_fn, n, include_init, takes_aux, constant_aux, spectral_carry, cuda_graph)
 
 
 def repeat(stepper_fn, n: int, *, takes_aux: bool = False, constant_aux: bool = True,
-           spectral_carry: bool = False):
+           spectral_carry: bool = False, cuda_graph: bool = False):
     """Apply the stepper n times, return only the final state (exponax/_utils.py:189-254)."""
-    return _Repeat(stepper_fn, n, takes_aux, constant_aux, spectral_carry)
+    return _Repeat(stepper_fn, n, takes_aux, constant_aux, spectral_carry, cuda_graph)
