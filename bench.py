@@ -438,8 +438,8 @@ def main():
         pinned_out = torch.empty(res_shape, dtype=out.dtype, pin_memory=True)
         nchunk = 8 if B >= 64 else 1
         bounds = np.linspace(0, B, nchunk + 1).astype(int)
-        # N-D plans share one workspace: keep their chunks on one stream
-        streams = [torch.cuda.Stream() for _ in range(2 if D == 1 else 1)]
+        # two streams: the D2H copy of chunk i overlaps the compute of chunk i+1 (scratch is per stream)
+        streams = [torch.cuda.Stream() for _ in range(2)]
 
         def e2e_call():
             # chunked over the batch so the D2H of chunk i overlaps the compute of chunk i+1

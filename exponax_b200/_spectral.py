@@ -186,13 +186,14 @@ _WS = {}
 
 
 def workspace(nbytes: int):
-    """Grow-only per-device scratch buffer handed to libexb as its workspace."""
+    """Grow-only scratch buffer handed to libexb as its workspace, one per (device, stream): calls
+    enqueued on different streams may overlap on the GPU and must not share scratch memory."""
     if nbytes <= 0:
         return None
-    dev = A.torch.cuda.current_device()
-    w = _WS.get(dev)
+    key = (A.torch.cuda.current_device(), A.torch.cuda.current_stream().cuda_stream)
+    w = _WS.get(key)
     if w is None or w.numel() < nbytes:
-        _WS[dev] = w = A.torch.empty(int(nbytes), dtype=A.torch.uint8, device="cuda")
+        _WS[key] = w = A.torch.empty(int(nbytes), dtype=A.torch.uint8, device="cuda")
     return w
 
 
