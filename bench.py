@@ -79,6 +79,7 @@ def run_c5(args, w, rank, world, local_rank):
     slab = ex.SlabStepper.navier_stokes_velocity(L, N, w["dt"], injection_mode=4, **w["kw"])
     slab.plan()
     slab.overlap = not args.no_overlap
+    slab.raw_exchange = not args.no_raw_exchange
     t_ctor = time.time() - t0
     # Taylor-Green + small-mode perturbation generated on the device, slab by slab (never on the host)
     n = N // world
@@ -296,6 +297,7 @@ def main():
     ap.add_argument("--spectral-carry", action="store_true")
     ap.add_argument("--N", type=int, default=None, help="override the grid size (c5)")
     ap.add_argument("--cuda-graph", action="store_true", help="replay the fused call from a captured CUDA graph")
+    ap.add_argument("--no-raw-exchange", action="store_true", help="c5: pack / unpack copies around the all-to-all")
     ap.add_argument("--no-overlap", action="store_true", help="c5: do not pipeline transposes against passes")
     args = ap.parse_args()
 

@@ -19,6 +19,7 @@ EXB_F32, EXB_F64 = 0, 1
 ROLLOUT_INCLUDE_INIT, ROLLOUT_LAYOUT_TB, ROLLOUT_FINAL_ONLY, ROLLOUT_SPECTRAL_CARRY = 1, 2, 4, 8
 (SLAB_ROW_R2C, SLAB_ROW_C2R, SLAB_COL1_FWD, SLAB_COL1_INV, SLAB_COL0_FWD, SLAB_COL0_INV, SLAB_COL0_INV_PRO,
  SLAB_ROW_NL, SLAB_COL0_FWD_EPI, SLAB_COL1_INV_NL, SLAB_COL1_FWD_NL) = range(11)
+SLAB_SEGMENTED = 0x100
 EXB_MAX_POLY = 8
 
 

@@ -82,6 +82,21 @@ def transpose_b_to_a(x: torch.Tensor, group=None, out: torch.Tensor | None = Non
     return out
 
 
+def exchange_b_to_a_raw(x_b: torch.Tensor, out_a: torch.Tensor, group=None):
+    """All-to-all of ONE field from the spectral slab (N, n, K) straight into `out_a`, which then holds the
+    raw peer-major layout [peer][x][k1 within peer][K] (EXB_SLAB_SEGMENTED): no pack, no unpack."""
+    rank, P = _group_info(group)
+    N, n, K = x_b.shape
+    dist.all_to_all_single(out_a.view(P, n, n, K), x_b.view(P, n, n, K), group=group)
+
+
+def exchange_a_to_b_raw(x_a: torch.Tensor, out_b: torch.Tensor, group=None):
+    """Inverse of `exchange_b_to_a_raw`: raw peer-major A buffer -> spectral slab (N, n, K)."""
+    rank, P = _group_info(group)
+    N, n, K = out_b.shape
+    dist.all_to_all_single(out_b.view(P, n, n, K), x_a.view(P, n, n, K), group=group)
+
+
 class _ShapeOnly:
     """stands in for a freed operator array where only its shape is consulted"""
 
@@ -177,6 +192,7 @@ class SlabStepper:
         self._plan = None
         self._bufs = {}
         self.overlap = True   # pipeline the all-to-all transposes against the passes (two streams)
+        self.raw_exchange = True  # no pack / unpack copies around the all-to-all (EXB_SLAB_SEGMENTED)
 
     # ---- plan with the LOCAL slices of the coefficient tables --------------------------------
     def _local(self, arr):
@@ -289,16 +305,23 @@ class SlabStepper:
         winv_a = self._buf("winv_a", self.n_inv)
         wfwd_a = self._buf("wfwd_a", self.n_fwd)
         overlap = self.overlap and self.P > 1
+        # multi-rank: layout A stays in the raw all-to-all (peer-major) order for the whole N(u) evaluation --
+        # the axis-1 passes address it with segmented lines, the row pass is order-agnostic
+        seg = nat.SLAB_SEGMENTED if (self.raw_exchange and self.P > 1) else 0
+        b2a = exchange_b_to_a_raw if seg else (lambda xb, oa, group=None: transpose_b_to_a(xb[None], group, out=oa[None]))
+        a2b = exchange_a_to_b_raw if seg else (lambda xa, ob, group=None: transpose_a_to_b(xa[None], group, out=ob[None]))
         for s in range(self.order):
             si = etdrk_stage_input(self.order, s)
             src = uh if si < 0 else S[si]
             if not overlap:
                 self._pass(nat.SLAB_COL0_INV_PRO, self.n_inv, src, winv_b)
-                transpose_b_to_a(winv_b, self.group, out=winv_a)
-                self._pass(nat.SLAB_COL1_INV_NL, self.n_inv, winv_a, winv_a)
+                for f in range(self.n_inv):
+                    b2a(winv_b[f], winv_a[f], self.group)
+                self._pass(nat.SLAB_COL1_INV_NL | seg, self.n_inv, winv_a, winv_a)
                 self._pass(nat.SLAB_ROW_NL, self.n_inv, winv_a, wfwd_a)
-                self._pass(nat.SLAB_COL1_FWD_NL, self.n_fwd, wfwd_a, wfwd_a)
-                transpose_a_to_b(wfwd_a, self.group, out=wfwd_b)
+                self._pass(nat.SLAB_COL1_FWD_NL | seg, self.n_fwd, wfwd_a, wfwd_a)
+                for g in range(self.n_fwd):
+                    a2b(wfwd_a[g], wfwd_b[g], self.group)
             else:
                 # field-by-field pipeline on two streams: the all-to-all of field f (comm stream, NVLink)
                 # runs while the compute stream works on the prologue of field f+1 / the axis-1 pass of
@@ -312,22 +335,22 @@ class SlabStepper:
                     ready.record(main)
                     with torch.cuda.stream(comm):
                         comm.wait_event(ready)
-                        transpose_b_to_a(winv_b[f:f + 1], self.group, out=winv_a[f:f + 1])
+                        b2a(winv_b[f], winv_a[f], self.group)
                         ev = torch.cuda.Event()
                         ev.record(comm)
                     arrived.append(ev)
                 for f in range(self.n_inv):
                     main.wait_event(arrived[f])
-                    self._pass(nat.SLAB_COL1_INV_NL, 1, winv_a[f], winv_a[f])
+                    self._pass(nat.SLAB_COL1_INV_NL | seg, 1, winv_a[f], winv_a[f])
                 self._pass(nat.SLAB_ROW_NL, self.n_inv, winv_a, wfwd_a)
                 arrived = []
                 for g in range(self.n_fwd):
-                    self._pass(nat.SLAB_COL1_FWD_NL, 1, wfwd_a[g], wfwd_a[g])
+                    self._pass(nat.SLAB_COL1_FWD_NL | seg, 1, wfwd_a[g], wfwd_a[g])
                     ready = torch.cuda.Event()
                     ready.record(main)
                     with torch.cuda.stream(comm):
                         comm.wait_event(ready)
-                        transpose_a_to_b(wfwd_a[g:g + 1], self.group, out=wfwd_b[g:g + 1])
+                        a2b(wfwd_a[g], wfwd_b[g], self.group)
                         ev = torch.cuda.Event()
                         ev.record(comm)
                     arrived.append(ev)

@@ -432,7 +432,7 @@ template <class T> struct PlanImpl : exb_plan {
 
   template <int DIR>
   int col_plain(cudaStream_t st, int axis, long long batch, int nfields, const cpx<T>* in, cpx<T>* out,
-                int prune = 0) {
+                int prune = 0, bool segmented = false) {
     ColParams<T> p;
     memset(&p, 0, sizeof(p));
     p.prune = prune;
@@ -448,6 +448,11 @@ template <class T> struct PlanImpl : exb_plan {
     p.in = in;
     p.out = out;
     col_geom(p, axis);
+    if (segmented) {  // slab layout A as received from / sent to the peers: [peer][x][n][Nh]
+      p.seg_len = nloc;
+      p.seg_stride = (long long)nloc * nloc * Nh;
+      p.outer_stride = (long long)nloc * Nh;
+    }
     if (fast_nd) return launch_col_fast(st, p, DIR, p.n_outer * batch * nfields);
     long long ntiles = (p.inner + p.TW - 1) / p.TW;
     long long grid = ntiles * p.n_outer * batch * nfields;
@@ -655,19 +660,24 @@ template <class T> struct PlanImpl : exb_plan {
                 void* OUT, void* const* S) override {
     if (D != 3) return fail(EXB_EINVAL, "exb_slab_pass needs a 3-D plan");
     const long long rows_stride_c = M;  // per-field stride, half-complex
+    const bool seg = (pass & EXB_SLAB_SEGMENTED) != 0;
+    pass &= ~EXB_SLAB_SEGMENTED;
+    if (seg && (nranks <= 1 || (pass != EXB_SLAB_COL1_FWD && pass != EXB_SLAB_COL1_INV &&
+                                pass != EXB_SLAB_COL1_FWD_NL && pass != EXB_SLAB_COL1_INV_NL)))
+      return fail(EXB_EINVAL, "EXB_SLAB_SEGMENTED applies to the axis-1 passes of a multi-rank slab plan");
     switch (pass) {
       case EXB_SLAB_ROW_R2C:
         return row_pass(st, ROW_R2C, 1, nfields, nfields, in, (long long)nfields * G, out, (long long)nfields * rows_stride_c);
       case EXB_SLAB_ROW_C2R:
         return row_pass(st, ROW_C2R, 1, nfields, nfields, in, (long long)nfields * rows_stride_c, out, (long long)nfields * G);
       case EXB_SLAB_COL1_FWD:
-        return col_plain<-1>(st, 1, 1, nfields, (const cpx<T>*)in, (cpx<T>*)out);
+        return col_plain<-1>(st, 1, 1, nfields, (const cpx<T>*)in, (cpx<T>*)out, 0, seg);
       case EXB_SLAB_COL1_INV:
-        return col_plain<+1>(st, 1, 1, nfields, (const cpx<T>*)in, (cpx<T>*)out);
+        return col_plain<+1>(st, 1, 1, nfields, (const cpx<T>*)in, (cpx<T>*)out, 0, seg);
       case EXB_SLAB_COL1_FWD_NL:
-        return col_plain<-1>(st, 1, 1, nfields, (const cpx<T>*)in, (cpx<T>*)out, PRUNE_COLS | PRUNE_OUT_ROWS);
+        return col_plain<-1>(st, 1, 1, nfields, (const cpx<T>*)in, (cpx<T>*)out, PRUNE_COLS | PRUNE_OUT_ROWS, seg);
       case EXB_SLAB_COL1_INV_NL:
-        return col_plain<+1>(st, 1, 1, nfields, (const cpx<T>*)in, (cpx<T>*)out, PRUNE_COLS | PRUNE_IN_ROWS);
+        return col_plain<+1>(st, 1, 1, nfields, (const cpx<T>*)in, (cpx<T>*)out, PRUNE_COLS | PRUNE_IN_ROWS, seg);
       case EXB_SLAB_COL0_FWD:
         return col_plain<-1>(st, 0, 1, nfields, (const cpx<T>*)in, (cpx<T>*)out);
       case EXB_SLAB_COL0_INV:

@@ -36,6 +36,8 @@ template <class T> struct ColParams {
   int stage;               // ETDRK stage (FWD_EPI)
   int prune;               // fast kernels only: PRUNE_* bits (dealiased modes are never touched)
   int f0, fcount;          // COL_INV_PRO: inverse fields [f0, f0 + fcount) (fcount <= 0: all)
+  int seg_len;             // COL_PLAIN, slab transposes without pack/unpack: line entry i lives at
+  long long seg_stride;    //   (i / seg_len) * seg_stride + (i % seg_len) * line_stride   (seg_len = 0: off)
   long long line_stride;   // elements between successive points of a line
   long long inner;         // contiguous positions across which lines are tiled
   long long n_outer;       // independent slabs per field (3-D axis-1 pass: N)
@@ -77,15 +79,19 @@ template <class T, int DIR> __global__ void col_pass_kernel(const ColParams<T> p
     const size_t base = (size_t)fb * p.M + (size_t)o * p.outer_stride + w0;
     cpx<T>* A = sm;
     cpx<T>* B = sm + tile;
+    auto line_off = [&](int i) -> size_t {
+      if (p.seg_len > 0) return (size_t)(i / p.seg_len) * p.seg_stride + (size_t)(i % p.seg_len) * p.line_stride;
+      return (size_t)i * p.line_stride;
+    };
     for (int q = threadIdx.x; q < N * TW; q += blockDim.x) {
       int i = q / TW, w = q - i * TW;
-      A[q] = w < wv ? p.in[base + (size_t)i * p.line_stride + w] : zero;
+      A[q] = w < wv ? p.in[base + line_off(i) + w] : zero;
     }
     __syncthreads();
     cpx<T>* R = fft_lines<T, DIR>(A, B, TW, 1, TW, true, p.fd, p.tw);
     for (int q = threadIdx.x; q < N * TW; q += blockDim.x) {
       int i = q / TW, w = q - i * TW;
-      if (w < wv) p.out[base + (size_t)i * p.line_stride + w] = R[q];
+      if (w < wv) p.out[base + line_off(i) + w] = R[q];
     }
     return;
   }

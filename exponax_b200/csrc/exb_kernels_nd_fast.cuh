@@ -75,15 +75,20 @@ col_fast_kernel(const ColParams<float> p) {
     bid /= p.n_outer;
     const size_t base = (size_t)bid * p.M + (size_t)o * p.outer_stride + w0 + w;
     if (!any_keep) return;
+    // line entry i -> element offset (segmented lines: the slab all-to-all buffers are used in place)
+    auto line_off = [&](int i) -> size_t {
+      if (p.seg_len > 0) return (size_t)(i / p.seg_len) * p.seg_stride + (size_t)(i % p.seg_len) * ls;
+      return (size_t)i * ls;
+    };
     cpx<float> v[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q)
-      v[q] = (col_keep && (!prune_rows_in || row_keep(j + P * q))) ? p.in[base + (size_t)(j + P * q) * ls] : zero;
+      v[q] = (col_keep && (!prune_rows_in || row_keep(j + P * q))) ? p.in[base + line_off(j + P * q)] : zero;
     fft8_run<N, DIR>(v, ex, j, tw);
     if (col_keep) {
 #pragma unroll
       for (int q = 0; q < 8; ++q)
-        if (!prune_rows_out || row_keep(j + P * q)) p.out[base + (size_t)(j + P * q) * ls] = v[q];
+        if (!prune_rows_out || row_keep(j + P * q)) p.out[base + line_off(j + P * q)] = v[q];
     }
     return;
   }

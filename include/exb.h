@@ -169,6 +169,10 @@ int exb_rollout(exb_plan *plan, void *stream, int64_t batch, int64_t n_saved, in
 #define EXB_SLAB_COL0_FWD_EPI 8 /* in: n_fwd fields B; ETDRK stage update on (U, OUT, S[0..3])        */
 #define EXB_SLAB_COL1_INV_NL 9  /* COL1_INV with dealiasing-aware pruning (inside N(u) only)          */
 #define EXB_SLAB_COL1_FWD_NL 10 /* COL1_FWD with dealiasing-aware pruning (inside N(u) only)          */
+/* OR-ed into a COL1 pass id: layout A is the raw all-to-all buffer [peer][x][k1 or y within peer][K]
+   (no pack / unpack copies around the transposes; rows are merely permuted, which the pointwise row
+   pass does not care about).  The pass runs in place. */
+#define EXB_SLAB_SEGMENTED 0x100
 int exb_slab_pass(exb_plan *plan, void *stream, int32_t pass, int32_t nfields, int32_t stage,
                   const void *in, void *out, const void *U, void *OUT, void *const *S);
 /* EXB_SLAB_COL0_INV_PRO restricted to the inverse fields [field0, field0 + nfields): lets the caller

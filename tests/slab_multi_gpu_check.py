@@ -48,13 +48,18 @@ def main():
         u0 = taylor_green(N, L)
         st = getattr(ex.stepper, name)(3, L, N, dt, order=order)
         slab = ex.SlabStepper(st)
-        got = slab.gather(slab.repeat(slab.scatter(u0), 3)).cpu().numpy()
         ref = ox.repeat(getattr(ox, name)(3, L, N, dt, order=order), 3)(u0)
         single = ex.repeat(st, 3, spectral_carry=True)(torch.as_tensor(u0, device="cuda")).cpu().numpy()
-        report[f"{name}_N{N}_vs_oracle"] = rel(got, ref)
-        report[f"{name}_N{N}_vs_single_gpu"] = rel(got, single)
-        assert rel(got, ref) < 5e-5, report
-        assert rel(got, single) < 5e-6, report
+        # every combination of {pipelined, serial} x {raw all-to-all buffers, packed transposes}
+        for overlap in (True, False):
+            for raw in (True, False):
+                slab.overlap, slab.raw_exchange = overlap, raw
+                got = slab.gather(slab.repeat(slab.scatter(u0), 3)).cpu().numpy()
+                tag = f"{name}_N{N}_ov{int(overlap)}_raw{int(raw)}"
+                report[f"{tag}_vs_oracle"] = rel(got, ref)
+                report[f"{tag}_vs_single_gpu"] = rel(got, single)
+                assert rel(got, ref) < 5e-5, report
+                assert rel(got, single) < 5e-6, report
     if args.bench:
         N = args.bench
         st = ex.stepper.NavierStokesVelocity(3, L, N, dt)
