@@ -21,7 +21,8 @@ template <class K> int set_smem(K kernel, size_t smem, const char** err) {
 
 template <int N, int TW, class S, int NFWD, int MODE, int DIR>
 int launch_col(cudaStream_t st, const ColParams<float>& p, long long grid, const char** err) {
-  const size_t smem = (size_t)(Fft8Tw<N>::SIZE + ExTile<TW>::rows(N) * TW) * sizeof(cpx<float>);
+  constexpr bool usm = MODE == COL_INV_PRO && S::C == 1 && EXB_INVPRO_SMEM_U != 0;  // parked stage input
+  const size_t smem = (size_t)(Fft8Tw<N>::SIZE + ExTile<TW>::rows(N) * TW + (usm ? N * TW : 0)) * sizeof(cpx<float>);
   // (set on every launch: the attribute is per device, and a process may drive several devices)
   if (int rc = set_smem(col_fast_kernel<N, TW, S, NFWD, MODE, DIR>, smem, err)) return rc;
   ColParams<float> q = p;
@@ -40,7 +41,9 @@ int launch_row(cudaStream_t st, const RowParams<float>& p, const char** err) {
   constexpr int P = N / 8, GROUPS = 256 / P;
   const bool prefetch = MODE == ROW_NL && (EXB_ROW_PREFETCH != 0);  // staging rows, see row_fast_kernel
   const int nhp = (N / 2 + 1 + 7) / 8 * 8;
-  const size_t smem = (size_t)(Fft8Tw<N>::SIZE + GROUPS * (N + N / 8 + (prefetch ? 2 * nhp : 0))) * sizeof(cpx<float>);
+  constexpr int kst = row_streams<S, NINV, NFWD, MODE>() ? row_stream_stash<S>() : 0;  // parked fields
+  const size_t smem =
+      (size_t)(Fft8Tw<N>::SIZE + GROUPS * (N + N / 8 + kst * N + (prefetch ? 2 * nhp : 0))) * sizeof(cpx<float>);
   if (int rc = set_smem(row_fast_kernel<N, S, NINV, NFWD, MODE, GROUPS>, smem, err)) return rc;
   const long long npairs = (p.rows + 1) / 2 * p.batch;
   const long long grid = (npairs + GROUPS - 1) / GROUPS;

@@ -122,13 +122,24 @@ __device__ __forceinline__ void fft8_run(cpx<float> (&v)[8], const Ex& ex, int j
   fft8_last_pass<N, DIR, Tw::T4>(v, j, tw);
 }
 
-// exchange through a contiguous, padded line buffer (row kernels): element i at i + i/8
+// exchange through a contiguous line buffer (row kernels).  Element i lives at the XOR-swizzled slot
+//   i ^ ((i >> 4) & 7) ^ ((i >> 3) & 8)
+// which makes every access pattern of fft8_run conflict-free per half-warp (8-byte elements, 16 bank
+// pairs): the stride-8 stores of pass 1, the k + 64 m stores of pass 2, the stride-64 stores of pass 3
+// and the unit-stride loads.  (The former padding i + i/8 cost the loads a second wavefront: 16
+// consecutive elements spanned 17 slots.)  EXB_LINE_SWIZZLE=0 restores the padded layout.
+#ifndef EXB_LINE_SWIZZLE
+#define EXB_LINE_SWIZZLE 1
+#endif
 struct ExLine {
   cpx<float>* base;
   int sync_kind;  // 0: __syncwarp, otherwise named barrier id
   int nthreads;
-  __device__ __forceinline__ void st(int i, cpx<float> x) const { base[i + (i >> 3)] = x; }
-  __device__ __forceinline__ cpx<float> ld(int i) const { return base[i + (i >> 3)]; }
+  static __device__ __forceinline__ int slot(int i) {
+    return EXB_LINE_SWIZZLE ? (i ^ ((i >> 4) & 7) ^ ((i >> 3) & 8)) : (i + (i >> 3));
+  }
+  __device__ __forceinline__ void st(int i, cpx<float> x) const { base[slot(i)] = x; }
+  __device__ __forceinline__ cpx<float> ld(int i) const { return base[slot(i)]; }
   __device__ __forceinline__ void sync() const {
     if (sync_kind == 0) __syncwarp();
     else asm volatile("bar.sync %0, %1;" ::"r"(sync_kind), "r"(nthreads) : "memory");

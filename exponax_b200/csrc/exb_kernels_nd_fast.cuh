@@ -16,6 +16,12 @@
 #ifndef EXB_ROW_PREFETCH
 #define EXB_ROW_PREFETCH 1
 #endif
+// COL_INV_PRO, single-channel state: park the 8 loaded modes of a thread in a thread-private slice of
+// shared memory across the field loop instead of 16 registers (the kernel is capped at 64 registers for
+// two 512-thread CTAs per SM and spilled to local memory otherwise)
+#ifndef EXB_INVPRO_SMEM_U
+#define EXB_INVPRO_SMEM_U 1
+#endif
 
 namespace exb {
 
@@ -113,11 +119,18 @@ col_fast_kernel(const ColParams<float> p) {
     // registers, i.e. two 512-thread CTAs per SM
     // (single-channel inputs are cheap enough to keep in registers: measured faster, r01g)
     const cpx<float>* ubase = p.in + (size_t)b * C * p.M + iw;
-    cpx<float> u0[8];
+    constexpr bool USM = (C == 1) && (EXB_INVPRO_SMEM_U != 0);
+    constexpr int NT = P * TW;
+    constexpr int TROWS = ExTile<TW>::PAD ? N + N / 8 : N;
+    cpx<float>* ustash = tile + TROWS * TW + threadIdx.x;  // [q][thread], conflict-free
+    cpx<float> u0[USM ? 1 : 8];
     if (C == 1) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
-        u0[q] = (col_keep && (kmax < 0 || row_keep(j + P * q))) ? ubase[(size_t)(j + P * q) * ls] : zero;
+      for (int q = 0; q < 8; ++q) {
+        cpx<float> t = (col_keep && (kmax < 0 || row_keep(j + P * q))) ? ubase[(size_t)(j + P * q) * ls] : zero;
+        if (USM) ustash[q * NT] = t;
+        else u0[q] = t;
+      }
     }
     const int f_begin = p.fcount > 0 ? p.f0 : 0, f_end = p.fcount > 0 ? p.f0 + p.fcount : Pn.n_inv;
     for (int f = f_begin; f < f_end; ++f) {
@@ -131,7 +144,7 @@ col_fast_kernel(const ColParams<float> p) {
           cpx<float> u[EXB_MAXC];
 #pragma unroll
           for (int c = 0; c < EXB_MAXC; ++c)
-            u[c] = c < C ? (C == 1 ? u0[q] : ubase[(size_t)c * p.M + (size_t)i0 * ls]) : zero;
+            u[c] = c < C ? (C == 1 ? (USM ? ustash[q * NT] : u0[USM ? 0 : q]) : ubase[(size_t)c * p.M + (size_t)i0 * ls]) : zero;
           val = nl_inv_field<float, S>(Pn, f, u, m);
         }
         v[q] = val;
@@ -182,9 +195,33 @@ col_fast_kernel(const ColParams<float> p) {
 }
 
 // ---------------------------------------------------------------------------------- row pass
+// ROW_NL "streaming": the nonlinearities of the fast kinds are sums of products of one early and one
+// late inverse field (u . grad w, u x curl u, |grad u|^2, (u . grad) u).  The first KST physical-space
+// fields are parked in a thread-private slice of shared memory, every later field is folded into the
+// forward-input accumulators as soon as its inverse transform is done, so only ONE inverse line plus
+// the accumulators live in registers (instead of all NINV lines): 2-3x the resident warps per SM.
+// row_stream_stash<S>() = KST (number of parked fields), -1: this kind is not streamed.
+#ifndef EXB_ROW_STREAM
+#define EXB_ROW_STREAM 1
+#endif
+template <class S> __host__ __device__ constexpr int row_stream_stash() {
+  return !EXB_ROW_STREAM ? -1
+         : S::kind == EXB_NL_VORTICITY_2D ? 2
+         : S::kind == EXB_NL_PROJECTED_3D ? 3
+         : (S::kind == EXB_NL_GRADIENT_NORM && S::C == 1) ? 0
+         : (S::kind == EXB_NL_CONVECTION && S::var == 0 && S::C == S::D) ? S::C
+         : -1;
+}
+template <class S, int NINV, int NFWD, int MODE> __host__ __device__ constexpr bool row_streams() {
+  return MODE == ROW_NL && NINV >= 2 && row_stream_stash<S>() >= 0;
+}
+template <class S, int NINV, int NFWD, int MODE> __host__ __device__ constexpr int row_min_blocks() {
+  return MODE != ROW_NL ? 4 : row_streams<S, NINV, NFWD, MODE>() ? (NFWD == 1 ? 3 : 2) : (NINV <= 4 ? 2 : 1);
+}
+
 // GROUPS row pairs per CTA, N/8 threads each.
 template <int N, class S, int NINV, int NFWD, int MODE, int GROUPS>
-__global__ void __launch_bounds__((N / 8) * GROUPS, (MODE == ROW_NL ? (NINV <= 4 ? 2 : 1) : 4))
+__global__ void __launch_bounds__((N / 8) * GROUPS, row_min_blocks<S, NINV, NFWD, MODE>())
 row_fast_kernel(const RowParams<float> p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int P = N / 8, Nh = N / 2 + 1, XB = N + N / 8;
@@ -196,14 +233,16 @@ row_fast_kernel(const RowParams<float> p) {
   // buffer while line f is being transformed (global-load latency off the critical path, no registers).
   constexpr bool PREFETCH = (MODE == ROW_NL) && (EXB_ROW_PREFETCH != 0);
   constexpr int NHP = (Nh + 7) / 8 * 8;
-  constexpr int SLOT = XB + (STASH ? NINV * N : 0) + (PREFETCH ? 2 * NHP : 0);  // complex elements per group
+  constexpr bool STREAM = row_streams<S, NINV, NFWD, MODE>();
+  constexpr int KST = STREAM ? row_stream_stash<S>() : 0;
+  constexpr int SLOT = XB + (STASH ? NINV * N : 0) + KST * N + (PREFETCH ? 2 * NHP : 0);  // complex elements per group
   cpx<float>* tw = reinterpret_cast<cpx<float>*>(smem_raw);
   Fft8Tw<N>::fill(tw, p.tw);
   const int g = threadIdx.x / P, j = threadIdx.x % P;
   cpx<float>* gbase = tw + Fft8Tw<N>::SIZE + (size_t)g * SLOT;
   ExLine ex{gbase, P <= 32 ? 0 : 1 + g, P};
   cpx<float>* stash = gbase + XB;
-  cpx<float>* stage = gbase + XB + (STASH ? NINV * N : 0);
+  cpx<float>* stage = gbase + XB + (STASH ? NINV * N : 0) + KST * N;
   __syncthreads();
   const NlParams<float>& Pn = p.P;
   const long long npairs = (p.rows + 1) / 2;
@@ -289,7 +328,73 @@ row_fast_kernel(const RowParams<float> p) {
   const cpx<float>* in = (const cpx<float>*)p.in + (size_t)b * p.in_batch_stride;
   cpx<float>* out = (cpx<float>*)p.out + (size_t)b * p.out_batch_stride;
   cpx<float> wl[NFWD][8];
-  if (STASH) {
+  if (STREAM) {
+#pragma unroll
+    for (int gg = 0; gg < NFWD; ++gg)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) wl[gg][q] = zero;
+    cpx<float>* park = stash + j;  // field g, point q of this thread at park[(g * 8 + q) * P]
+    auto fetch = [&](int f) {      // asynchronous copy of the two half-complex rows of inverse field f
+      const cpx<float>* a = in + ((size_t)f * p.rows + r1) * Nh;
+      const cpx<float>* c = in + ((size_t)f * p.rows + r2) * Nh;
+      for (int k = j; k < Nh && k <= kin; k += P) {
+        if (has1) cp_async8(stage + k, a + k);
+        if (has2) cp_async8(stage + NHP + k, c + k);
+      }
+      cp_async_commit();
+    };
+    if (PREFETCH) fetch(0);
+#pragma unroll
+    for (int f = 0; f < NINV; ++f) {
+      cpx<float> z[8];
+      if (PREFETCH) {
+        cp_async_wait_all();
+        ex.sync();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int n = j + P * q;
+          const bool upper = n > N / 2;
+          const int k = upper ? N - n : n;
+          cpx<float> F1 = (has1 && k <= kin) ? stage[k] : zero;
+          cpx<float> F2 = (has2 && k <= kin) ? stage[NHP + k] : zero;
+          cpx<float> zz;
+          if (k == 0 || 2 * k == N) zz = cpx<float>(F1.x, F2.x);
+          else if (!upper) zz = cpx<float>(F1.x - F2.y, F1.y + F2.x);
+          else zz = cpx<float>(F1.x + F2.y, F2.x - F1.y);
+          z[q] = zz;
+        }
+        ex.sync();
+        if (f + 1 < NINV) fetch(f + 1);
+      } else {
+        load_packed(in + ((size_t)f * p.rows + r1) * Nh, in + ((size_t)f * p.rows + r2) * Nh, z);
+      }
+      fft8_run<N, +1>(z, ex, j, tw);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const cpx<float> a(z[q].x * Pn.inv_norm, z[q].y * Pn.inv_norm);  // (row r1, row r2) at point j + P*q
+        auto pk = [&](int g) { return park[(g * 8 + q) * P]; };
+        auto acc = [&](int gg, cpx<float> s, float sign) {
+          wl[gg][q].x = fmaf(sign * s.x, a.x, wl[gg][q].x);
+          wl[gg][q].y = fmaf(sign * s.y, a.y, wl[gg][q].y);
+        };
+        if (f < KST) {
+          park[(f * 8 + q) * P] = a;
+        } else if (S::kind == EXB_NL_VORTICITY_2D) {    // u w_x + v w_y       (fields: u, v, w_x, w_y)
+          acc(0, pk(f - 2), 1.f);
+        } else if (S::kind == EXB_NL_PROJECTED_3D) {    // velocity x curl     (fields: curl 0..2, velocity 3..5)
+          if (f == 3) { acc(1, pk(2), -1.f); acc(2, pk(1), 1.f); }
+          if (f == 4) { acc(0, pk(2), 1.f); acc(2, pk(0), -1.f); }
+          if (f == 5) { acc(0, pk(1), -1.f); acc(1, pk(0), 1.f); }
+        } else if (S::kind == EXB_NL_GRADIENT_NORM) {   // sum_d (d_d u)^2
+          acc(0, a, 1.f);
+        } else if (S::kind == EXB_NL_CONVECTION) {      // out_c = sum_d u_d d_d u_c (fields: u_0.., then d_d u_c at C + c*D + d)
+          constexpr int Cc = S::C, Dd = S::D;
+          const int idx = f - Cc;
+          acc(idx / Dd, pk(idx % Dd), 1.f);
+        }
+      }
+    }
+  } else if (STASH) {
     for (int f = 0; f < NINV; ++f) {
       cpx<float> z[8];
       load_packed(in + ((size_t)f * p.rows + r1) * Nh, in + ((size_t)f * p.rows + r2) * Nh, z);
