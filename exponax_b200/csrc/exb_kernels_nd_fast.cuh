@@ -19,6 +19,11 @@
 // COL_INV_PRO, single-channel state: park the 8 loaded modes of a thread in a thread-private slice of
 // shared memory across the field loop instead of 16 registers (the kernel is capped at 64 registers for
 // two 512-thread CTAs per SM and spilled to local memory otherwise)
+// COL_FWD_EPI: prefetch the ETDRK stage operands into L2 ahead of the transforms.  Measured 2-3 % SLOWER
+// on c3 / c4 (r01k: the kernels wait on DRAM queues, not on a cold L2), so it is compiled out.
+#ifndef EXB_EPI_PREFETCH
+#define EXB_EPI_PREFETCH 0
+#endif
 #ifndef EXB_INVPRO_SMEM_U
 #define EXB_INVPRO_SMEM_U 1
 #endif
@@ -160,6 +165,17 @@ col_fast_kernel(const ColParams<float> p) {
   }
 
   // COL_FWD_EPI / COL_FWD_NL
+  if (MODE == COL_FWD_EPI && EXB_EPI_PREFETCH && act && (w == 0 || w == TW - 1 || iw == p.inner - 1)) {
+    // first / last lane of each row segment pulls the lines holding the stage operands into L2
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const long long mode = (long long)(j + P * q) * ls + iw;
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+        etdrk_prefetch(p.K, p.stage, (long long)(p.K.E == 1 ? 0 : c) * p.K.M + mode, ((size_t)b * C + c) * p.M + mode,
+                       p.sb, c == 0 || p.K.E != 1);
+    }
+  }
   cpx<float> W[NFWD][8];
 #pragma unroll
   for (int g = 0; g < NFWD; ++g) {

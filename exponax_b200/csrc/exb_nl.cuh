@@ -401,4 +401,38 @@ __device__ __forceinline__ void etdrk_update(const EtdrkCoefs<T>& K, int stage, 
   }
 }
 
+// L2 prefetch of everything etdrk_update(stage) will read at (ci, off): issued by the column-pass
+// epilogue kernels BEFORE their transforms, so that the DRAM latency of the stage operands (2/3 of the
+// bytes these kernels read) overlaps the FFT instead of being paid once per mode afterwards.
+__device__ __forceinline__ void prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+template <class T>
+__device__ __forceinline__ void etdrk_prefetch(const EtdrkCoefs<T>& K, int stage, long long ci, size_t off,
+                                               const StateBufs<T>& B, bool coefs) {
+  auto pc = [&](int i) { if (coefs) prefetch_l2(K.c[i] + ci); };
+  auto pe = [&](const cpx<T>* e) { if (coefs) prefetch_l2(e + ci); };
+  const int o = K.order;
+  const bool last = stage == o - 1;
+  if (o == 1 || (o == 2 && stage == 0) || o == 3 || (o == 4 && stage != 2)) prefetch_l2(B.U + off);
+  switch (o) {
+    case 1: pe(K.exp_term); pc(0); break;
+    case 2:
+      if (stage == 0) { pe(K.exp_term); pc(0); }
+      else { prefetch_l2(B.S[0] + off); prefetch_l2(B.S[1] + off); pc(1); }
+      break;
+    case 3:
+      if (stage == 0) { pe(K.half_exp); pc(0); }
+      else if (stage == 1) { pe(K.exp_term); pc(1); prefetch_l2(B.S[1] + off); }
+      else { pe(K.exp_term); pc(2); pc(3); pc(4); prefetch_l2(B.S[1] + off); prefetch_l2(B.S[2] + off); }
+      break;
+    case 4:
+      if (stage == 0) { pe(K.half_exp); pc(0); }
+      else if (stage == 1) { pe(K.half_exp); pc(1); }
+      else if (stage == 2) { pe(K.half_exp); pc(2); prefetch_l2(B.S[0] + off); prefetch_l2(B.S[1] + off); prefetch_l2(B.S[3] + off); }
+      else { pe(K.exp_term); pc(3); pc(4); pc(5); prefetch_l2(B.S[1] + off); prefetch_l2(B.S[3] + off); }
+      break;
+    default: break;
+  }
+  (void)last;
+}
+
 }  // namespace exb
