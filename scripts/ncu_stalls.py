@@ -15,8 +15,8 @@ stall = [h for h in hdr if h.startswith("smsp__average_warps_issue_stalled") and
 for r in rows[2:]:
     print("---", r[col["Kernel Name"]][:100])
     unit = {h: rows[1][i] for h, i in col.items()}
-    print("  time %.1f us  dram rd %.3f %s wr %.3f %s  dram%% %.1f  regs %d  warps_active %.1f%%  issue_active %.1f%%" % (
-        f(r, "gpu__time_duration.sum"), f(r, "dram__bytes_read.sum"), unit["dram__bytes_read.sum"],
+    print("  time %.3f %s  dram rd %.3f %s wr %.3f %s  dram%% %.1f  regs %d  warps_active %.1f%%  issue_active %.1f%%" % (
+        f(r, "gpu__time_duration.sum"), unit["gpu__time_duration.sum"], f(r, "dram__bytes_read.sum"), unit["dram__bytes_read.sum"],
         f(r, "dram__bytes_write.sum"), unit["dram__bytes_write.sum"],
         f(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"), f(r, "launch__registers_per_thread"),
         f(r, "sm__warps_active.avg.pct_of_peak_sustained_active"), f(r, "smsp__issue_active.avg.pct_of_peak_sustained_active")))
