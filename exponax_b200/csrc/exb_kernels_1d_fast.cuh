@@ -70,7 +70,7 @@ template <int R, int DIR> __device__ __forceinline__ void dft_reg(cpx<float>* v)
 // N = R*R point FFT of the line held as v[r] = x[j + R*r] by the R threads j of a group.
 // On return v[r] = X[j + R*r].  xb: per-pair exchange buffer ((R+1)*R complex, padded).
 template <int R, int DIR>
-__device__ __forceinline__ void fft_reg(cpx<float> (&v)[R], cpx<float>* xb, int j, const cpx<float>* tw2) {
+__device__ __forceinline__ void fft_reg_body(cpx<float> (&v)[R], cpx<float>* xb, int j, const cpx<float>* tw2) {
   dft_reg<R, DIR>(v);
   __syncwarp();
 #pragma unroll
@@ -90,6 +90,43 @@ __device__ __forceinline__ void fft_reg(cpx<float> (&v)[R], cpx<float>* xb, int 
 #pragma unroll
     for (int p = 0; p < R; ++p) v[p] = o[p];
   }
+}
+
+#ifndef EXB_1D_CTA_SYNC
+#define EXB_1D_CTA_SYNC 1
+#endif
+
+// The step body calls the transform from five places; inlined everywhere it is > 64 KB of code and the
+// warps stall on instruction fetch.  EXB_1D_FFT_CALL=1 makes the transform a real function: the line
+// travels by value (the ABI keeps the 2R floats in registers both ways, no stack traffic), the body
+// exists once per direction.
+#ifndef EXB_1D_FFT_CALL
+#define EXB_1D_FFT_CALL 1
+#endif
+#ifndef EXB_1D_FFT_UNIFY
+#define EXB_1D_FFT_UNIFY 1
+#endif
+template <int R> struct RegLine { cpx<float> v[R]; };
+template <int R, int DIR>
+__device__ __noinline__ RegLine<R> fft_reg_call(RegLine<R> a, cpx<float>* xb, int j, const cpx<float>* tw2) {
+  fft_reg_body<R, DIR>(a.v, xb, j, tw2);
+  return a;
+}
+template <int R, int DIR>
+__device__ __forceinline__ void fft_reg(cpx<float> (&v)[R], cpx<float>* xb, int j, const cpx<float>* tw2) {
+#if EXB_1D_FFT_CALL
+  // EXB_1D_FFT_UNIFY: the inverse transform is conj(forward(conj(x))) -- sign flips are exact, so one
+  // function body serves both directions
+  constexpr bool CONJ = (EXB_1D_FFT_UNIFY != 0) && DIR > 0;
+  RegLine<R> a;
+#pragma unroll
+  for (int r = 0; r < R; ++r) a.v[r] = CONJ ? cpx<float>(v[r].x, -v[r].y) : v[r];
+  a = fft_reg_call<R, CONJ ? -1 : DIR>(a, xb, j, tw2);
+#pragma unroll
+  for (int r = 0; r < R; ++r) v[r] = CONJ ? cpx<float>(a.v[r].x, -a.v[r].y) : a.v[r];
+#else
+  fft_reg_body<R, DIR>(v, xb, j, tw2);
+#endif
 }
 
 template <int R, class S, int NINV, int NFWD> struct Fast1d {
@@ -286,6 +323,12 @@ template <int R, class S, int NINV, int NFWD> struct Fast1d {
         }
       }
       __syncwarp();
+#if EXB_1D_CTA_SYNC
+      // No data is shared between warps: the barrier only keeps the warps of the CTA at the same place of
+      // the (fully unrolled, > 64 KB) step body, so that they share instruction-cache lines instead of
+      // each streaming the body from L2 on its own (ncu r01: `no_instruction` was the top stall reason).
+      __syncthreads();
+#endif
     }
   }
 };

@@ -13,7 +13,7 @@ for line in txt.splitlines():
         name = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip()
         cnt[name] = collections.Counter()
         continue
-    m = re.match(r"\s*/\*[0-9a-f]{4}\*/\s+(@!?U?P\d\s+)?([A-Z0-9_.]+)", line)
+    m = re.match(r"\s*/\*[0-9a-f]{4,6}\*/\s+(@!?U?P\d\s+)?([A-Z0-9_.]+)", line)
     if m and name:
         op = m.group(2).split(".")[0]
         cnt[name][op] += 1
