@@ -12,14 +12,14 @@ NumPy arrays (copied to the device and back).  There is no CPU fallback.
 """
 from . import _spectral as spectral
 from . import _distributed as distributed
-from . import etdrk, nonlin_fun, stepper
+from . import etdrk, ic, metrics, nonlin_fun, stepper
 from ._base_stepper import BaseStepper
 from ._config import config
 from ._forced_stepper import ForcedStepper
 from ._repeated_stepper import RepeatedStepper
 from ._slab import SlabStepper
-from ._spectral import fft, ifft
-from ._utils import make_grid, repeat, rollout, vmap
+from ._spectral import fft, get_spectrum, ifft
+from ._utils import build_ic_set, make_grid, repeat, rollout, stack_sub_trajectories, vmap
 
 __version__ = "0.1.0"
 
@@ -28,16 +28,21 @@ __all__ = [
     "ForcedStepper",
     "RepeatedStepper",
     "SlabStepper",
+    "build_ic_set",
     "config",
     "distributed",
     "etdrk",
     "fft",
+    "get_spectrum",
+    "ic",
     "ifft",
     "make_grid",
+    "metrics",
     "nonlin_fun",
     "repeat",
     "rollout",
     "spectral",
+    "stack_sub_trajectories",
     "stepper",
     "vmap",
 ]

@@ -78,6 +78,14 @@ SYMBOLS = {
                                 C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "exb_slab_inv_pro_fields": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "exb_plan_nl_fields": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "exb_ic_shape": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_double, C.c_double,
+                               C.c_double]),
+    "exb_ic_normalize": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,
+                                   C.c_int32, C.c_void_p]),
+    "exb_metric_sums": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_double,
+                                  C.c_void_p]),
+    "exb_spectrum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                               C.c_void_p]),
 }
 
 

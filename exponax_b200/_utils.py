@@ -44,10 +44,58 @@ class vmap:
                 return fn._step_batched(x)
             if isinstance(fn, (_Rollout, _Repeat)):
                 return fn._call(x, batched=True)
+        if hasattr(fn, "_batched"):   # functions with a native batched form (ex.get_spectrum, ex.metrics.*)
+            return fn._batched(x, *aux)
         outs = [fn(x[i], *(a[i] for a in aux)) for i in range(len(x))]
         if isinstance(outs[0], np.ndarray):
             return np.stack(outs)
         return A.torch.stack(outs)
+
+
+def stack_sub_trajectories(trj, sub_len: int):
+    """Slice a trajectory `(T, ...)` into its `T - sub_len + 1` overlapping windows `(n_windows, sub_len, ...)`
+    == exponax.stack_sub_trajectories (exponax/_utils.py:257-313).  `trj` is an array or a (nested) tuple /
+    list / dict of arrays with the same number of time steps.  Torch tensors come back as a strided VIEW of
+    `trj` (no copy: the window axis reuses the time stride); NumPy arrays as a read-only sliding-window view."""
+    if isinstance(trj, (tuple, list, dict)):
+        leaves = list(trj.values()) if isinstance(trj, dict) else list(trj)
+        flat = []
+        def collect(x):
+            if isinstance(x, (tuple, list)):
+                for y in x:
+                    collect(y)
+            elif isinstance(x, dict):
+                for y in x.values():
+                    collect(y)
+            else:
+                flat.append(x.shape[0])
+        collect(leaves)
+        if len(set(flat)) != 1:
+            raise ValueError("All arrays in trj must have the same number of time steps in the leading axis")
+        if isinstance(trj, dict):
+            return {k: stack_sub_trajectories(v, sub_len) for k, v in trj.items()}
+        return type(trj)(stack_sub_trajectories(v, sub_len) for v in trj)
+    n_time = trj.shape[0]
+    if sub_len > n_time:
+        raise ValueError("n must be smaller than or equal to the number of time steps in trj")
+    n_win = n_time - sub_len + 1
+    if isinstance(trj, np.ndarray):
+        v = np.lib.stride_tricks.sliding_window_view(trj, sub_len, axis=0)   # (n_win, ..., sub_len)
+        return np.moveaxis(v, -1, 1)
+    st = trj.stride()
+    return trj.as_strided((n_win, sub_len) + tuple(trj.shape[1:]), (st[0], st[0]) + tuple(st[1:]))
+
+
+def build_ic_set(ic_generator, *, num_points: int, num_samples: int, key=0):
+    """`num_samples` initial conditions `(S, C, N, .., N)` == exponax.build_ic_set (exponax/_utils.py:316-348).
+    Generators of `exponax_b200.ic` produce the whole set in one batched pipeline; any other callable
+    `ic_generator(num_points, key=...)` is called sample by sample with the seeds key, key + 1, ..."""
+    if hasattr(ic_generator, "batch"):
+        return ic_generator.batch(num_points, num_samples, key=key)
+    outs = [ic_generator(num_points, key=key + i) for i in range(num_samples)]
+    if isinstance(outs[0], np.ndarray):
+        return np.stack(outs)
+    return A.torch.stack(outs)
 
 
 def _native_target(stepper_fn):

@@ -14,6 +14,9 @@
 #include "exb_fast1d.h"
 #include "exb_fastnd.h"
 #include "exb_kernels_nd.cuh"
+#include "exb_spectrum.cuh"
+#include "exb_metrics.cuh"
+#include "exb_ic.cuh"
 
 using namespace exb;
 
@@ -51,6 +54,10 @@ struct exb_plan {
                         const void* U, void* OUT, void* const* S) = 0;
   virtual void nl_fields(int* ni, int* nf) const = 0;
   virtual int slab_inv_pro_fields(cudaStream_t st, int f0, int nf, const void* in, void* out) = 0;
+  virtual int spectrum(cudaStream_t st, int64_t nfields, const void* uh, void* out, int power, int average,
+                       void* counts) = 0;
+  virtual int ic_shape(cudaStream_t st, int64_t nfields, void* uh, int kind, double param, double domain_extent,
+                       double dc_value) = 0;
 };
 
 static void factorize(int N, FftDesc& fd) {
@@ -730,6 +737,55 @@ template <class T> struct PlanImpl : exb_plan {
     return ifft_nd(st, batch, channels, (const cpx<T>*)uh, w.Winv, (T*)u, (long long)channels * G);
   }
 
+  int ic_shape(cudaStream_t st, int64_t nfields, void* uh, int kind, double param, double domain_extent,
+               double dc_value) override {
+    if (nranks > 1) return fail(EXB_EINVAL, "slab plans only support exb_slab_pass");
+    if (nfields < 1 || (kind != 0 && kind != 1)) return fail(EXB_EINVAL, "exb_ic_shape: bad arguments");
+    if (kind == 1 && !(domain_extent > 0)) return fail(EXB_EINVAL, "exb_ic_shape: domain_extent must be > 0");
+    const long long total = (long long)nfields * M;
+    const double two_pi = 6.283185307179586476925286766559;
+    ic_shape_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        (cpx<T>*)uh, D, N, Nh, M, total, kind, (T)param, (T)(kind == 1 ? two_pi / domain_extent : 0.0), (T)dc_value);
+    CUDA_OK(cudaGetLastError());
+    ++launches;
+    return EXB_OK;
+  }
+
+  int spectrum(cudaStream_t st, int64_t nfields, const void* uh, void* out, int power, int average,
+               void* counts) override {
+    if (nranks > 1) return fail(EXB_EINVAL, "slab plans only support exb_slab_pass");
+    if (nfields < 1) return fail(EXB_EINVAL, "nfields must be >= 1");
+    if (average && !counts) return fail(EXB_EINVAL, "radial average needs the counts scratch buffer");
+    SpectrumParams<T> sp;
+    sp.uh = (const cpx<T>*)uh;
+    sp.out = (T*)out;
+    sp.counts = average ? (unsigned*)counts : nullptr;
+    sp.D = D;
+    sp.N = N;
+    sp.Nh = Nh;
+    sp.M = M;
+    sp.power = power;
+    // enough CTAs to fill the GPU, at least 4096 modes each
+    long long nchunk = (M + 4095) / 4096;
+    const long long target = std::max<long long>(1, (8ll * sm_count + nfields - 1) / nfields);
+    if (nchunk > target) nchunk = target;
+    sp.chunk = (M + nchunk - 1) / nchunk;
+    CUDA_OK(cudaMemsetAsync(out, 0, (size_t)nfields * Nh * sizeof(T), st));
+    if (average) CUDA_OK(cudaMemsetAsync(counts, 0, (size_t)Nh * sizeof(unsigned), st));
+    dim3 grid((unsigned)nchunk, (unsigned)nfields);
+    const size_t smem = (size_t)Nh * (sizeof(T) + sizeof(unsigned));
+    spectrum_kernel<T><<<grid, 256, smem, st>>>(sp);
+    CUDA_OK(cudaGetLastError());
+    ++launches;
+    if (average) {
+      const long long tot = nfields * Nh;
+      spectrum_average_kernel<T><<<(unsigned)((tot + 255) / 256), 256, 0, st>>>((T*)out, (const unsigned*)counts, Nh, nfields);
+      CUDA_OK(cudaGetLastError());
+      ++launches;
+    }
+    return EXB_OK;
+  }
+
   int nonlinear(cudaStream_t st, int64_t batch, const void* uh, void* out, void* ws) override {
     if (nranks > 1) return fail(EXB_EINVAL, "slab plans only support exb_slab_pass");
     if (P.kind == EXB_NL_ZERO) {
@@ -859,6 +915,46 @@ template <class T> struct PlanImpl : exb_plan {
 };
 
 // ---------------------------------------------------------------------------------- C ABI
+template <class T>
+static int metric_sums_t(cudaStream_t st, int64_t nfields, int64_t npoints, const void* a, const void* b, double p,
+                         double* out) {
+  int dev = 0, sms = 0;
+  CUDA_OK(cudaGetDevice(&dev));
+  CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  long long nchunk = (npoints + 8191) / 8192;
+  const long long target = std::max<long long>(1, (8ll * sms + nfields - 1) / nfields);
+  if (nchunk > target) nchunk = target;
+  const long long chunk = (npoints + nchunk - 1) / nchunk;
+  const int pi = p == 1.0 ? 1 : (p == 2.0 ? 2 : 0);
+  CUDA_OK(cudaMemsetAsync(out, 0, (size_t)nfields * 4 * sizeof(double), st));
+  dim3 grid((unsigned)nchunk, (unsigned)nfields);
+  metric_sums_kernel<T><<<grid, 256, 0, st>>>((const T*)a, (const T*)b, npoints, chunk, (T)p, pi, out);
+  CUDA_OK(cudaGetLastError());
+  return EXB_OK;
+}
+
+template <class T>
+static int ic_normalize_t(cudaStream_t st, int64_t nfields, int64_t npoints, void* u, int zero_mean, int std_one,
+                          int max_one, double* stats) {
+  int dev = 0, sms = 0;
+  CUDA_OK(cudaGetDevice(&dev));
+  CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  long long nchunk = (npoints + 8191) / 8192;
+  const long long target = std::max<long long>(1, (8ll * sms + nfields - 1) / nfields);
+  if (nchunk > target) nchunk = target;
+  const long long chunk = (npoints + nchunk - 1) / nchunk;
+  const long long total = nfields * npoints;
+  dim3 grid((unsigned)nchunk, (unsigned)nfields);
+  CUDA_OK(cudaMemsetAsync(stats, 0, (size_t)nfields * 4 * sizeof(double), st));
+  ic_shift_kernel<T><<<(unsigned)((nfields + 255) / 256), 256, 0, st>>>((const T*)u, npoints, nfields, stats);
+  ic_stats_kernel<T><<<grid, 256, 0, st>>>((const T*)u, npoints, chunk, stats);
+  if (max_one) ic_maxabs_kernel<T><<<grid, 256, 0, st>>>((const T*)u, npoints, chunk, zero_mean, stats);
+  ic_apply_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>((T*)u, npoints, total, zero_mean, std_one,
+                                                                     max_one, stats);
+  CUDA_OK(cudaGetLastError());
+  return EXB_OK;
+}
+
 extern "C" {
 
 const char* exb_last_error(void) { return g_err.c_str(); }
@@ -929,6 +1025,34 @@ int exb_rollout(exb_plan* plan, void* stream, int64_t batch, int64_t n_saved, in
   return plan->rollout((cudaStream_t)stream, batch, n_saved, substeps, flags, u0, out, ws);
 }
 int64_t exb_launch_count(const exb_plan* plan) { return plan ? plan->launches : 0; }
+int exb_metric_sums(void* stream, int32_t dtype, int64_t nfields, int64_t npoints, const void* a, const void* b,
+                    double p, double* out) {
+  if (nfields < 1 || npoints < 1 || !a || !out) return fail(EXB_EINVAL, "exb_metric_sums: bad arguments");
+  if (nfields > 65535) return fail(EXB_EINVAL, "exb_metric_sums: at most 65535 fields per call");
+  if (dtype == EXB_F32) return metric_sums_t<float>((cudaStream_t)stream, nfields, npoints, a, b, p, out);
+  if (dtype == EXB_F64) return metric_sums_t<double>((cudaStream_t)stream, nfields, npoints, a, b, p, out);
+  return fail(EXB_EINVAL, "exb_metric_sums: unknown dtype");
+}
+int exb_ic_shape(exb_plan* plan, void* stream, int64_t nfields, void* u_hat, int32_t kind, double param,
+                 double domain_extent, double dc_value) {
+  if (!plan) return fail(EXB_EINVAL, "null plan");
+  return plan->ic_shape((cudaStream_t)stream, nfields, u_hat, kind, param, domain_extent, dc_value);
+}
+int exb_ic_normalize(void* stream, int32_t dtype, int64_t nfields, int64_t npoints, void* u, int32_t zero_mean,
+                     int32_t std_one, int32_t max_one, double* stats) {
+  if (nfields < 1 || npoints < 1 || !u || !stats) return fail(EXB_EINVAL, "exb_ic_normalize: bad arguments");
+  if (nfields > 65535) return fail(EXB_EINVAL, "exb_ic_normalize: at most 65535 fields per call");
+  if (dtype == EXB_F32)
+    return ic_normalize_t<float>((cudaStream_t)stream, nfields, npoints, u, zero_mean, std_one, max_one, stats);
+  if (dtype == EXB_F64)
+    return ic_normalize_t<double>((cudaStream_t)stream, nfields, npoints, u, zero_mean, std_one, max_one, stats);
+  return fail(EXB_EINVAL, "exb_ic_normalize: unknown dtype");
+}
+int exb_spectrum(exb_plan* plan, void* stream, int64_t nfields, const void* u_hat, void* out, int32_t power,
+                 int32_t average, void* counts) {
+  if (!plan) return fail(EXB_EINVAL, "null plan");
+  return plan->spectrum((cudaStream_t)stream, nfields, u_hat, out, power, average, counts);
+}
 int exb_slab_pass(exb_plan* plan, void* stream, int32_t pass, int32_t nfields, int32_t stage, const void* in,
                   void* out, const void* U, void* OUT, void* const* S) {
   if (!plan) return fail(EXB_EINVAL, "null plan");

@@ -14,6 +14,10 @@
  *   exb_step           <- exponax/_base_stepper.py:201-220  (fft -> step_fourier -> ifft)
  *   exb_rollout        <- exponax/_utils.py:92-254 (rollout / repeat) composed with
  *                         exponax/_repeated_stepper.py:56-102 (sub-steps with spectral carry)
+ *   exb_spectrum       <- exponax/_spectral.py:866-1030  (get_spectrum after its fft)
+ *   exb_ic_shape / exb_ic_normalize <- exponax/ic/_truncated_fourier_series.py:65-100,
+ *                         ic/_gaussian_random_field.py:64-93, ic/_base_ic.py:16-33
+ *   exb_metric_sums    <- exponax/metrics/_spatial.py:8-196, metrics/_correlation.py:6-60
  *
  * Conventions
  *   - every array pointer is a DEVICE pointer owned by the caller (C-contiguous,
@@ -181,6 +185,37 @@ int exb_slab_inv_pro_fields(exb_plan *plan, void *stream, int32_t field0, int32_
                             void *out);
 /* number of single-field inverse / forward transforms per N(u) evaluation of this plan */
 int exb_plan_nl_fields(const exb_plan *plan, int32_t *n_inv, int32_t *n_fwd);
+
+/* ---- consumer next to the loop: radially binned spectrum ----
+   exponax/_spectral.py:866-1030 `get_spectrum`, applied to u_hat = exb_fft(state).  u_hat: (nfields, N..,
+   N/2+1) complex of this plan's grid; out: (nfields, N/2+1) real.  power != 0: power spectrum, else
+   amplitude spectrum; average != 0: radial_binning="average" (needs `counts`, a device scratch of
+   N/2+1 uint32), else "sum" (`counts` may be NULL). */
+int exb_spectrum(exb_plan *plan, void *stream, int64_t nfields, const void *u_hat, void *out,
+                 int32_t power, int32_t average, void *counts);
+
+/* ---- producers in front of the loop: random initial conditions ----
+   exponax/ic generators are  white noise -> exb_fft -> exb_ic_shape -> exb_ifft -> exb_ic_normalize.
+   exb_ic_shape: per-mode real factor, in place on u_hat (nfields, N.., N/2+1) of this plan's grid
+     kind 0  RandomTruncatedFourierSeries (ic/_truncated_fourier_series.py:65-100): keep |k_d| <= param on every
+             axis, then the DC entry := dc_value (unnormalised coefficient, as the reference sets it)
+     kind 1  GaussianRandomField (ic/_gaussian_random_field.py:64-93): |2 pi k / domain_extent|^(-param / 2),
+             DC factor 1
+   exb_ic_normalize: normalize_ic (ic/_base_ic.py:16-33), in place per field of npoints values: subtract the
+     mean, divide by the (population) standard deviation, divide by max |x| -- each if flagged;
+     stats: device scratch double[nfields * 4]. */
+int exb_ic_shape(exb_plan *plan, void *stream, int64_t nfields, void *u_hat, int32_t kind, double param,
+                 double domain_extent, double dc_value);
+int exb_ic_normalize(void *stream, int32_t dtype, int64_t nfields, int64_t npoints, void *u,
+                     int32_t zero_mean, int32_t std_one, int32_t max_one, double *stats);
+
+/* fused reductions behind exponax.metrics (metrics/_spatial.py:8-196, metrics/_correlation.py:6-60), no plan
+   needed.  a, b: (nfields, npoints) real of `dtype` (b may be NULL = zeros); out: device double[nfields*4]:
+     out[4f+0] = sum |a-b|^p   out[4f+1] = sum |b|^p   out[4f+2] = sum |a|^p   out[4f+3] = sum a*b
+   A field is one channel of one sample; the caller combines the sums (scale (L/N)^D, outer exponent,
+   normalised / symmetric ratios, channel sum). */
+int exb_metric_sums(void *stream, int32_t dtype, int64_t nfields, int64_t npoints, const void *a,
+                    const void *b, double p, double *out);
 
 /* number of kernel launches issued through this plan so far (bench bookkeeping) */
 int64_t exb_launch_count(const exb_plan *plan);

@@ -169,6 +169,44 @@ def make_grid(D, L, N, dtype=np.float32):
     return np.stack(np.meshgrid(*([g] * D), indexing="ij"))
 
 
+def get_spectrum(state, *, power=True, radial_binning="sum"):
+    """exponax/_spectral.py:866-1030: power / amplitude spectrum (C, N//2+1), radially binned for D > 1
+    with the reference's bucket masks  k - dk/2 <= |k| < k + dk/2  evaluated in the state's precision."""
+    D = state.ndim - 1
+    N = state.shape[-1]
+    dt = state.dtype.type
+    a = np.abs(fft(state, num_spatial_dims=D))
+    magnitude = a / build_scaling_array(D, N, mode="reconstruction", dtype=dt)
+    if power:
+        quantity = dt(0.5) * magnitude * (a / build_scaling_array(D, N, mode="norm_compensation", dtype=dt))
+    else:
+        quantity = magnitude
+    if D == 1:
+        return quantity
+    wn = build_wavenumbers(D, N, dtype=dt)
+    wn1 = build_wavenumbers(1, N, dtype=dt)[0]
+    norm = np.sqrt(np.sum(wn * wn, axis=0)).astype(dt)           # jnp.linalg.norm(..., axis=0)
+    dk = wn1[1] - wn1[0]
+    out = np.empty((state.shape[0], wn1.shape[0]), dt)
+    for i, k in enumerate(wn1):
+        mask = (norm >= k - dk / 2) & (norm < k + dk / 2)
+        for c in range(state.shape[0]):
+            vals = quantity[c][mask]
+            if radial_binning == "average":
+                out[c, i] = vals.mean(dtype=dt) if vals.size else np.nan
+            else:
+                out[c, i] = vals.sum(dtype=dt)
+    return out
+
+
+def stack_sub_trajectories(trj, sub_len):
+    """exponax/_utils.py:257-313 for one array: windows trj[i : i + sub_len], i = 0 .. T - sub_len."""
+    n = trj.shape[0]
+    if sub_len > n:
+        raise ValueError("n must be smaller than or equal to the number of time steps in trj")
+    return np.stack([trj[i:i + sub_len] for i in range(n - sub_len + 1)])
+
+
 def get_spectrum_1d(u, dtype=np.float32):
     """Amplitude spectrum |u_hat|/scaling for 1-D states (test harness only;
     follows exponax/_spectral.py:866-1030 for D=1, power=False)."""
@@ -1209,3 +1247,111 @@ class Wave(BaseStepper):
         dc = (0,) * self.num_spatial_dims
         out[(0,) + dc] += t(self.dt) * u_hat[(1,) + dc]
         return out
+
+
+# --------------------------------------------------------------------------
+# metrics/  (spatial family + correlation; consumers of saved snapshots)
+# --------------------------------------------------------------------------
+def spatial_aggregator(state_no_channel, *, num_spatial_dims=None, domain_extent=1.0, num_points=None,
+                       inner_exponent=2.0, outer_exponent=None):
+    """exponax/metrics/_spatial.py:8-83."""
+    if num_spatial_dims is None:
+        num_spatial_dims = state_no_channel.ndim
+    if num_points is None:
+        num_points = state_no_channel.shape[-1]
+    if outer_exponent is None:
+        outer_exponent = 1 / inner_exponent
+    scale = (domain_extent / num_points) ** num_spatial_dims
+    aggregated = np.sum(np.abs(state_no_channel) ** inner_exponent)
+    return (scale * aggregated) ** outer_exponent
+
+
+def spatial_norm(state, state_ref=None, *, mode="absolute", domain_extent=1.0, inner_exponent=2.0,
+                 outer_exponent=None):
+    """exponax/metrics/_spatial.py:86-196."""
+    if state_ref is None:
+        if mode == "normalized":
+            raise ValueError("mode 'normalized' requires state_ref")
+        if mode == "symmetric":
+            raise ValueError("mode 'symmetric' requires state_ref")
+        diff = state
+    else:
+        diff = state - state_ref
+    agg = lambda x: np.array([spatial_aggregator(c, domain_extent=domain_extent, inner_exponent=inner_exponent,
+                                                 outer_exponent=outer_exponent) for c in x])
+    d = agg(diff)
+    if mode == "normalized":
+        d = d / agg(state_ref)
+    elif mode == "symmetric":
+        d = 2 * d / (agg(state) + agg(state_ref))
+    return np.sum(d)
+
+
+def _metric(mode, p, q):
+    def fn(u_pred, u_ref=None, *, domain_extent=1.0):
+        return spatial_norm(u_pred, u_ref, mode=mode, domain_extent=domain_extent, inner_exponent=p,
+                            outer_exponent=q)
+    return fn
+
+
+MAE, nMAE, sMAE = _metric("absolute", 1.0, 1.0), _metric("normalized", 1.0, 1.0), _metric("symmetric", 1.0, 1.0)
+MSE, nMSE, sMSE = _metric("absolute", 2.0, 1.0), _metric("normalized", 2.0, 1.0), _metric("symmetric", 2.0, 1.0)
+RMSE, nRMSE, sRMSE = _metric("absolute", 2.0, 0.5), _metric("normalized", 2.0, 0.5), _metric("symmetric", 2.0, 0.5)
+
+
+def correlation(u_pred, u_ref):
+    """exponax/metrics/_correlation.py:6-60."""
+    per_channel = [np.dot((a / np.linalg.norm(a)).ravel(), (b / np.linalg.norm(b)).ravel())
+                   for a, b in zip(u_pred, u_ref)]
+    return np.mean(per_channel)
+
+
+def mean_metric(metric_fn, *args, **kwargs):
+    """exponax/metrics/_utils.py:5-18."""
+    return np.mean([metric_fn(*(a[i] for a in args), **kwargs) for i in range(len(args[0]))], axis=0)
+
+
+# --------------------------------------------------------------------------
+# ic/  (the spectral random generators, deterministic part: noise in, state out)
+# --------------------------------------------------------------------------
+def normalize_ic(ic, *, zero_mean=True, std_one=False, max_one=False):
+    """exponax/ic/_base_ic.py:16-33."""
+    if zero_mean:
+        ic = ic - np.mean(ic)
+    if std_one:
+        ic = ic / np.std(ic)
+    if max_one:
+        ic = ic / np.max(np.abs(ic))
+    return ic
+
+
+def ic_truncated_fourier_series(noise, *, cutoff=5, offset=0.0, zero_mean=True, std_one=False, max_one=False):
+    """exponax/ic/_truncated_fourier_series.py:65-100 from a given white-noise array (1, N, .., N)."""
+    D, N = noise.ndim - 1, noise.shape[-1]
+    nh = fft(noise, num_spatial_dims=D) * low_pass_filter_mask(D, N, cutoff=cutoff, axis_separate=True,
+                                                                 dtype=noise.dtype.type)
+    shp = nh.shape
+    nh = nh.ravel()
+    nh[0] = offset
+    ic = ifft(nh.reshape(shp), num_spatial_dims=D, num_points=N).astype(noise.dtype)
+    return normalize_ic(ic, zero_mean=zero_mean, std_one=std_one, max_one=max_one)
+
+
+def ic_gaussian_random_field(noise, *, L=1.0, powerlaw_exponent=3.0, zero_mean=True, std_one=False, max_one=False):
+    """exponax/ic/_gaussian_random_field.py:64-93 from a given white-noise array."""
+    D, N = noise.ndim - 1, noise.shape[-1]
+    dt = noise.dtype.type
+    nh = fft(noise, num_spatial_dims=D)
+    norm = np.linalg.norm(build_scaled_wavenumbers(D, L, N, dt), axis=0, keepdims=True)
+    with np.errstate(divide="ignore"):
+        amp = np.power(norm, dt(-powerlaw_exponent / 2.0))
+    amp.ravel()[0] = 1.0
+    ic = ifft(nh * amp, num_spatial_dims=D, num_points=N).astype(noise.dtype)
+    return normalize_ic(ic, zero_mean=zero_mean, std_one=std_one, max_one=max_one)
+
+
+def ic_diffused_noise(noise, *, L=1.0, intensity=0.001, zero_mean=True, std_one=False, max_one=False):
+    """exponax/ic/_diffused_noise.py:58-77 from a given white-noise array."""
+    D, N = noise.ndim - 1, noise.shape[-1]
+    ic = Diffusion(D, L, N, 1.0, diffusivity=intensity, dtype=noise.dtype.type)(noise)
+    return normalize_ic(ic, zero_mean=zero_mean, std_one=std_one, max_one=max_one)

@@ -855,3 +855,199 @@ def test_cuda_graph_replay_matches_direct_call():
     b = fn(u0 * 0.5)          # second call: replay with new input
     assert torch.equal(a, direct)
     assert torch.equal(b, ex.vmap(ex.rollout(st, 6, include_init=True))(u0 * 0.5))
+
+
+# ---------------------------------------------------------------------------- spectrum
+@pytest.mark.parametrize("D,N", [(1, 128), (1, 200), (2, 48), (2, 128), (3, 16), (3, 64), (2, 45)])
+@pytest.mark.parametrize("power", [True, False])
+@pytest.mark.parametrize("binning", ["sum", "average"])
+def test_get_spectrum_matches_oracle(D, N, power, binning):
+    rng = np.random.default_rng(D * 1000 + N)
+    u = rng.standard_normal((2,) + (N,) * D).astype(np.float32)
+    got = ex.get_spectrum(torch.as_tensor(u, device="cuda"), power=power, radial_binning=binning).cpu().numpy()
+    ref = ox.get_spectrum(u, power=power, radial_binning=binning)
+    assert got.shape == ref.shape == (2, N // 2 + 1)
+    assert np.allclose(got, ref, rtol=2e-5, atol=1e-6 * np.abs(ref).max())
+
+
+def test_get_spectrum_reference_known_answers():
+    # the reference's own closed-form checks (tests/test_spectrum.py:30-66), through the CUDA path
+    g = ex.make_grid(2, 2 * np.pi, 48)
+    u = (3.0 * np.sin(2 * g[0:1]) * np.cos(2 * g[1:2])).astype(np.float32)
+    s = ex.get_spectrum(torch.as_tensor(u, device="cuda"), power=False).cpu().numpy()
+    assert s[0, 3] == pytest.approx(3.0)
+    assert s[0, 2] == pytest.approx(0.0, abs=1e-5)
+    u = (4.0 * np.sin(2 * g[0:1]) * np.cos(3 * g[1:2])).astype(np.float32)
+    s = ex.get_spectrum(torch.as_tensor(u, device="cuda"), power=True).cpu().numpy()
+    assert float(s.sum()) == pytest.approx(float(0.5 * np.mean(u.astype(np.float64) ** 2)), rel=1e-4)
+
+
+def test_get_spectrum_f64_and_vmap():
+    rng = np.random.default_rng(5)
+    u = rng.standard_normal((3, 2, 32, 32))
+    ex.config.update("enable_x64", True)
+    try:
+        got = ex.vmap(ex.get_spectrum)(torch.as_tensor(u, device="cuda")).cpu().numpy()
+    finally:
+        ex.config.update("enable_x64", False)
+    ref = np.stack([ox.get_spectrum(u[b]) for b in range(3)])
+    assert got.dtype == np.float64 and got.shape == (3, 2, 17)
+    assert np.allclose(got, ref, rtol=1e-12, atol=1e-14)
+
+
+def test_stack_sub_trajectories_is_a_view():
+    st = ex.stepper.Burgers(1, 2 * np.pi, 64, 0.01, diffusivity=0.1)
+    u0 = torch.as_tensor(np.sin(ex.make_grid(1, 2 * np.pi, 64)).astype(np.float32), device="cuda")
+    trj = ex.rollout(st, 9, include_init=True)(u0)            # (10, 1, 64)
+    sub = ex.stack_sub_trajectories(trj, 4)
+    assert tuple(sub.shape) == (7, 4, 1, 64)
+    assert sub.data_ptr() == trj.data_ptr()                   # strided view, no copy
+    assert np.array_equal(sub.cpu().numpy(), ox.stack_sub_trajectories(trj.cpu().numpy(), 4))
+
+
+# ---------------------------------------------------------------------------- metrics
+_METRICS = ["MAE", "nMAE", "sMAE", "MSE", "nMSE", "sMSE", "RMSE", "nRMSE", "sRMSE"]
+
+
+@pytest.mark.parametrize("shape", [(1, 200), (2, 64, 64), (3, 24, 24, 24)])
+@pytest.mark.parametrize("name", _METRICS)
+def test_spatial_metrics_match_oracle(shape, name):
+    rng = np.random.default_rng(len(shape))
+    a = rng.standard_normal(shape).astype(np.float32)
+    b = (a + 0.3 * rng.standard_normal(shape)).astype(np.float32)
+    got = getattr(ex.metrics, name)(torch.as_tensor(a, device="cuda"), torch.as_tensor(b, device="cuda"),
+                                    domain_extent=3.0)
+    ref = getattr(ox, name)(a.astype(np.float64), b.astype(np.float64), domain_extent=3.0)
+    assert got.ndim == 0 and got.dtype == torch.float32
+    assert float(got) == pytest.approx(float(ref), rel=2e-6)
+
+
+def test_metrics_reference_known_answers_and_errors():
+    # tests/test_metrics.py:8-88 of the reference, through the CUDA reduction
+    for D in (1, 2, 3):
+        g = ex.make_grid(D, 5.0, 40)
+        u0 = torch.as_tensor(2.0 * np.ones_like(g[0:1]), device="cuda")
+        u1 = torch.as_tensor(4.0 * np.ones_like(g[0:1]), device="cuda")
+        assert float(ex.metrics.MSE(u1, u0, domain_extent=5.0)) == pytest.approx(5.0**D * 4.0, rel=1e-6)
+        assert float(ex.metrics.nMSE(u0, u1)) == pytest.approx(0.25, rel=1e-6)
+        assert float(ex.metrics.sMSE(u1, u0)) == pytest.approx(0.4, rel=1e-6)
+        assert float(ex.metrics.sRMSE(u1, u0)) == pytest.approx(2 / 3, rel=1e-6)
+        assert float(ex.metrics.MAE(u1)) == pytest.approx(4.0, rel=1e-6)
+    u = torch.ones((1, 64), device="cuda")
+    with pytest.raises(ValueError, match="normalized.*requires"):
+        ex.metrics.spatial_norm(u, mode="normalized")
+    with pytest.raises(ValueError, match="symmetric.*requires"):
+        ex.metrics.spatial_norm(u, mode="symmetric")
+    assert float(ex.metrics.spatial_norm(u, inner_exponent=2.0)) == pytest.approx(1.0, abs=1e-6)
+    assert float(ex.metrics.spatial_norm(2 * u, inner_exponent=3.0)) == pytest.approx(2.0, rel=1e-6)
+    assert float(ex.metrics.spatial_aggregator(3 * u[0], inner_exponent=1.0)) == pytest.approx(3.0, rel=1e-6)
+
+
+def test_correlation_mean_metric_vmap_and_f64():
+    rng = np.random.default_rng(7)
+    a = rng.standard_normal((6, 2, 32, 32))
+    b = a + 0.5 * rng.standard_normal((6, 2, 32, 32))
+    ex.config.update("enable_x64", True)
+    try:
+        ta, tb = torch.as_tensor(a, device="cuda"), torch.as_tensor(b, device="cuda")
+        c = ex.metrics.correlation(ta[0], tb[0])
+        assert float(c) == pytest.approx(float(ox.correlation(a[0], b[0])), rel=1e-12)
+        m = ex.metrics.mean_metric(ex.metrics.nRMSE, ta, tb, domain_extent=2.0)
+        assert m.ndim == 0 and m.dtype == torch.float64
+        assert float(m) == pytest.approx(float(ox.mean_metric(ox.nRMSE, a, b, domain_extent=2.0)), rel=1e-12)
+        v = ex.vmap(ex.metrics.MSE)(ta, tb).cpu().numpy()
+        assert v.shape == (6,)
+        assert np.allclose(v, [ox.MSE(a[i], b[i]) for i in range(6)], rtol=1e-12)
+        vc = ex.vmap(ex.metrics.correlation)(ta, tb).cpu().numpy()
+        assert np.allclose(vc, [ox.correlation(a[i], b[i]) for i in range(6)], rtol=1e-12)
+    finally:
+        ex.config.update("enable_x64", False)
+    # NumPy in -> NumPy out
+    r = ex.metrics.RMSE(a[0].astype(np.float32), b[0].astype(np.float32))
+    assert isinstance(r, np.ndarray) and r.dtype == np.float32
+
+
+def test_rollout_error_metric_pipeline():
+    # the consumer the metrics exist for: nRMSE of a rollout against the oracle's, every saved step, one call
+    st = ex.stepper.Burgers(1, 2 * np.pi, 128, 0.01, diffusivity=0.05)
+    so = ox.Burgers(1, 2 * np.pi, 128, 0.01, diffusivity=0.05)
+    u0 = np.sin(ex.make_grid(1, 2 * np.pi, 128)).astype(np.float32)
+    trj = ex.rollout(st, 50)(torch.as_tensor(u0, device="cuda"))
+    ref = ox.rollout(so, 50)(u0)
+    err = ex.vmap(ex.metrics.nRMSE)(trj, torch.as_tensor(ref, device="cuda"))
+    assert tuple(err.shape) == (50,) and float(err.max()) < 1e-5
+
+
+# ---------------------------------------------------------------------------- initial conditions
+def _ic_cases():
+    return [
+        ("RandomTruncatedFourierSeries", dict(cutoff=4), "ic_truncated_fourier_series", dict(cutoff=4)),
+        ("RandomTruncatedFourierSeries", dict(cutoff=3, max_one=True), "ic_truncated_fourier_series",
+         dict(cutoff=3, max_one=True)),
+        ("RandomTruncatedFourierSeries", dict(cutoff=5, std_one=True), "ic_truncated_fourier_series",
+         dict(cutoff=5, std_one=True)),
+        ("GaussianRandomField", dict(powerlaw_exponent=3.5, max_one=True), "ic_gaussian_random_field",
+         dict(powerlaw_exponent=3.5, max_one=True)),
+        ("GaussianRandomField", dict(domain_extent=5.0, std_one=True), "ic_gaussian_random_field",
+         dict(L=5.0, std_one=True)),
+        ("GaussianRandomField", dict(zero_mean=False), "ic_gaussian_random_field", dict(zero_mean=False)),
+        ("DiffusedNoise", dict(intensity=0.002, max_one=True), "ic_diffused_noise", dict(intensity=0.002, max_one=True)),
+        ("DiffusedNoise", dict(domain_extent=3.0, std_one=True), "ic_diffused_noise", dict(L=3.0, std_one=True)),
+    ]
+
+
+@pytest.mark.parametrize("D,N", [(1, 128), (1, 100), (2, 64), (3, 32)])
+@pytest.mark.parametrize("case", _ic_cases(), ids=lambda c: c[0] + "-" + "-".join(f"{k}" for k in c[1]))
+def test_ic_generators_match_oracle_on_the_same_noise(D, N, case):
+    cls, kw, oname, okw = case
+    noise = np.random.default_rng(N + D).standard_normal((1,) + (N,) * D).astype(np.float32)
+    got = getattr(ex.ic, cls)(D, **kw)(N, noise=torch.as_tensor(noise, device="cuda")).cpu().numpy()
+    ref = getattr(ox, oname)(noise, **okw)
+    assert got.shape == ref.shape == (1,) + (N,) * D and got.dtype == np.float32
+    assert rel(got, ref) < 2e-5
+
+
+def test_ic_offset_batch_and_seeding():
+    gen = ex.ic.RandomTruncatedFourierSeries(1, cutoff=3, offset_range=(0.5, 0.5))
+    noise = np.random.default_rng(0).standard_normal((1, 64)).astype(np.float32)
+    got = gen(64, noise=noise)                                     # NumPy in -> NumPy out
+    ref = ox.ic_truncated_fourier_series(noise, cutoff=3, offset=0.5, zero_mean=False)
+    assert isinstance(got, np.ndarray) and rel(got, ref) < 2e-5
+    g2 = ex.ic.GaussianRandomField(2, powerlaw_exponent=3.0, max_one=True)
+    a = ex.build_ic_set(g2, num_points=48, num_samples=5, key=7)
+    b = ex.build_ic_set(g2, num_points=48, num_samples=5, key=7)
+    c = ex.build_ic_set(g2, num_points=48, num_samples=5, key=8)
+    assert tuple(a.shape) == (5, 1, 48, 48)
+    assert torch.equal(a, b) and not torch.equal(a, c)              # deterministic per key, different across keys
+    assert torch.allclose(a.abs().amax(dim=(1, 2, 3)), torch.ones(5, device="cuda"), atol=1e-6)   # per-sample max_one
+    assert float(a.mean(dim=(1, 2, 3)).abs().max()) < 1e-3
+    assert not torch.equal(a[0], a[1])
+    w = ex.ic.WhiteNoise(3, std=2.0)(16, key=0)
+    assert tuple(w.shape) == (1, 16, 16, 16) and float(w.std()) == pytest.approx(2.0, rel=0.1)
+    with pytest.raises(ValueError, match="zero_mean=False"):
+        ex.ic.DiffusedNoise(1, zero_mean=False, std_one=True)
+    with pytest.raises(ValueError, match="std_one=True"):
+        ex.ic.GaussianRandomField(1, std_one=True, max_one=True)
+
+
+def test_normalize_ic_matches_oracle_f64():
+    x = np.random.default_rng(2).standard_normal((2, 40, 40)) * 3 + 1.5
+    ex.config.update("enable_x64", True)
+    try:
+        for kw in (dict(), dict(std_one=True), dict(max_one=True), dict(zero_mean=False, max_one=True)):
+            got = ex.ic.normalize_ic(torch.as_tensor(x, device="cuda"), **kw).cpu().numpy()
+            assert np.allclose(got, ox.normalize_ic(x, **kw), rtol=1e-12, atol=1e-13)
+    finally:
+        ex.config.update("enable_x64", False)
+
+
+def test_readme_pipeline_on_device():
+    # ic -> rollout -> spectrum / metric, everything resident on the GPU (README.md:60-80 of the reference)
+    ic = ex.ic.RandomTruncatedFourierSeries(1, cutoff=5)(200, key=0)
+    st = ex.stepper.KuramotoSivashinskyConservative(1, 100.0, 200, 0.1)
+    trj = ex.rollout(st, 100, include_init=True)(ic)
+    assert tuple(trj.shape) == (101, 1, 200) and bool(torch.isfinite(trj).all())
+    spec = ex.vmap(ex.get_spectrum)(trj)
+    assert tuple(spec.shape) == (101, 1, 101)
+    ref = np.stack([ox.get_spectrum(t) for t in trj.cpu().numpy()])
+    assert np.allclose(spec.cpu().numpy(), ref, rtol=1e-4, atol=1e-7 * ref.max())

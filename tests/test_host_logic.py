@@ -294,3 +294,16 @@ def test_normalized_and_difficulty_reparametrisations():
         assert st.num_points == 48 and st.domain_extent == 1.0 and st.dt == 1.0
     with pytest.warns(DeprecationWarning):
         g.DiffultyLinearStepperSimple()
+
+
+def test_stack_sub_trajectories_numpy_and_pytree():
+    import exponax_b200 as ex
+    from oracle import exponax_np as ox
+    trj = np.arange(6 * 2 * 4, dtype=np.float32).reshape(6, 2, 4)
+    assert np.array_equal(ex.stack_sub_trajectories(trj, 3), ox.stack_sub_trajectories(trj, 3))
+    a, b = ex.stack_sub_trajectories((trj, trj[:, :1]), 2)
+    assert a.shape == (5, 2, 2, 4) and b.shape == (5, 2, 1, 4)
+    with pytest.raises(ValueError):
+        ex.stack_sub_trajectories(trj, 7)
+    with pytest.raises(ValueError):
+        ex.stack_sub_trajectories((trj, trj[:4]), 2)
