@@ -24,6 +24,16 @@
 #ifndef EXB_EPI_PREFETCH
 #define EXB_EPI_PREFETCH 0
 #endif
+// COL_FWD_EPI / COL_FWD_NL with several channels: evaluate N(u) of all 8 modes first, then stream the update.
+// Measured on c4 (r01l): 9.04e9 vs 9.42e9 interleaved (more spills at 64 registers) -> off.
+#ifndef EXB_EPI_TWO_PHASE
+#define EXB_EPI_TWO_PHASE 0
+#endif
+// resident CTAs per SM the multi-field epilogue kernels are compiled for (2: 64 registers with spills,
+// 1: 96 registers without).  Measured on c4 (r01l): 1 -> 8.2e9, 2 -> 9.42e9: occupancy wins.
+#ifndef EXB_EPI_MULTI_MINBLOCKS
+#define EXB_EPI_MULTI_MINBLOCKS 2
+#endif
 #ifndef EXB_INVPRO_SMEM_U
 #define EXB_INVPRO_SMEM_U 1
 #endif
@@ -41,7 +51,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // ------------------------------------------------------------------------------- column pass
 template <int N, int TW, class S, int NFWD, int MODE, int DIR>
 __global__ void __launch_bounds__((N / 8) * TW, (MODE == COL_PLAIN ? 2048 / ((N / 8) * TW)
-                                                 : (MODE == COL_INV_PRO ? 2 : (NFWD == 1 ? 3 : 2))))
+                                                 : (MODE == COL_INV_PRO ? 2 : (NFWD == 1 ? 3 : EXB_EPI_MULTI_MINBLOCKS))))
 col_fast_kernel(const ColParams<float> p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int P = N / 8;
@@ -188,6 +198,36 @@ col_fast_kernel(const ColParams<float> p) {
     for (int g = 0; g < NFWD; ++g) fft8_run<N, DIR>(W[g], ex, j, tw);
   }
   if (!act) return;
+  if (EXB_EPI_TWO_PHASE && C == NFWD && C > 1) {
+    // phase A, registers only: N(u)_c of every mode overwrites the forward fields; phase B streams the
+    // ETDRK operands through (its loads depend on nothing, the registers of consumed modes free up)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      ModeK<float> m = make_mode<float, S>(Pn, j + P * q, i1, i2);
+      cpx<float> wq[NFWD], n[EXB_MAXC];
+#pragma unroll
+      for (int g = 0; g < NFWD; ++g) wq[g] = W[g][q];
+      nl_from_fwd<float, S>(Pn, wq, m, n);
+#pragma unroll
+      for (int c = 0; c < C; ++c) W[c < NFWD ? c : 0][q] = n[c];
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const long long mode = (long long)(j + P * q) * ls + iw;
+        const size_t off = ((size_t)b * C + c) * p.M + mode;
+        const cpx<float> n = W[c < NFWD ? c : 0][q];
+        if (MODE == COL_FWD_NL) {
+          p.out[off] = n;
+        } else {
+          const long long ci = (long long)(p.K.E == 1 ? 0 : c) * p.K.M + mode;
+          etdrk_update(p.K, p.stage, ci, off, n, p.sb);
+        }
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const int i0 = j + P * q;
