@@ -80,6 +80,8 @@ def run_c5(args, w, rank, world, local_rank):
     slab.plan()
     slab.overlap = not args.no_overlap
     slab.raw_exchange = not args.no_raw_exchange
+    if args.no_peer_stores:
+        slab.peer_stores = False
     t_ctor = time.time() - t0
     # Taylor-Green + small-mode perturbation generated on the device, slab by slab (never on the host)
     n = N // world
@@ -137,7 +139,10 @@ def run_c5(args, w, rank, world, local_rank):
                 "config": {"workload": f"c5: {w['desc']}", "N": N, "D": 3, "order": 2, "channels": 3,
                            "parallelism": f"slab decomposition x{world}, all_to_all_single (NCCL)",
                            "carry": "spectral (step_fourier loop)",
-                           "overlap": "transposes pipelined per field on a second stream" if slab.overlap else "none"},
+                           "transposes": ("fused into the pass kernels' stores over NVLink peer memory (symmetric memory) + barrier"
+                                          if slab.peer_stores and getattr(slab, "_peer", None) is not None
+                                          else "all_to_all_single (NCCL)" + (", pipelined per field on a second stream" if slab.overlap else "")),
+                           "peer_store_fallback_reason": getattr(slab, "_peer_error", None)},
                 "roofline": {"bound": "hbm", "achieved": per_gpu, "peak": peak, "unit": "GB/s", "frac": per_gpu / peak,
                              "traffic": None, "algorithmic_bytes_per_step_all_gpus": abytes,
                              "alltoall_bytes_per_gpu_per_step": a2a,
@@ -298,6 +303,8 @@ def main():
     ap.add_argument("--N", type=int, default=None, help="override the grid size (c5)")
     ap.add_argument("--cuda-graph", action="store_true", help="replay the fused call from a captured CUDA graph")
     ap.add_argument("--no-raw-exchange", action="store_true", help="c5: pack / unpack copies around the all-to-all")
+    ap.add_argument("--no-peer-stores", action="store_true",
+                    help="c5: NCCL all-to-all transposes instead of pass kernels storing into peer memory")
     ap.add_argument("--no-overlap", action="store_true", help="c5: do not pipeline transposes against passes")
     args = ap.parse_args()
 

@@ -16,6 +16,8 @@ own slab of the state, of the intermediates and of the ETDRK coefficient tables.
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 
 import numpy as np
@@ -193,6 +195,8 @@ class SlabStepper:
         self._bufs = {}
         self.overlap = True   # pipeline the all-to-all transposes against the passes (two streams)
         self.raw_exchange = True  # no pack / unpack copies around the all-to-all (EXB_SLAB_SEGMENTED)
+        # transposes fused into the pass kernels' stores over NVLink peer memory (falls back to the all-to-all)
+        self.peer_stores = os.environ.get("EXB_SLAB_PEER_STORES", "1") != "0"
 
     # ---- plan with the LOCAL slices of the coefficient tables --------------------------------
     def _local(self, arr):
@@ -297,6 +301,32 @@ class SlabStepper:
             return out
         S = [self._buf(f"S{i}", self.Cn).view(self.Cn, self.N, self.n, self.Nh) for i in range(self.order)]
         S += [None] * (4 - self.order)
+        peer = self._peer_buffers() if (self.peer_stores and self.raw_exchange and self.P > 1) else None
+        if peer is not None:
+            # Transposes fused into the stores of the passes that feed them: every rank writes its results
+            # straight into the peers' buffers over NVLink (symmetric memory), a barrier replaces the
+            # all-to-all.  Hazards: a peer overwrites my winv_a (wfwd_b) only after the barrier that follows
+            # my last read of it in stream order, see DESIGN.md section 5.
+            lib, h, st = nat.lib(), self.plan().handle, A.stream_ptr()
+            wfwd_a = self._buf("wfwd_a", self.n_fwd)
+            try:
+                for s in range(self.order):
+                    si = etdrk_stage_input(self.order, s)
+                    src = uh if si < 0 else S[si]
+                    nat.check(lib.exb_slab_pass_peer(h, st, nat.SLAB_COL0_INV_PRO, 0, self.n_inv, A.ptr(src),
+                                                     peer["ptrs_inv"]))
+                    peer["hdl_inv"].barrier(channel=0)
+                    self._pass(nat.SLAB_COL1_INV_NL | nat.SLAB_SEGMENTED, self.n_inv, peer["winv_a"], peer["winv_a"])
+                    self._pass(nat.SLAB_ROW_NL, self.n_inv, peer["winv_a"], wfwd_a)
+                    nat.check(lib.exb_slab_pass_peer(h, st, nat.SLAB_COL1_FWD_NL | nat.SLAB_SEGMENTED, 0, self.n_fwd,
+                                                     A.ptr(wfwd_a), peer["ptrs_fwd"]))
+                    peer["hdl_fwd"].barrier(channel=0)
+                    self._pass(nat.SLAB_COL0_FWD_EPI, self.n_fwd, peer["wfwd_b"], None, stage=s, U=uh, OUT=out, S=S)
+                return out
+            except NotImplementedError:
+                # generic kernels (grid size without a fast instantiation): raised by the FIRST call on every
+                # rank alike, before anything was enqueued -> use the all-to-all path from now on
+                self.peer_stores = False
         # the B-layout buffer is shared by the inverse fields and (later in the stage) the forward fields
         nb = max(self.n_inv, self.n_fwd)
         wb = self._buf("w_b", nb)
@@ -364,6 +394,38 @@ class SlabStepper:
                 done.record(torch.cuda.current_stream())
                 self._comm_stream().wait_event(done)
         return out
+
+    def _peer_buffers(self):
+        """winv_a (n_inv fields, layout A) and wfwd_b (n_fwd fields, layout B) in symmetric memory + the peers'
+        base pointers; None (and peer_stores switched off on EVERY rank) if symmetric memory is unavailable."""
+        if getattr(self, "_peer", None) is not None or not self.peer_stores:
+            return getattr(self, "_peer", None)
+        import ctypes
+        ok, peer = 1, None
+        try:
+            import torch.distributed._symmetric_memory as symm
+            group = self.group if self.group is not None else dist.group.WORLD
+            per_field = self.N * self.n * self.Nh
+            rt = A.real_t(self.stepper._dtype)
+
+            def make(nfields, shape):
+                flat = symm.empty(nfields * per_field * 2, dtype=rt, device=torch.device("cuda", torch.cuda.current_device()))
+                hdl = symm.rendezvous(flat, group)
+                ptrs = (ctypes.c_void_p * self.P)(*[int(x) for x in hdl.buffer_ptrs])
+                return torch.view_as_complex(flat.view(-1, 2)).view((nfields,) + shape), hdl, ptrs
+
+            winv_a, hdl_inv, ptrs_inv = make(self.n_inv, (self.n, self.N, self.Nh))
+            wfwd_b, hdl_fwd, ptrs_fwd = make(self.n_fwd, (self.N, self.n, self.Nh))
+            peer = dict(winv_a=winv_a, hdl_inv=hdl_inv, ptrs_inv=ptrs_inv, wfwd_b=wfwd_b, hdl_fwd=hdl_fwd,
+                        ptrs_fwd=ptrs_fwd)
+        except Exception as e:  # noqa: BLE001 -- any failure means: no peer memory here
+            ok, self._peer_error = 0, repr(e)
+        flag = torch.tensor([ok], device="cuda", dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)     # all ranks take the same path
+        if int(flag.item()) == 0:
+            self.peer_stores, peer = False, None
+        self._peer = peer
+        return peer
 
     def _comm_stream(self):
         if getattr(self, "_comm", None) is None:

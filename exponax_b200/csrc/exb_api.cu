@@ -54,6 +54,7 @@ struct exb_plan {
                         const void* U, void* OUT, void* const* S) = 0;
   virtual void nl_fields(int* ni, int* nf) const = 0;
   virtual int slab_inv_pro_fields(cudaStream_t st, int f0, int nf, const void* in, void* out) = 0;
+  virtual int slab_pass_peer(cudaStream_t st, int pass, int f0, int nf, const void* in, void* const* peers) = 0;
   virtual int spectrum(cudaStream_t st, int64_t nfields, const void* uh, void* out, int power, int average,
                        void* counts) = 0;
   virtual int ic_shape(cudaStream_t st, int64_t nfields, void* uh, int kind, double param, double domain_extent,
@@ -439,7 +440,7 @@ template <class T> struct PlanImpl : exb_plan {
 
   template <int DIR>
   int col_plain(cudaStream_t st, int axis, long long batch, int nfields, const cpx<T>* in, cpx<T>* out,
-                int prune = 0, bool segmented = false) {
+                int prune = 0, bool segmented = false, void* const* peers = nullptr, long long peer_field_off = 0) {
     ColParams<T> p;
     memset(&p, 0, sizeof(p));
     p.prune = prune;
@@ -460,6 +461,12 @@ template <class T> struct PlanImpl : exb_plan {
       p.seg_stride = (long long)nloc * nloc * Nh;
       p.outer_stride = (long long)nloc * Nh;
     }
+    if (peers) {
+      if (!fast_nd || !segmented) return fail(EXB_EUNSUPPORTED, "peer stores need the fast N-D kernels");
+      p.peer = 1;
+      p.peer_off = (long long)this->d.slab_rank * p.seg_stride + peer_field_off;
+      for (int r = 0; r < nranks; ++r) p.peer_out[r] = (cpx<T>*)peers[r];
+    }
     if (fast_nd) return launch_col_fast(st, p, DIR, p.n_outer * batch * nfields);
     long long ntiles = (p.inner + p.TW - 1) / p.TW;
     long long grid = ntiles * p.n_outer * batch * nfields;
@@ -470,7 +477,8 @@ template <class T> struct PlanImpl : exb_plan {
     return EXB_OK;
   }
 
-  int col_inv_pro(cudaStream_t st, long long batch, const cpx<T>* state, cpx<T>* winv, int f0 = 0, int fcount = 0) {
+  int col_inv_pro(cudaStream_t st, long long batch, const cpx<T>* state, cpx<T>* winv, int f0 = 0, int fcount = 0,
+                  void* const* peers = nullptr) {
     ColParams<T> p;
     memset(&p, 0, sizeof(p));
     p.f0 = f0;
@@ -488,6 +496,13 @@ template <class T> struct PlanImpl : exb_plan {
     p.in = state;
     p.out = winv;
     col_geom(p, 0);
+    if (peers) {
+      if (!fast_nd || nranks <= 1) return fail(EXB_EUNSUPPORTED, "peer stores need the fast N-D kernels");
+      p.peer = 1;
+      p.seg_len = nloc;                                      // x-planes per rank
+      p.peer_off = (long long)this->d.slab_rank * nloc * p.line_stride;   // block [me] of the peer's [src][x][k1][K] buffer
+      for (int r = 0; r < nranks; ++r) p.peer_out[r] = (cpx<T>*)peers[r];
+    }
     if (fast_nd) return launch_col_fast(st, p, +1, batch);
     long long ntiles = (p.inner + p.TW - 1) / p.TW;
     long long grid = ntiles * batch;
@@ -658,6 +673,21 @@ template <class T> struct PlanImpl : exb_plan {
     if (D != 3) return fail(EXB_EINVAL, "exb_slab_inv_pro_fields needs a 3-D plan");
     if (f0 < 0 || nf < 1 || f0 + nf > P.n_inv) return fail(EXB_EINVAL, "field range out of bounds");
     return col_inv_pro(st, 1, (const cpx<T>*)in, (cpx<T>*)out, f0, nf);
+  }
+  int slab_pass_peer(cudaStream_t st, int pass, int f0, int nf, const void* in, void* const* peers) override {
+    if (D != 3 || nranks <= 1) return fail(EXB_EINVAL, "exb_slab_pass_peer needs a multi-rank 3-D slab plan");
+    if (nranks > EXB_MAX_PEERS) return fail(EXB_EUNSUPPORTED, "at most %d ranks", EXB_MAX_PEERS);
+    if (!peers) return fail(EXB_EINVAL, "null peer table");
+    if (pass == EXB_SLAB_COL0_INV_PRO) {
+      if (f0 < 0 || nf < 1 || f0 + nf > P.n_inv) return fail(EXB_EINVAL, "field range out of bounds");
+      return col_inv_pro(st, 1, (const cpx<T>*)in, nullptr, f0, nf, peers);
+    }
+    if (pass == (EXB_SLAB_COL1_FWD_NL | EXB_SLAB_SEGMENTED) || pass == (EXB_SLAB_COL1_FWD | EXB_SLAB_SEGMENTED)) {
+      if (f0 < 0 || nf < 1) return fail(EXB_EINVAL, "field range out of bounds");
+      const int prune = pass == (EXB_SLAB_COL1_FWD_NL | EXB_SLAB_SEGMENTED) ? (PRUNE_COLS | PRUNE_OUT_ROWS) : 0;
+      return col_plain<-1>(st, 1, 1, nf, (const cpx<T>*)in, nullptr, prune, true, peers, (long long)f0 * M);
+    }
+    return fail(EXB_EINVAL, "exb_slab_pass_peer: pass must be COL0_INV_PRO or a segmented COL1_FWD pass");
   }
   void nl_fields(int* ni, int* nf) const override {
     *ni = P.n_inv;
@@ -1057,6 +1087,11 @@ int exb_slab_pass(exb_plan* plan, void* stream, int32_t pass, int32_t nfields, i
                   void* out, const void* U, void* OUT, void* const* S) {
   if (!plan) return fail(EXB_EINVAL, "null plan");
   return plan->slab_pass((cudaStream_t)stream, pass, nfields, stage, in, out, U, OUT, S);
+}
+int exb_slab_pass_peer(exb_plan* plan, void* stream, int32_t pass, int32_t field0, int32_t nfields, const void* in,
+                       void* const* peer_out) {
+  if (!plan) return fail(EXB_EINVAL, "null plan");
+  return plan->slab_pass_peer((cudaStream_t)stream, pass, field0, nfields, in, peer_out);
 }
 int exb_slab_inv_pro_fields(exb_plan* plan, void* stream, int32_t field0, int32_t nfields, const void* in, void* out) {
   if (!plan) return fail(EXB_EINVAL, "null plan");

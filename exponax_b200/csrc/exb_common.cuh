@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #define EXB_MAX_STAGES 24
+#define EXB_MAX_PEERS 8     // ranks of one slab-decomposed field (one NVSwitch domain)
 #define EXB_MAXC 3        // channels handled in registers by the per-mode operators
 #define EXB_MAX_INV 12    // inverse fields per nonlinear evaluation (3-D multi-channel convection)
 #define EXB_MAX_FWD 9     // forward fields (3-D conservative multi-channel convection)

@@ -38,6 +38,12 @@ template <class T> struct ColParams {
   int f0, fcount;          // COL_INV_PRO: inverse fields [f0, f0 + fcount) (fcount <= 0: all)
   int seg_len;             // COL_PLAIN, slab transposes without pack/unpack: line entry i lives at
   long long seg_stride;    //   (i / seg_len) * seg_stride + (i % seg_len) * line_stride   (seg_len = 0: off)
+  // peer output (fast kernels, COL_INV_PRO / COL_PLAIN of a slab plan): entry i of an output line is stored
+  // into the buffer of rank i / seg_len -- peer_out[r] is that rank's destination buffer mapped into this
+  // process (NVLink peer memory) -- at peer_off + (i % seg_len) * line_stride; the pass IS the transpose.
+  int peer;
+  long long peer_off;
+  cpx<T>* peer_out[EXB_MAX_PEERS];
   long long line_stride;   // elements between successive points of a line
   long long inner;         // contiguous positions across which lines are tiled
   long long n_outer;       // independent slabs per field (3-D axis-1 pass: N)

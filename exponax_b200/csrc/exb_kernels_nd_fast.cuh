@@ -107,9 +107,18 @@ col_fast_kernel(const ColParams<float> p) {
       v[q] = (col_keep && (!prune_rows_in || row_keep(j + P * q))) ? p.in[base + line_off(j + P * q)] : zero;
     fft8_run<N, DIR>(v, ex, j, tw);
     if (col_keep) {
+      if (p.peer) {  // the store is the transpose: segment r of the line lives on rank r
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
-        if (!prune_rows_out || row_keep(j + P * q)) p.out[base + line_off(j + P * q)] = v[q];
+        for (int q = 0; q < 8; ++q) {
+          const int i = j + P * q;
+          if (!prune_rows_out || row_keep(i))
+            p.peer_out[i / p.seg_len][base + p.peer_off + (size_t)(i % p.seg_len) * ls] = v[q];
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (!prune_rows_out || row_keep(j + P * q)) p.out[base + line_off(j + P * q)] = v[q];
+      }
     }
     return;
   }
@@ -167,8 +176,16 @@ col_fast_kernel(const ColParams<float> p) {
       fft8_run<N, DIR>(v, ex, j, tw);
       if (col_keep) {
         const size_t obase = ((size_t)b * Pn.n_inv + f) * p.M + iw;
+        if (p.peer) {  // x-plane i of the result belongs to rank i / seg_len: store it there (NVLink)
 #pragma unroll
-        for (int q = 0; q < 8; ++q) p.out[obase + (size_t)(j + P * q) * ls] = v[q];
+          for (int q = 0; q < 8; ++q) {
+            const int i = j + P * q;
+            p.peer_out[i / p.seg_len][obase + p.peer_off + (size_t)(i % p.seg_len) * ls] = v[q];
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) p.out[obase + (size_t)(j + P * q) * ls] = v[q];
+        }
       }
     }
     return;

@@ -183,6 +183,16 @@ int exb_slab_pass(exb_plan *plan, void *stream, int32_t pass, int32_t nfields, i
    overlap the all-to-all of field f with the prologue pass of field f+1 (out = base of ALL fields) */
 int exb_slab_inv_pro_fields(exb_plan *plan, void *stream, int32_t field0, int32_t nfields, const void *in,
                             void *out);
+/* The two passes that feed a transpose, with the transpose fused into their stores: the results go straight
+   into the peers' buffers over NVLink (peer_out[r] = base of rank r's destination buffer for ALL fields,
+   mapped into this process -- CUDA IPC / symmetric memory), so no collective is needed, only a barrier
+   before the consumers read.  Fast kernels only (EXB_EUNSUPPORTED otherwise: use the all-to-all path).
+     pass = EXB_SLAB_COL0_INV_PRO:                      in = stage input (layout B);   peers' n_inv-field A buffers
+     pass = EXB_SLAB_COL1_FWD[_NL] | EXB_SLAB_SEGMENTED: in = local raw-order A field(s) [field0, +nfields);
+                                                         peers' n_fwd-field B buffers
+   (in points at field `field0` for the COL1 pass, at the stage input for COL0_INV_PRO.) */
+int exb_slab_pass_peer(exb_plan *plan, void *stream, int32_t pass, int32_t field0, int32_t nfields,
+                       const void *in, void *const *peer_out);
 /* number of single-field inverse / forward transforms per N(u) evaluation of this plan */
 int exb_plan_nl_fields(const exb_plan *plan, int32_t *n_inv, int32_t *n_fwd);
 

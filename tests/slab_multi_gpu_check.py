@@ -50,12 +50,19 @@ def main():
         slab = ex.SlabStepper(st)
         ref = ox.repeat(getattr(ox, name)(3, L, N, dt, order=order), 3)(u0)
         single = ex.repeat(st, 3, spectral_carry=True)(torch.as_tensor(u0, device="cuda")).cpu().numpy()
-        # every combination of {pipelined, serial} x {raw all-to-all buffers, packed transposes}
-        for overlap in (True, False):
-            for raw in (True, False):
-                slab.overlap, slab.raw_exchange = overlap, raw
+        # peer-memory stores, then every combination of {pipelined, serial} x {raw all-to-all buffers, packed}
+        want_peer = slab.peer_stores
+        for peer, overlap, raw in ((True, True, True), (False, True, True), (False, True, False),
+                                   (False, False, True), (False, False, False)):
+            if peer and not want_peer:
+                continue
+            if True:
+                slab.peer_stores, slab.overlap, slab.raw_exchange = peer, overlap, raw
                 got = slab.gather(slab.repeat(slab.scatter(u0), 3)).cpu().numpy()
-                tag = f"{name}_N{N}_ov{int(overlap)}_raw{int(raw)}"
+                if peer:
+                    report[f"{name}_N{N}_peer_active"] = bool(slab.peer_stores and getattr(slab, "_peer", None) is not None)
+                    report[f"{name}_N{N}_peer_error"] = getattr(slab, "_peer_error", None)
+                tag = f"{name}_N{N}_peer{int(peer)}_ov{int(overlap)}_raw{int(raw)}"
                 report[f"{tag}_vs_oracle"] = rel(got, ref)
                 report[f"{tag}_vs_single_gpu"] = rel(got, single)
                 assert rel(got, ref) < 5e-5, report
