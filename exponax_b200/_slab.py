@@ -195,8 +195,12 @@ class SlabStepper:
         self._bufs = {}
         self.overlap = True   # pipeline the all-to-all transposes against the passes (two streams)
         self.raw_exchange = True  # no pack / unpack copies around the all-to-all (EXB_SLAB_SEGMENTED)
-        # transposes fused into the pass kernels' stores over NVLink peer memory (falls back to the all-to-all)
-        self.peer_stores = os.environ.get("EXB_SLAB_PEER_STORES", "1") != "0"
+        # Transposes fused into the pass kernels' stores over NVLink peer memory (falls back to the all-to-all).
+        # A pass CTA owns an [N x TW] tile, so a remote store is TW * 8 contiguous bytes: measured +7 % at
+        # 1024^3 on 2 GPUs (TW = 4: 109 vs 117 ms) but -38 % at 2048^3 on 8 GPUs (TW = 2, 16-byte NVLink writes:
+        # 539 vs 391 ms) -> on by default only up to N = 1024; EXB_SLAB_PEER_STORES=1 / 0 forces it on / off.
+        env = os.environ.get("EXB_SLAB_PEER_STORES", "auto")
+        self.peer_stores = env == "1" or (env != "0" and N <= 1024)
 
     # ---- plan with the LOCAL slices of the coefficient tables --------------------------------
     def _local(self, arr):
