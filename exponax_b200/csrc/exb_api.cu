@@ -55,6 +55,8 @@ struct exb_plan {
   virtual void nl_fields(int* ni, int* nf) const = 0;
   virtual int slab_inv_pro_fields(cudaStream_t st, int f0, int nf, const void* in, void* out) = 0;
   virtual int slab_pass_peer(cudaStream_t st, int pass, int f0, int nf, const void* in, void* const* peers) = 0;
+  virtual int fourier_sums(cudaStream_t st, int64_t nfields, const void* xh, double p, int low, int high,
+                           double order, double domain_extent, double* out) = 0;
   virtual int spectrum(cudaStream_t st, int64_t nfields, const void* uh, void* out, int power, int average,
                        void* counts) = 0;
   virtual int ic_shape(cudaStream_t st, int64_t nfields, void* uh, int kind, double param, double domain_extent,
@@ -781,6 +783,38 @@ template <class T> struct PlanImpl : exb_plan {
     return EXB_OK;
   }
 
+  int fourier_sums(cudaStream_t st, int64_t nfields, const void* xh, double p, int low, int high, double order,
+                   double domain_extent, double* out) override {
+    if (nranks > 1) return fail(EXB_EINVAL, "slab plans only support exb_slab_pass");
+    if (nfields < 1 || nfields > 65535 || !xh || !out) return fail(EXB_EINVAL, "exb_fourier_sums: bad arguments");
+    if (!(domain_extent > 0)) return fail(EXB_EINVAL, "exb_fourier_sums: domain_extent must be > 0");
+    FourierSumParams<T> q;
+    q.xh = (const cpx<T>*)xh;
+    q.out = out;
+    q.D = D;
+    q.N = N;
+    q.Nh = Nh;
+    q.ncomp = order >= 0 ? D : 1;
+    q.M = M;
+    long long nchunk = (M + 4095) / 4096;
+    const long long target = std::max<long long>(1, (8ll * sm_count + nfields - 1) / nfields);
+    if (nchunk > target) nchunk = target;
+    q.chunk = (M + nchunk - 1) / nchunk;
+    q.p = (T)p;
+    q.pi = p == 1.0 ? 1 : (p == 2.0 ? 2 : 0);
+    q.filter = (low >= 0 || high >= 0) ? 1 : 0;
+    q.low = low >= 0 ? low : 0;
+    q.high = high >= 0 ? high : N / 2 + 1;
+    q.order = (T)order;
+    q.two_pi_over_L = (T)(6.283185307179586476925286766559 / domain_extent);
+    CUDA_OK(cudaMemsetAsync(out, 0, (size_t)nfields * q.ncomp * sizeof(double), st));
+    dim3 grid((unsigned)nchunk, (unsigned)nfields);
+    fourier_sums_kernel<T><<<grid, 256, 0, st>>>(q);
+    CUDA_OK(cudaGetLastError());
+    ++launches;
+    return EXB_OK;
+  }
+
   int spectrum(cudaStream_t st, int64_t nfields, const void* uh, void* out, int power, int average,
                void* counts) override {
     if (nranks > 1) return fail(EXB_EINVAL, "slab plans only support exb_slab_pass");
@@ -1077,6 +1111,11 @@ int exb_ic_normalize(void* stream, int32_t dtype, int64_t nfields, int64_t npoin
   if (dtype == EXB_F64)
     return ic_normalize_t<double>((cudaStream_t)stream, nfields, npoints, u, zero_mean, std_one, max_one, stats);
   return fail(EXB_EINVAL, "exb_ic_normalize: unknown dtype");
+}
+int exb_fourier_sums(exb_plan* plan, void* stream, int64_t nfields, const void* x_hat, double p, int32_t low,
+                     int32_t high, double derivative_order, double domain_extent, double* out) {
+  if (!plan) return fail(EXB_EINVAL, "null plan");
+  return plan->fourier_sums((cudaStream_t)stream, nfields, x_hat, p, low, high, derivative_order, domain_extent, out);
 }
 int exb_spectrum(exb_plan* plan, void* stream, int64_t nfields, const void* u_hat, void* out, int32_t power,
                  int32_t average, void* counts) {

@@ -17,6 +17,7 @@
  *   exb_spectrum       <- exponax/_spectral.py:866-1030  (get_spectrum after its fft)
  *   exb_ic_shape / exb_ic_normalize <- exponax/ic/_truncated_fourier_series.py:65-100,
  *                         ic/_gaussian_random_field.py:64-93, ic/_base_ic.py:16-33
+ *   exb_fourier_sums   <- exponax/metrics/_fourier.py:15-140 (fourier_aggregator after its fft)
  *   exb_metric_sums    <- exponax/metrics/_spatial.py:8-196, metrics/_correlation.py:6-60
  *
  * Conventions
@@ -226,6 +227,15 @@ int exb_ic_normalize(void *stream, int32_t dtype, int64_t nfields, int64_t npoin
    normalised / symmetric ratios, channel sum). */
 int exb_metric_sums(void *stream, int32_t dtype, int64_t nfields, int64_t npoints, const void *a,
                     const void *b, double p, double *out);
+
+/* Fourier-space aggregation behind exponax.metrics.fourier_* / H1_* (metrics/_fourier.py:15-140), applied to
+   x_hat = exb_fft(x), x_hat: (nfields, N.., N/2+1) complex of this plan's grid.  Per field and derivative
+   component d:  out[f * ncomp + d] = sum_modes band * (|x_hat| * |2 pi k_d / domain_extent|^order)^p / recon
+   with |x_hat| < 1e-5 dropped, band = not(all |k_d| <= low-1) and (all |k_d| <= high) when low >= 0 or
+   high >= 0 (a negative bound = not given), recon = the "reconstruction" scaling of the rfft layout.
+   derivative_order < 0: no derivative, ncomp = 1; otherwise ncomp = D.  out: device double[nfields * ncomp]. */
+int exb_fourier_sums(exb_plan *plan, void *stream, int64_t nfields, const void *x_hat, double p,
+                     int32_t low, int32_t high, double derivative_order, double domain_extent, double *out);
 
 /* number of kernel launches issued through this plan so far (bench bookkeeping) */
 int64_t exb_launch_count(const exb_plan *plan);

@@ -1355,3 +1355,70 @@ def ic_diffused_noise(noise, *, L=1.0, intensity=0.001, zero_mean=True, std_one=
     D, N = noise.ndim - 1, noise.shape[-1]
     ic = Diffusion(D, L, N, 1.0, diffusivity=intensity, dtype=noise.dtype.type)(noise)
     return normalize_ic(ic, zero_mean=zero_mean, std_one=std_one, max_one=max_one)
+
+
+def fourier_aggregator(state_no_channel, *, num_spatial_dims=None, domain_extent=1.0, num_points=None,
+                       inner_exponent=2.0, outer_exponent=None, low=None, high=None, derivative_order=None):
+    """exponax/metrics/_fourier.py:15-140."""
+    D = state_no_channel.ndim if num_spatial_dims is None else num_spatial_dims
+    N = state_no_channel.shape[-1] if num_points is None else num_points
+    dt = state_no_channel.dtype.type
+    if outer_exponent is None:
+        outer_exponent = 1 / inner_exponent
+    sh = fft(state_no_channel, num_spatial_dims=D)
+    sh = np.where(np.abs(sh) < 1e-5, np.zeros_like(sh), sh)
+    if low is not None or high is not None:
+        low = 0 if low is None else low
+        high = N // 2 + 1 if high is None else high
+        low_mask = low_pass_filter_mask(D, N, cutoff=low - 1, dtype=dt)
+        high_mask = low_pass_filter_mask(D, N, cutoff=high, dtype=dt)
+        sh = sh * (np.invert(low_mask) & high_mask)[0]
+    if derivative_order is not None:
+        dop = build_derivative_operator(D, domain_extent, N, dt)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            sd = sh[None] * np.abs(dop) ** derivative_order     # only |.| is used below: |(i k c)^o| = |k c|^o
+    else:
+        sd = sh[None]
+    recon = build_scaling_array(D, N, mode="reconstruction", dtype=dt)[0]
+    scale = (domain_extent / N) ** D
+    return sum((scale * np.sum(np.abs(s) ** inner_exponent / recon)) ** outer_exponent for s in sd)
+
+
+def fourier_norm(state, state_ref=None, *, mode="absolute", domain_extent=1.0, inner_exponent=2.0,
+                 outer_exponent=None, low=None, high=None, derivative_order=None):
+    """exponax/metrics/_fourier.py:143-235."""
+    if state_ref is None:
+        if mode == "normalized":
+            raise ValueError("mode 'normalized' requires state_ref")
+        diff = state
+    else:
+        diff = state - state_ref
+    kw = dict(domain_extent=domain_extent, inner_exponent=inner_exponent, outer_exponent=outer_exponent, low=low,
+              high=high, derivative_order=derivative_order)
+    d = np.array([fourier_aggregator(c, **kw) for c in diff])
+    if mode == "normalized":
+        d = d / np.array([fourier_aggregator(c, **kw) for c in state_ref])
+    return np.sum(d)
+
+
+def _fmetric(mode, p, q):
+    def fn(u_pred, u_ref=None, *, domain_extent=1.0, low=None, high=None, derivative_order=None):
+        return fourier_norm(u_pred, u_ref, mode=mode, domain_extent=domain_extent, inner_exponent=p,
+                            outer_exponent=q, low=low, high=high, derivative_order=derivative_order)
+    return fn
+
+
+fourier_MAE, fourier_nMAE = _fmetric("absolute", 1.0, 1.0), _fmetric("normalized", 1.0, 1.0)
+fourier_MSE, fourier_nMSE = _fmetric("absolute", 2.0, 1.0), _fmetric("normalized", 2.0, 1.0)
+fourier_RMSE, fourier_nRMSE = _fmetric("absolute", 2.0, 0.5), _fmetric("normalized", 2.0, 0.5)
+
+
+def _h1(base):
+    def fn(u_pred, u_ref=None, *, domain_extent=1.0, low=None, high=None):
+        kw = dict(domain_extent=domain_extent, low=low, high=high)
+        return base(u_pred, u_ref, derivative_order=None, **kw) + base(u_pred, u_ref, derivative_order=1, **kw)
+    return fn
+
+
+H1_MAE, H1_nMAE, H1_MSE = _h1(fourier_MAE), _h1(fourier_nMAE), _h1(fourier_MSE)
+H1_nMSE, H1_RMSE, H1_nRMSE = _h1(fourier_nMSE), _h1(fourier_RMSE), _h1(fourier_nRMSE)

@@ -1051,3 +1051,52 @@ def test_readme_pipeline_on_device():
     assert tuple(spec.shape) == (101, 1, 101)
     ref = np.stack([ox.get_spectrum(t) for t in trj.cpu().numpy()])
     assert np.allclose(spec.cpu().numpy(), ref, rtol=1e-4, atol=1e-7 * ref.max())
+
+
+_FMETRICS = ["fourier_MAE", "fourier_nMAE", "fourier_MSE", "fourier_nMSE", "fourier_RMSE", "fourier_nRMSE"]
+
+
+@pytest.mark.parametrize("shape", [(1, 200), (2, 48, 48), (2, 17, 17, 17)])
+@pytest.mark.parametrize("name", _FMETRICS)
+@pytest.mark.parametrize("kw", [dict(), dict(low=2, high=9), dict(derivative_order=1), dict(high=6, derivative_order=2)],
+                         ids=["plain", "band", "d1", "band-d2"])
+def test_fourier_metrics_match_oracle(shape, name, kw):
+    rng = np.random.default_rng(len(shape) + 11)
+    a = rng.standard_normal(shape).astype(np.float32)
+    b = (a + 0.3 * rng.standard_normal(shape)).astype(np.float32)
+    got = getattr(ex.metrics, name)(torch.as_tensor(a, device="cuda"), torch.as_tensor(b, device="cuda"),
+                                    domain_extent=3.0, **kw)
+    ref = getattr(ox, name)(a, b, domain_extent=3.0, **kw)
+    assert got.ndim == 0 and got.dtype == torch.float32
+    assert float(got) == pytest.approx(float(ref), rel=5e-5)
+
+
+def test_fourier_and_h1_reference_known_answers():
+    # tests/test_metrics.py:95-224 of the reference through the CUDA path
+    for D in (1, 2, 3):
+        g = ex.make_grid(D, 2 * np.pi, 40)
+        u = np.sin(4 * g[0:1])
+        for d in range(1, D):
+            u = u * np.sin(4 * g[d:d + 1])
+        u = torch.as_tensor(u.astype(np.float32), device="cuda")
+        nz = lambda **kw: abs(float(ex.metrics.fourier_MSE(u, **kw))) > 1e-6
+        assert nz() and not nz(low=8) and nz(high=8) and not nz(high=2) and nz(low=2) and nz(low=2, high=8)
+        assert not nz(low=8, high=16) and not nz(low=0, high=2) and nz(low=4, high=8) and nz(low=0, high=4)
+        rng = np.random.default_rng(D)
+        a = ex.ic.RandomTruncatedFourierSeries(D, offset_range=(-1, 1))(40, key=1)
+        b = ex.ic.RandomTruncatedFourierSeries(D, offset_range=(-1, 1))(40, key=2)
+        assert float(ex.metrics.fourier_MSE(a, b, domain_extent=5.0)) == pytest.approx(
+            float(ex.metrics.MSE(a, b, domain_extent=5.0)), rel=1e-4)                 # Parseval
+        for name in ("MAE", "nMAE", "MSE", "nMSE", "RMSE", "nRMSE"):
+            f = getattr(ex.metrics, "fourier_" + name)
+            want = float(f(a, b, domain_extent=5.0)) + float(f(a, b, domain_extent=5.0, derivative_order=1))
+            assert float(getattr(ex.metrics, "H1_" + name)(a, b, domain_extent=5.0)) == pytest.approx(want, rel=1e-5)
+            ref = getattr(ox, "H1_" + name)(a.cpu().numpy(), b.cpu().numpy(), domain_extent=5.0)
+            assert float(getattr(ex.metrics, "H1_" + name)(a, b, domain_extent=5.0)) == pytest.approx(float(ref), rel=1e-4)
+    with pytest.raises(ValueError, match="normalized"):
+        ex.metrics.fourier_norm(torch.ones((1, 64), device="cuda"), mode="normalized")
+    v = ex.vmap(ex.metrics.fourier_nRMSE)(torch.stack([a, b]), torch.stack([b, a]))
+    assert tuple(v.shape) == (2,)
+    assert float(v[0]) == pytest.approx(float(ex.metrics.fourier_nRMSE(a, b)), rel=1e-6)
+    agg = ex.metrics.fourier_aggregator(a[0], domain_extent=5.0)
+    assert float(agg) == pytest.approx(float(ox.fourier_aggregator(a[0].cpu().numpy(), domain_extent=5.0)), rel=1e-4)
