@@ -58,7 +58,7 @@ WORKLOADS = {
                         "('under a second on a modern GPU'); every step saved"),
     "c5": dict(stepper="KolmogorovFlowVelocity", D=3, L=2 * np.pi, N=2048, dt=1e-3, kw=dict(diffusivity=0.01), C=3,
                B=1, T=1, final_only=True,
-               desc="KolmogorovFlowVelocity 3-D single field, slab-decomposed FFT with NCCL all-to-all (needs --gpus >= 2)"),
+               desc="KolmogorovFlowVelocity 3-D single field, slab-decomposed FFT (needs --gpus >= 2)"),
 }
 
 
@@ -137,7 +137,7 @@ def run_c5(args, w, rank, world, local_rank):
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"c5: {w['desc']}", "N": N, "D": 3, "order": 2, "channels": 3,
-                           "parallelism": f"slab decomposition x{world}, all_to_all_single (NCCL)",
+                           "parallelism": f"slab decomposition x{world}",
                            "carry": "spectral (step_fourier loop)",
                            "transposes": ("fused into the pass kernels' stores over NVLink peer memory (symmetric memory) + barrier"
                                           if slab.peer_stores and getattr(slab, "_peer", None) is not None

@@ -1,5 +1,5 @@
-// Fast 2-D / 3-D pass kernels (f32, N in {64,128,256,512}) built on the register FFT core
-// exb_fft8.cuh.  Same pass structure and fusion as the generic kernels (exb_kernels_nd.cuh):
+// Fast 2-D / 3-D pass kernels (f32, N in {128,256,512} and, for the slab-decomposed 3-D path, 1024 / 2048)
+// built on the register FFT core exb_fft8.cuh.  Same pass structure and fusion as the generic kernels (exb_kernels_nd.cuh):
 //   col_fast<MODE>:  strided axis; a CTA owns a [N x TW] tile; thread (j, w) holds 8 points of
 //                    column w in registers, global loads/stores are coalesced across w, the
 //                    shared-memory tile is only the exchange buffer between radix passes;
@@ -9,6 +9,9 @@
 //                    (two-for-one), runs the n_inv inverse transforms, the pointwise
 //                    nonlinearity in registers and the n_fwd forward transforms.
 // The nonlinear function is a compile-time descriptor S (NlS<...>).
+// Slab extras: COL_PLAIN addresses segmented lines (the raw all-to-all buffer of a slab transpose), and
+// COL_PLAIN / COL_INV_PRO can store their results straight into the peers' buffers (ColParams::peer_out).
+// Compile-time switches below are A/B knobs (scripts/build_variant.sh); their defaults are the measured best.
 #pragma once
 #include "exb_fft8.cuh"
 #include "exb_kernels_nd.cuh"
