@@ -307,3 +307,54 @@ def test_stack_sub_trajectories_numpy_and_pytree():
         ex.stack_sub_trajectories(trj, 7)
     with pytest.raises(ValueError):
         ex.stack_sub_trajectories((trj, trj[:4]), 2)
+
+
+def test_substack_trjs_reference_cases():
+    # tests/test_substack_trjs.py of the reference, on NumPy arrays (host path of ex.stack_sub_trajectories)
+    import exponax_b200 as ex
+    trj = np.array([1, 2, 3, 4, 5, 6])
+    want = np.array([[1, 2, 3], [2, 3, 4], [3, 4, 5], [4, 5, 6]])
+    got = ex.stack_sub_trajectories(trj, 3)
+    assert got.shape == want.shape and np.array_equal(got, want)
+    tree = {"a": trj, "b": trj + 9}
+    got = ex.stack_sub_trajectories(tree, 3)
+    assert got.keys() == tree.keys()
+    assert np.array_equal(got["a"], want) and np.array_equal(got["b"], want + 9)
+    with pytest.raises(ValueError):
+        ex.stack_sub_trajectories({"a": trj, "b": trj[:5]}, 3)
+    with pytest.raises(ValueError):
+        ex.stack_sub_trajectories(trj, 7)
+    assert np.array_equal(ex.stack_sub_trajectories(trj, 6), trj[None])
+
+
+@pytest.mark.parametrize("D,N", [(D, N) for D in (1, 2, 3) for N in (10, 11)])
+def test_scaling_arrays_reference_cases(D, N):
+    # tests/test_spectral_scaling_arrays.py of the reference: host builder of the product AND the oracle's
+    import exponax_b200 as ex
+    from oracle import exponax_np as ox
+    noise = np.random.default_rng(0).standard_normal((1,) + (N,) * D)
+    axes = tuple(range(-D, 0))
+    back = np.fft.rfftn(noise, axes=axes)
+    fwd = np.fft.rfftn(noise, axes=axes, norm="forward")
+    for build in (lambda **kw: ex.spectral.build_scaling_array(D, N, dtype=np.float64, **kw),
+                  lambda **kw: ox.build_scaling_array(D, N, dtype=np.float64, **kw)):
+        assert np.allclose(back / build(mode="norm_compensation"), fwd)
+    for mode in ("norm_compensation", "reconstruction", "coef_extraction"):
+        assert np.array_equal(ex.spectral.build_scaling_array(D, N, mode=mode, dtype=np.float64),
+                              ox.build_scaling_array(D, N, mode=mode, dtype=np.float64))
+    with pytest.raises(ValueError):
+        ex.spectral.build_scaling_array(D, N, mode="nope")
+
+
+def test_coef_extraction_reads_amplitudes():
+    # tests/test_spectral_scaling_arrays.py:44-90 of the reference (through the oracle's fft)
+    from oracle import exponax_np as ox
+    g = ox.make_grid(1, 2 * np.pi, 10)
+    s = ox.build_scaling_array(1, 10, mode="coef_extraction")
+    assert (ox.fft(3 * np.cos(2 * g)) / s).round(5)[0, 2] == pytest.approx(3.0 + 0.0j)
+    assert (ox.fft(3.0 * np.ones_like(g)) / s).round(5)[0, 0] == pytest.approx(3.0 + 0.0j)
+    g2 = ox.make_grid(2, 2 * np.pi, 10)
+    s2 = ox.build_scaling_array(2, 10, mode="coef_extraction")
+    u = 3 * np.cos(2 * g2[0:1]) * np.cos(3 * g2[1:2])
+    # a product of two cosines carries amplitude 3 split over the +-k pair of the full axis: 3 / 2 each
+    assert abs((ox.fft(u) / s2)[0, 2, 3]) == pytest.approx(3.0, rel=1e-5)
