@@ -18,8 +18,8 @@ from ._config import config
 from ._forced_stepper import ForcedStepper
 from ._repeated_stepper import RepeatedStepper
 from ._slab import SlabStepper
-from ._spectral import fft, get_spectrum, ifft
-from ._utils import build_ic_set, make_grid, repeat, rollout, stack_sub_trajectories, vmap
+from ._spectral import derivative, fft, get_spectrum, ifft
+from ._utils import build_ic_set, make_grid, repeat, rollout, stack_sub_trajectories, vmap, wrap_bc
 
 __version__ = "0.1.0"
 
@@ -30,6 +30,7 @@ __all__ = [
     "SlabStepper",
     "build_ic_set",
     "config",
+    "derivative",
     "distributed",
     "etdrk",
     "fft",
@@ -45,4 +46,5 @@ __all__ = [
     "stack_sub_trajectories",
     "stepper",
     "vmap",
+    "wrap_bc",
 ]

@@ -84,6 +84,7 @@ SYMBOLS = {
                                C.c_double]),
     "exb_ic_normalize": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,
                                    C.c_int32, C.c_void_p]),
+    "exb_derivative": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32, C.c_double]),
     "exb_fourier_sums": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_double, C.c_int32, C.c_int32,
                                    C.c_double, C.c_double, C.c_void_p]),
     "exb_metric_sums": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_double,

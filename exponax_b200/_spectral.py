@@ -241,6 +241,35 @@ def ifft(field_hat, *, num_spatial_dims: int | None = None, num_points: int | No
     return A.from_device(out, kind)
 
 
+def derivative(field, domain_extent: float, *, order: int = 1, indexing: str = "ij"):
+    """Spectral derivative of every channel along every axis == exponax.derivative
+    (exponax/_spectral.py:724-792): `(C, N, .., N)` -> `(C, D, N, .., N)`, or `(D, N, .., N)` for C == 1.
+    exb_fft -> exb_derivative (u_hat * (i k_d 2 pi / L)^order) -> exb_ifft."""
+    if indexing != "ij":
+        raise NotImplementedError("only indexing='ij' is supported")
+    if int(order) != order or order < 0:
+        raise ValueError("order must be a non-negative integer")
+    rd = real_dtype()
+    t, kind = A.to_device(field, rd)
+    C_ = t.shape[0]
+    D = t.ndim - 1
+    N = t.shape[-1]
+    if any(s != N for s in t.shape[1:]):
+        raise ValueError("all spatial axes must have the same length")
+    torch = A.torch
+    uh = torch.empty((C_,) + wavenumber_shape(D, N), dtype=A.cplx_t(rd), device="cuda")
+    dh = torch.empty((C_ * D,) + wavenumber_shape(D, N), dtype=A.cplx_t(rd), device="cuda")
+    out = torch.empty((C_ * D,) + spatial_shape(D, N), dtype=A.real_t(rd), device="cuda")
+    plan = _plain_plan(D, N, rd)
+    ws = workspace(plan.workspace_bytes(C_ * D))
+    lib, st = nat.lib(), A.stream_ptr()
+    nat.check(lib.exb_fft(plan.handle, st, C_, 1, A.ptr(t), A.ptr(uh), A.ptr(ws)))
+    nat.check(lib.exb_derivative(plan.handle, st, C_, A.ptr(uh), A.ptr(dh), int(order), float(domain_extent)))
+    nat.check(lib.exb_ifft(plan.handle, st, C_ * D, 1, A.ptr(dh), A.ptr(out), A.ptr(ws)))
+    out = out.view((C_, D) + spatial_shape(D, N))
+    return A.from_device(out[0] if C_ == 1 else out, kind)
+
+
 def get_spectrum(state, *, power: bool = True, radial_binning: Literal["average", "sum"] = "sum",
                  num_spatial_dims: int | None = None):
     """Power (default) or amplitude spectrum of a state `(C, N, .., N)` -> `(C, N//2 + 1)`, radially binned in

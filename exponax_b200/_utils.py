@@ -86,6 +86,16 @@ def stack_sub_trajectories(trj, sub_len: int):
     return trj.as_strided((n_win, sub_len) + tuple(trj.shape[1:]), (st[0], st[0]) + tuple(st[1:]))
 
 
+def wrap_bc(u):
+    """Append the periodic image: `(C, N, .., N)` -> `(C, N+1, .., N+1)` == exponax.wrap_bc
+    (exponax/_utils.py:69-89; for plotting the full domain)."""
+    if isinstance(u, np.ndarray):
+        return np.pad(u, ((0, 0),) + ((0, 1),) * (u.ndim - 1), mode="wrap")
+    for axis in range(1, u.ndim):
+        u = A.torch.cat([u, u.narrow(axis, 0, 1)], dim=axis)
+    return u
+
+
 def build_ic_set(ic_generator, *, num_points: int, num_samples: int, key=0):
     """`num_samples` initial conditions `(S, C, N, .., N)` == exponax.build_ic_set (exponax/_utils.py:316-348).
     Generators of `exponax_b200.ic` produce the whole set in one batched pipeline; any other callable

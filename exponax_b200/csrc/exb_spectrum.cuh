@@ -82,4 +82,38 @@ __global__ void spectrum_average_kernel(T* out, const unsigned* counts, int Nh, 
   out[i] = c ? out[i] / (T)c : (T)NAN;
 }
 
+// exponax.derivative (exponax/_spectral.py:724-792) between its fft and ifft:
+//   out[(f * D + d) * M + m] = u_hat[f * M + m] * (i * 2 pi k_d / L)^order        (integer order >= 0)
+// The Nyquist entries are left as the reference leaves them (no "fix"); the inverse transform drops the
+// imaginary part an odd order produces on the rfft axis, exactly as irfftn does.
+template <class T>
+__global__ void derivative_kernel(const cpx<T>* __restrict__ uh, cpx<T>* __restrict__ out, int D, int N, int Nh,
+                                  long long M, long long total, int order, T two_pi_over_L) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long f = i / M, m = i - f * M;
+  int k[3] = {0, 0, 0};
+  k[D - 1] = (int)(m % Nh);
+  long long rest = m / Nh;
+  for (int d = D - 2; d >= 0; --d) {
+    k[d] = wavenumber_of((int)(rest % N), N);
+    rest /= N;
+  }
+  const cpx<T> v = uh[i];
+  // v * i^order
+  cpx<T> r;
+  switch (order & 3) {
+    case 0: r = v; break;
+    case 1: r = cpx<T>(-v.y, v.x); break;
+    case 2: r = cpx<T>(-v.x, -v.y); break;
+    default: r = cpx<T>(v.y, -v.x); break;
+  }
+  for (int d = 0; d < D; ++d) {
+    const T kc = (T)k[d] * two_pi_over_L;
+    T w = (T)1;
+    for (int e = 0; e < order; ++e) w *= kc;
+    out[((size_t)f * D + d) * M + m] = cpx<T>(r.x * w, r.y * w);
+  }
+}
+
 }  // namespace exb

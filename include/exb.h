@@ -17,6 +17,7 @@
  *   exb_spectrum       <- exponax/_spectral.py:866-1030  (get_spectrum after its fft)
  *   exb_ic_shape / exb_ic_normalize <- exponax/ic/_truncated_fourier_series.py:65-100,
  *                         ic/_gaussian_random_field.py:64-93, ic/_base_ic.py:16-33
+ *   exb_derivative     <- exponax/_spectral.py:724-792  (derivative between its fft and ifft)
  *   exb_fourier_sums   <- exponax/metrics/_fourier.py:15-140 (fourier_aggregator after its fft)
  *   exb_metric_sums    <- exponax/metrics/_spatial.py:8-196, metrics/_correlation.py:6-60
  *
@@ -227,6 +228,12 @@ int exb_ic_normalize(void *stream, int32_t dtype, int64_t nfields, int64_t npoin
    normalised / symmetric ratios, channel sum). */
 int exb_metric_sums(void *stream, int32_t dtype, int64_t nfields, int64_t npoints, const void *a,
                     const void *b, double p, double *out);
+
+/* exponax.derivative (exponax/_spectral.py:724-792) between its fft and ifft: out_hat (nfields, D, N.., N/2+1)
+   = u_hat (nfields, N.., N/2+1) * (i 2 pi k_d / domain_extent)^order for every axis d; order >= 0 integer;
+   out_hat must not alias u_hat. */
+int exb_derivative(exb_plan *plan, void *stream, int64_t nfields, const void *u_hat, void *out_hat,
+                   int32_t order, double domain_extent);
 
 /* Fourier-space aggregation behind exponax.metrics.fourier_* / H1_* (metrics/_fourier.py:15-140), applied to
    x_hat = exb_fft(x), x_hat: (nfields, N.., N/2+1) complex of this plan's grid.  Per field and derivative

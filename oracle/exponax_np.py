@@ -169,6 +169,20 @@ def make_grid(D, L, N, dtype=np.float32):
     return np.stack(np.meshgrid(*([g] * D), indexing="ij"))
 
 
+def derivative(field, domain_extent, *, order=1):
+    """exponax/_spectral.py:724-792."""
+    D, N = field.ndim - 1, field.shape[-1]
+    dop = build_derivative_operator(D, domain_extent, N, field.dtype.type) ** order
+    fh = fft(field, num_spatial_dims=D)
+    dh = dop * fh if field.shape[0] == 1 else fh[:, None] * dop[None]
+    return ifft(dh, num_spatial_dims=D, num_points=N).astype(field.dtype)
+
+
+def wrap_bc(u):
+    """exponax/_utils.py:69-89."""
+    return np.pad(u, ((0, 0),) + ((0, 1),) * (u.ndim - 1), mode="wrap")
+
+
 def get_spectrum(state, *, power=True, radial_binning="sum"):
     """exponax/_spectral.py:866-1030: power / amplitude spectrum (C, N//2+1), radially binned for D > 1
     with the reference's bucket masks  k - dk/2 <= |k| < k + dk/2  evaluated in the state's precision."""

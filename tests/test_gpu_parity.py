@@ -1100,3 +1100,52 @@ def test_fourier_and_h1_reference_known_answers():
     assert float(v[0]) == pytest.approx(float(ex.metrics.fourier_nRMSE(a, b)), rel=1e-6)
     agg = ex.metrics.fourier_aggregator(a[0], domain_extent=5.0)
     assert float(agg) == pytest.approx(float(ox.fourier_aggregator(a[0].cpu().numpy(), domain_extent=5.0)), rel=1e-4)
+
+
+# ---------------------------------------------------------------------------- derivative / wrap_bc
+@pytest.mark.parametrize("shape", [(1, 128), (2, 100), (1, 48, 48), (2, 32, 32), (1, 16, 16, 16), (3, 20, 20, 20)])
+@pytest.mark.parametrize("order", [1, 2, 3, 4])
+def test_derivative_matches_oracle(shape, order):
+    rng = np.random.default_rng(len(shape) * 7 + order)
+    D, N = len(shape) - 1, shape[-1]
+    noise = rng.standard_normal((shape[0], 1) + shape[1:]).astype(np.float32)
+    u = np.stack([ox.ic_truncated_fourier_series(n, cutoff=4)[0] for n in noise])
+    # orders 3 and 4 amplify the f32 rounding noise of ANY fft by (k_max 2 pi / L)^order (up to 3e-3 relative
+    # between two correct f32 implementations at N = 100): those are compared in double precision
+    x64 = order >= 3
+    if x64:
+        u = u.astype(np.float64)
+        ex.config.update("enable_x64", True)
+    try:
+        got = ex.derivative(torch.as_tensor(u, device="cuda"), 3.0, order=order).cpu().numpy()
+    finally:
+        ex.config.update("enable_x64", False)
+    ref = ox.derivative(u, 3.0, order=order)
+    assert got.dtype == ref.dtype
+    assert got.shape == ref.shape == ((D,) + shape[1:] if shape[0] == 1 else (shape[0], D) + shape[1:])
+    assert rel(got, ref) < (1e-9 if x64 else 1e-4)
+
+
+def test_derivative_and_wrap_bc_known_answers():
+    # tests/test_spectral.py:36-66 and tests/test_utils.py:8-24 of the reference
+    L, k = 3.0, 3
+    for D, axis in ((1, 0), (2, 0), (2, 1)):
+        g = ex.make_grid(D, L, 64)
+        u = np.sin(k * 2 * np.pi * g[axis:axis + 1] / L).astype(np.float32)
+        d = ex.derivative(u, L, order=1)                              # NumPy in -> NumPy out
+        assert isinstance(d, np.ndarray)
+        assert np.allclose(d[axis], k * 2 * np.pi / L * np.cos(k * 2 * np.pi * g[axis] / L), atol=1e-4)
+    for D in (1, 2, 3):
+        u = torch.as_tensor(np.sin(2 * np.pi * ex.make_grid(D, L, 10)[0:1] / L), device="cuda")
+        full = np.sin(2 * np.pi * ex.make_grid(D, L, 10, full=True)[0:1] / L)
+        w = ex.wrap_bc(u)
+        assert tuple(w.shape) == (1,) + (11,) * D and np.allclose(w.cpu().numpy(), full, atol=1e-5)
+    ex.config.update("enable_x64", True)
+    try:
+        g = ex.make_grid(1, 2 * np.pi, 64)
+        d = ex.derivative(torch.as_tensor(np.sin(3 * g), device="cuda"), 2 * np.pi, order=2).cpu().numpy()
+        assert d.dtype == np.float64 and np.allclose(d, -9 * np.sin(3 * g), atol=1e-10)
+    finally:
+        ex.config.update("enable_x64", False)
+    with pytest.raises(ValueError):
+        ex.derivative(torch.zeros((1, 8), device="cuda"), 1.0, order=-1)

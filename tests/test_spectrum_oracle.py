@@ -109,3 +109,38 @@ def test_stack_sub_trajectories():
         assert np.array_equal(s[i], trj[i:i + 3])
     with pytest.raises(ValueError):
         ox.stack_sub_trajectories(trj, 8)
+
+
+# ---- exponax.derivative / wrap_bc (tests/test_spectral.py:36-86, 172-196, 447-480; test_utils.py:8-24) ----
+@pytest.mark.parametrize("D,axis", [(1, 0), (2, 0), (2, 1)])
+def test_derivative_of_sine(D, axis):
+    L, k = 3.0, 3
+    g = ox.make_grid(D, L, 64)
+    u = np.sin(k * 2 * np.pi * g[axis:axis + 1] / L).astype(np.float32)
+    want = k * 2 * np.pi / L * np.cos(k * 2 * np.pi * g[axis] / L)
+    assert np.allclose(ox.derivative(u, L, order=1)[axis], want, atol=1e-4)
+
+
+def test_higher_order_and_multi_channel_derivatives():
+    g = ox.make_grid(1, 2 * np.pi, 64)
+    assert np.allclose(ox.derivative(np.sin(3 * g).astype(np.float32), 2 * np.pi, order=2), -9 * np.sin(3 * g), atol=1e-3)
+    g = ox.make_grid(1, 2 * np.pi, 32)
+    u = np.sin(g).astype(np.float32)
+    assert np.allclose(ox.derivative(u, 2 * np.pi, order=3), -np.cos(g), atol=1e-3)
+    assert np.allclose(ox.derivative(u, 2 * np.pi, order=4), np.sin(g), atol=0.01)
+    u2 = np.concatenate([np.sin(g), np.cos(2 * g)]).astype(np.float32)
+    d = ox.derivative(u2, 2 * np.pi)
+    assert d.shape == (2, 1, 32)
+    assert np.allclose(d[0, 0], np.cos(g[0]), atol=1e-4) and np.allclose(d[1, 0], -2 * np.sin(2 * g[0]), atol=1e-4)
+    g2 = ox.make_grid(2, 1.0, 16)
+    u = np.concatenate([np.sin(2 * np.pi * g2[0:1]), np.cos(2 * np.pi * g2[1:2])]).astype(np.float32)
+    d = ox.derivative(u, 1.0)
+    assert d.shape == (2, 2, 16, 16) and np.all(np.isfinite(d))
+
+
+@pytest.mark.parametrize("D", [1, 2, 3])
+def test_wrap_bc(D):
+    L = 3.0
+    u = np.sin(2 * np.pi * ox.make_grid(D, L, 10)[0:1] / L)
+    full = np.sin(2 * np.pi * np.stack(np.meshgrid(*([np.linspace(0, L, 11)] * D), indexing="ij"))[0:1] / L)
+    assert np.allclose(ox.wrap_bc(u), full, atol=1e-5)
