@@ -294,8 +294,12 @@ def get_spectrum(state, *, power: bool = True, radial_binning: Literal["average"
     nat.check(nat.lib().exb_fft(plan.handle, A.stream_ptr(), nf, 1, A.ptr(t), A.ptr(uh), A.ptr(ws)))
     average = radial_binning == "average" and D > 1   # 1-D: one mode per bin, nothing to average
     counts = torch.empty(N // 2 + 1, dtype=torch.int32, device="cuda") if average else None
-    nat.check(nat.lib().exb_spectrum(plan.handle, A.stream_ptr(), nf, A.ptr(uh), A.ptr(out), int(bool(power)),
-                                     int(average), A.ptr(counts)))
+    M = int(np.prod(wavenumber_shape(D, N)))
+    for f0 in range(0, nf, 65535):           # one launch covers at most 65535 fields (grid.y)
+        n = min(65535, nf - f0)
+        nat.check(nat.lib().exb_spectrum(plan.handle, A.stream_ptr(), n, A.ptr(uh) + f0 * M * uh.element_size(),
+                                         A.ptr(out) + f0 * (N // 2 + 1) * out.element_size(), int(bool(power)),
+                                         int(average), A.ptr(counts)))
     return A.from_device(out, kind)
 
 

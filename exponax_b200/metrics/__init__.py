@@ -32,8 +32,13 @@ def _sums(a, b, p: float, nfields: int):
             raise ValueError(f"shape mismatch: {tuple(ta.shape)} vs {tuple(tb.shape)}")
     npoints = ta.numel() // nfields
     out = A.torch.empty((nfields, 4), dtype=A.torch.float64, device="cuda")
-    nat.check(nat.lib().exb_metric_sums(A.stream_ptr(), nat.EXB_F32 if rd == np.float32 else nat.EXB_F64, nfields,
-                                        npoints, A.ptr(ta), A.ptr(tb), float(p), A.ptr(out)))
+    es = ta.element_size()
+    for f0 in range(0, nfields, 65535):      # one launch covers at most 65535 fields (grid.y)
+        n = min(65535, nfields - f0)
+        nat.check(nat.lib().exb_metric_sums(
+            A.stream_ptr(), nat.EXB_F32 if rd == np.float32 else nat.EXB_F64, n, npoints,
+            A.ptr(ta) + f0 * npoints * es, (A.ptr(tb) + f0 * npoints * es) if tb is not None else 0, float(p),
+            A.ptr(out) + f0 * 4 * 8))
     return out, kind, rd, ta
 
 
