@@ -97,6 +97,23 @@ def _slab_worker(rank, ws, port, q):
         assert torch.equal(transpose_a_to_b(a), b)
         assert torch.equal(transpose_b_to_a(b), a)
         assert torch.equal(transpose_b_to_a(transpose_a_to_b(a)), a)
+        # raw exchange (EXB_SLAB_SEGMENTED): the all-to-all lands in peer-major order [src][x][k1 within src][K];
+        # entry i of an axis-1 line lives at (i // n) * (n*n*K) + x * (n*K) + (i % n) * K  -- what the segmented
+        # column pass and the peer-store kernels address
+        from exponax_b200._slab import exchange_a_to_b_raw, exchange_b_to_a_raw
+        for f in range(F):
+            raw = torch.empty_like(a[f])
+            exchange_b_to_a_raw(b[f], raw)
+            seg = raw.view(ws, n, n, K)                                  # [src][x][k1_r][K]
+            assert torch.equal(seg.permute(1, 0, 2, 3).reshape(n, N, K), a[f])
+            flat = raw.reshape(-1)
+            for x in range(n):
+                for i in (0, n - 1, n, N - 1):
+                    off = (i // n) * (n * n * K) + x * (n * K) + (i % n) * K
+                    assert torch.equal(flat[off:off + K], a[f, x, i])
+            back = torch.empty_like(b[f])
+            exchange_a_to_b_raw(raw, back)
+            assert torch.equal(back, b[f])
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         q.put((rank, repr(e)))
