@@ -358,3 +358,22 @@ def test_coef_extraction_reads_amplitudes():
     u = 3 * np.cos(2 * g2[0:1]) * np.cos(3 * g2[1:2])
     # a product of two cosines carries amplitude 3 split over the +-k pair of the full axis: 3 / 2 each
     assert abs((ox.fft(u) / s2)[0, 2, 3]) == pytest.approx(3.0, rel=1e-5)
+
+
+@pytest.mark.parametrize("N", [128, 256, 512, 1024, 2048])
+def test_line_exchange_swizzle_is_conflict_free(N):
+    # model of ExLine::slot (exponax_b200/csrc/exb_fft8.cuh): every store / load pattern of the radix passes is
+    # one wavefront per half-warp; only the reversed partner load of the two-for-one split pays a second one
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("smem_conflicts", os.path.join(ROOT, "scripts", "smem_conflicts.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    tot, ideal = m.cost(m.slot_swizzle, N, kinds=("st1", "st2", "st3", "ld"))
+    assert tot == ideal
+    rev, rev_ideal = m.cost(m.slot_swizzle, N, kinds=("rev",))
+    assert rev <= 2 * rev_ideal
+    padded, _ = m.cost(m.slot_padded, N, kinds=("ld",))
+    assert padded > m.cost(m.slot_swizzle, N, kinds=("ld",))[0]      # what the swizzle removed
+    # the formula in the kernel source is the one modelled here
+    src = open(os.path.join(ROOT, "exponax_b200", "csrc", "exb_fft8.cuh")).read()
+    assert "i ^ ((i >> 4) & 7) ^ ((i >> 3) & 8)" in src
