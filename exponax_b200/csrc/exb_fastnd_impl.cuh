@@ -1,6 +1,12 @@
 // Shared body of exb_fastnd_n{256,512}.cu: instantiations + launchers for one line length.
 #include "exb_fastnd.h"
 #include "exb_kernels_nd_fast.cuh"
+#ifndef EXB_ROW16
+#define EXB_ROW16 0
+#endif
+#if EXB_ROW16
+#include "exb_row16.cuh"
+#endif
 
 using namespace exb;
 
@@ -38,6 +44,21 @@ int launch_col(cudaStream_t st, const ColParams<float>& p, long long grid, const
 
 template <int N, class S, int NINV, int NFWD, int MODE>
 int launch_row(cudaStream_t st, const RowParams<float>& p, const char** err) {
+#if EXB_ROW16
+  // experimental 16-points-per-thread row pass (one shared-memory exchange per transform), see exb_row16.cuh
+  if constexpr (N == 256 && MODE == ROW_NL && row_streams<S, NINV, NFWD, MODE>()) {
+    const size_t smem16 = row16_smem<S, NINV, NFWD>();
+    if (int rc = set_smem(row16_kernel<S, NINV, NFWD>, smem16, err)) return rc;
+    const long long np16 = (p.rows + 1) / 2 * p.batch;
+    row16_kernel<S, NINV, NFWD><<<(unsigned)((np16 + 15) / 16), 256, smem16, st>>>(p);
+    cudaError_t e16 = cudaGetLastError();
+    if (e16 != cudaSuccess) {
+      *err = cudaGetErrorString(e16);
+      return EXB_ECUDA;
+    }
+    return EXB_OK;
+  }
+#endif
   constexpr int P = N / 8, GROUPS = 256 / P;
   const bool prefetch = MODE == ROW_NL && (EXB_ROW_PREFETCH != 0);  // staging rows, see row_fast_kernel
   const int nhp = (N / 2 + 1 + 7) / 8 * 8;
