@@ -377,3 +377,13 @@ def test_line_exchange_swizzle_is_conflict_free(N):
     # the formula in the kernel source is the one modelled here
     src = open(os.path.join(ROOT, "exponax_b200", "csrc", "exb_fft8.cuh")).read()
     assert "i ^ ((i >> 4) & 7) ^ ((i >> 3) & 8)" in src
+
+
+def test_experimental_kernels_are_not_in_the_shipped_library():
+    # exb_row16.cuh is an un-run A/B candidate: it must only exist in variant builds (-DEXB_ROW16=1)
+    lib = os.path.join(ROOT, "exponax_b200", "libexb.so")
+    if not os.path.exists(lib):
+        pytest.skip("library not built")
+    assert b"row16_kernel" not in open(lib, "rb").read()
+    impl = open(os.path.join(ROOT, "exponax_b200", "csrc", "exb_fastnd_impl.cuh")).read()
+    assert "#define EXB_ROW16 0" in impl
