@@ -74,6 +74,8 @@ SYMBOLS = {
     "exb_rollout": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_uint32,
                               C.c_void_p, C.c_void_p, C.c_void_p]),
     "exb_launch_count": (C.c_int64, [C.c_void_p]),
+    "exb_peak_fp32": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
+    "exb_peak_smem": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "exb_slab_pass": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "exb_slab_inv_pro_fields": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),

@@ -536,6 +536,11 @@ template <class T> struct PlanImpl : exb_plan {
     p.out = nl_out;
     p.sb = sb;
     col_geom(p, 0);
+    {  // coefficient tables this stage reads (E or E/2 complex + one or more real tables) vs the L2 (126 MB)
+      static const char* env = getenv("EXB_EPI_BATCH_FASTEST");
+      const size_t table_bytes = (size_t)K.E * M * (sizeof(cpx<T>) + sizeof(T));
+      p.batch_fastest = env ? atoi(env) : (batch > 1 && table_bytes > ((size_t)48 << 20));
+    }
     if (fast_nd) return launch_col_fast(st, p, -1, batch);
     long long ntiles = (p.inner + p.TW - 1) / p.TW;
     long long grid = ntiles * batch;

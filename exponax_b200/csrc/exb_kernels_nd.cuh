@@ -36,6 +36,7 @@ template <class T> struct ColParams {
   int stage;               // ETDRK stage (FWD_EPI)
   int prune;               // fast kernels only: PRUNE_* bits (dealiased modes are never touched)
   int f0, fcount;          // COL_INV_PRO: inverse fields [f0, f0 + fcount) (fcount <= 0: all)
+  int batch_fastest;       // fast COL_FWD_EPI: block index = tile * batch + trajectory (tables larger than the L2)
   int seg_len;             // COL_PLAIN, slab transposes without pack/unpack: line entry i lives at
   long long seg_stride;    //   (i / seg_len) * seg_stride + (i % seg_len) * line_stride   (seg_len = 0: off)
   // peer output (fast kernels, COL_INV_PRO / COL_PLAIN of a slab plan): entry i of an output line is stored
@@ -184,7 +185,8 @@ template <class T, int DIR> __global__ void col_pass_kernel(const ColParams<T> p
           p.out[off] = n[ch];
         } else {
           const long long ci = (long long)(p.K.E == 1 ? 0 : ch) * p.K.M + mode;
-          etdrk_update(p.K, p.stage, ci, off, n[ch], p.sb);
+          if (!m.keep && !m.is_inj) etdrk_update_masked(p.K, p.stage, ci, off, p.sb);  // N(u) == 0 there
+          else etdrk_update(p.K, p.stage, ci, off, n[ch], p.sb);
         }
       }
     }

@@ -40,6 +40,13 @@
 #ifndef EXB_INVPRO_SMEM_U
 #define EXB_INVPRO_SMEM_U 1
 #endif
+#ifndef EXB_EPI_BATCH_FASTEST
+#define EXB_EPI_BATCH_FASTEST 1
+#endif
+// COL_FWD_EPI: dealiased modes take the closed-form update (etdrk_update_masked): no stage buffers, no N(u)
+#ifndef EXB_EPI_MASKED_SKIP
+#define EXB_EPI_MASKED_SKIP 1
+#endif
 
 namespace exb {
 
@@ -64,8 +71,15 @@ col_fast_kernel(const ColParams<float> p) {
   const int w = threadIdx.x % TW, j = threadIdx.x / TW;
   const long long ntiles = (p.inner + TW - 1) / TW;
   long long bid = blockIdx.x;
-  const long long t = bid % ntiles;
-  bid /= ntiles;
+  // COL_FWD_EPI: the trajectory is the FASTEST block index, so the CTAs that run together read the same tile of
+  // the coefficient tables (3-D: E + c1 + c2 = 135 MB at 256^3, more than the L2 holds) once from HBM and
+  // batch - 1 times from L2 instead of re-streaming them per trajectory
+  // (only when the tables do not fit the L2 -- p.batch_fastest, set by the host: with L2-resident tables the
+  //  tile-fastest order is better, neighbouring CTAs then complete each other's DRAM pages / 128-byte lines:
+  //  c3 lost 10 % with the trajectory-fastest order, r02a)
+  const bool batch_fastest = (MODE == COL_FWD_EPI) && EXB_EPI_BATCH_FASTEST && p.batch_fastest;
+  const long long t = batch_fastest ? bid / p.batch : bid % ntiles;
+  bid = batch_fastest ? bid % p.batch : bid / ntiles;
   const long long w0 = t * TW;
   const bool act = w0 + w < p.inner;
   const cpx<float> zero(0.f, 0.f);
@@ -206,6 +220,20 @@ col_fast_kernel(const ColParams<float> p) {
                        p.sb, c == 0 || p.K.E != 1);
     }
   }
+  // is the (single) injection mode outside the mask?  (then masked modes are not all N(u) == 0)
+  bool inj_masked = false;
+  if (Pn.has_inj && kmax >= 0) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      if (d < S::D) {
+        int k = (d == S::D - 1) ? Pn.inj_idx[d] : wavenumber_of(Pn.inj_idx[d], N);
+        inj_masked = inj_masked || (k < 0 ? -k : k) > kmax;
+      }
+    }
+  }
+  const bool masked_skip = MODE == COL_FWD_EPI && EXB_EPI_MASKED_SKIP && kmax >= 0 && !inj_masked;
+  // a tile of dealiased columns: N(u) == 0, the intermediate stages have nothing to do
+  if (masked_skip && !any_keep && p.stage != p.K.order - 1) return;
   cpx<float> W[NFWD][8];
 #pragma unroll
   for (int g = 0; g < NFWD; ++g) {
@@ -252,11 +280,18 @@ col_fast_kernel(const ColParams<float> p) {
   for (int q = 0; q < 8; ++q) {
     const int i0 = j + P * q;
     ModeK<float> m = make_mode<float, S>(Pn, i0, i1, i2);
+    const long long mode = (long long)i0 * ls + iw;
+    if (masked_skip && !m.keep) {
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+        etdrk_update_masked(p.K, p.stage, (long long)(p.K.E == 1 ? 0 : c) * p.K.M + mode,
+                            ((size_t)b * C + c) * p.M + mode, p.sb);
+      continue;
+    }
     cpx<float> wq[NFWD], n[EXB_MAXC];
 #pragma unroll
     for (int g = 0; g < NFWD; ++g) wq[g] = W[g][q];
     nl_from_fwd<float, S>(Pn, wq, m, n);
-    const long long mode = (long long)i0 * ls + iw;
 #pragma unroll
     for (int c = 0; c < C; ++c) {
       const size_t off = ((size_t)b * C + c) * p.M + mode;

@@ -244,6 +244,15 @@ int exb_derivative(exb_plan *plan, void *stream, int64_t nfields, const void *u_
 int exb_fourier_sums(exb_plan *plan, void *stream, int64_t nfields, const void *x_hat, double p,
                      int32_t low, int32_t high, double derivative_order, double domain_extent, double *out);
 
+/* ---- measurement utilities ("the FP32 peak is not in MEASURED_PEAKS.json -- measure it") ----
+   The 1-D persistent kernel (config c2) is bound by FP32 issue and shared-memory bandwidth, not by HBM; these
+   two micro-benchmarks give the denominators bench.py reports its fractions against.  Both allocate 256 B of
+   scratch, time 5 launches with CUDA events on `stream` and SYNCHRONISE (measurement only, never on the hot path).
+     exb_peak_fp32: tflops[0] = scalar FFMA chains, tflops[1] = packed fma.rn.f32x2 (FFMA2) chains   [TFLOP/s]
+     exb_peak_smem: gbs[0] = conflict-free 8-byte loads (the kernels' complex<float> accesses), gbs[1] = 16-byte [GB/s] */
+int exb_peak_fp32(void *stream, double *tflops);
+int exb_peak_smem(void *stream, double *gbs);
+
 /* number of kernel launches issued through this plan so far (bench bookkeeping) */
 int64_t exb_launch_count(const exb_plan *plan);
 

@@ -4,6 +4,8 @@ NumPy oracle on identical seeded inputs.  Tolerances are those of BASELINE.json'
 relative L2 <= 1e-5 per step in float32, <= 1e-12 in float64, <= 1e-4 over 100-step rollouts of
 non-chaotic equations.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -479,6 +481,90 @@ def test_full_size_c4_navier_stokes_128():
     gh = ox.fft(got, num_spatial_dims=3)
     div = np.sum(ox.build_derivative_operator(3, L, N) * gh, axis=0)
     assert np.abs(div).max() / np.abs(gh).max() < 1e-4
+
+
+def test_full_size_c4_navier_stokes_256_benchmarked_instantiation():
+    """Config c4 at its benchmarked size (256^3, C = 3: `col_fast_kernel<256,16,NlS<5..>>`, the N = 256 row pass):
+    one and two ETDRK2 steps vs the oracle (VERDICT r01 missing #3; SURVEY 8d "256^3 oracle once for a few steps").
+    The field is Taylor-Green plus a full-spectrum perturbation, so the dealiased (masked) modes carry energy and
+    the closed-form masked update is exercised at this size too."""
+    L, N, dt = 2 * np.pi, 256, 0.005
+    g = ox.make_grid(3, L, N)
+    rng = np.random.default_rng(256)
+    u0 = np.stack([np.sin(g[0]) * np.cos(g[1]) * np.cos(g[2]),
+                   -np.cos(g[0]) * np.sin(g[1]) * np.cos(g[2]),
+                   np.zeros_like(g[0])]).astype(np.float32)
+    u0 += 0.01 * rng.standard_normal(u0.shape).astype(np.float32)
+    del g
+    ox.set_fft_workers(os.cpu_count() or 1)
+    st = ex.stepper.NavierStokesVelocity(3, L, N, dt, diffusivity=0.01)
+    ost = ox.NavierStokesVelocity(3, L, N, dt, diffusivity=0.01)
+    r1 = ost(u0)
+    got1 = host(st(dev(u0)))
+    assert rel(got1, r1) < F32_STEP, rel(got1, r1)
+    r2 = ost(r1)
+    # the benchmarked call: repeat(RepeatedStepper(stepper, 2), 1) == 2 ETDRK2 steps with a spectral carry, batch of 2
+    both = np.stack([u0, 0.5 * u0])
+    got2 = host(ex.vmap(ex.repeat(ex.RepeatedStepper(st, 2), 1))(dev(both)))
+    assert rel(got2[0], r2) < 3e-5, rel(got2[0], r2)
+    assert rel(got2[1], ost(ost(0.5 * u0))) < 3e-5
+    # the masked modes (|k_d| > 84 for some d) must have advanced by exp(dt L) exactly per step
+    gh = ox.fft(got1, num_spatial_dims=3)
+    rh = ox.fft(r1, num_spatial_dims=3)
+    mask = ox.low_pass_filter_mask(3, N, cutoff=(2 / 3) * (N // 2) - 1)
+    hi = ~np.broadcast_to(mask, gh.shape)
+    # (relative to the masked modes alone: the noise floor is the f32 rounding of the 100x larger Taylor-Green part)
+    assert np.linalg.norm(gh[hi] - rh[hi]) / np.linalg.norm(rh[hi]) < 1e-4
+
+
+def test_c2_production_batch_sampled_trajectories():
+    """Config c2 at the benchmarked batch (B = 16384, T = 1000: tail CTA, 74+ CTAs of 28 trajectories): 8 random
+    trajectories of the full call at steps 1 / 100 / 1000 vs the oracle (VERDICT r01 weak #1)."""
+    N, L, dt, B, T = 256, 2 * np.pi, 0.01, 16384, 1000
+    rng = np.random.default_rng(7)
+    k = np.arange(1, 6)
+    x = np.arange(N) * (2 * np.pi / N)
+    a = rng.standard_normal((B, 1, 5, 1)).astype(np.float32)
+    b = rng.standard_normal((B, 1, 5, 1)).astype(np.float32)
+    u0 = (a * np.cos(k[:, None] * x) + b * np.sin(k[:, None] * x)).sum(axis=2)
+    u0 = (u0 / np.abs(u0).max(axis=-1, keepdims=True)).astype(np.float32)
+    st = ex.stepper.Burgers(1, L, N, dt, diffusivity=0.1)
+    ost = ox.Burgers(1, L, N, dt, diffusivity=0.1)
+    trj = ex.vmap(ex.rollout(st, T))(dev(u0))
+    assert tuple(trj.shape) == (B, T, 1, N)
+    pick = np.concatenate([[0, 1, B - 2, B - 1], rng.integers(2, B - 2, size=4)])
+    sel = host(trj[torch.as_tensor(pick, device="cuda")])
+    assert bool(torch.isfinite(trj[:, -1]).all())
+    del trj
+    ref = per_sample(ox.rollout(ost, T), u0[pick])
+    assert rel(sel[:, 0], ref[:, 0]) < F32_STEP
+    assert rel(sel[:, 99], ref[:, 99]) < ROLLOUT_100
+    assert rel(sel[:, -1], ref[:, -1]) < 1e-3
+
+
+@pytest.mark.parametrize("name,D,N,C,order,L", [
+    ("KolmogorovFlowVorticity", 2, 128, 1, 2, 2 * np.pi), ("KolmogorovFlowVorticity", 2, 128, 1, 4, 2 * np.pi),
+    ("KolmogorovFlowVorticity", 2, 24, 1, 3, 2 * np.pi), ("KuramotoSivashinsky", 2, 128, 1, 1, 200.0),
+    ("NavierStokesVelocity", 3, 128, 3, 2, 2 * np.pi), ("NavierStokesVelocity", 3, 12, 3, 4, 2 * np.pi),
+    ("KolmogorovFlowVelocity", 3, 128, 3, 3, 2 * np.pi)])
+def test_full_spectrum_state_masked_modes(name, D, N, C, order, L):
+    """White-noise state: every mode, including the dealiased ones and the Nyquist lines, carries energy.  The
+    dealiased modes take the closed-form update exp(dt L) u (N(u) is masked to 0 there, nonlin_fun/_base.py:99-115);
+    fast (N = 128) and generic (N = 12 / 24) kernels, all ETDRK orders, step + in-place sub-stepped rollout."""
+    dt = 0.002
+    rng = np.random.default_rng(N * 10 + order)
+    u0 = (0.1 * rng.standard_normal((2, C) + (N,) * D)).astype(np.float32)
+    st = getattr(ex.stepper, name)(D, L, N, dt, order=order)
+    ost = getattr(ox, name)(D, L, N, dt, order=order)
+    got = host(ex.vmap(st)(dev(u0)))
+    ref = per_sample(ost, u0)
+    assert rel(got, ref) < F32_STEP, rel(got, ref)
+    gh, rh = ox.fft(got, num_spatial_dims=D), ox.fft(ref, num_spatial_dims=D)
+    hi = ~np.broadcast_to(ox.low_pass_filter_mask(D, N, cutoff=(2 / 3) * (N // 2) - 1), gh.shape)
+    assert np.linalg.norm(gh[hi] - rh[hi]) / np.linalg.norm(rh[hi]) < F32_STEP
+    got3 = host(ex.vmap(ex.repeat(ex.RepeatedStepper(st, 3), 1))(dev(u0)))
+    ref3 = per_sample(ox.repeat(ost, 3), u0)
+    assert rel(got3, ref3) < 5e-5, rel(got3, ref3)
 
 
 # ------------------------------------------------------------------ slab-decomposed path (c5)
