@@ -28,9 +28,9 @@ template <class T, int DIR> __device__ __forceinline__ void dft3(cpx<T>* v) {
   const T c = (T)-0.5, s = (T)0.86602540378443864676;
   cpx<T> t1 = v[1] + v[2];
   cpx<T> t2 = v[1] - v[2];
-  cpx<T> m = cpx<T>(v[0].x + c * t1.x, v[0].y + c * t1.y);
+  cpx<T> m = axpy(c, t1, v[0]);
   // forward: X1 = m - i*s*t2 ; X2 = m + i*s*t2
-  cpx<T> r = rot90<T, DIR>(cpx<T>(s * t2.x, s * t2.y));
+  cpx<T> r = rot90<T, DIR>(s * t2);
   v[0] = v[0] + t1;
   v[1] = m + r;
   v[2] = m - r;
@@ -51,10 +51,10 @@ template <class T, int DIR> __device__ __forceinline__ void dft5(cpx<T>* v) {
   const T s1 = (T)0.95105651629515357212, s2 = (T)0.58778525229247312917;
   cpx<T> a1 = v[1] + v[4], b1 = v[1] - v[4];
   cpx<T> a2 = v[2] + v[3], b2 = v[2] - v[3];
-  cpx<T> m1 = cpx<T>(v[0].x + c1 * a1.x + c2 * a2.x, v[0].y + c1 * a1.y + c2 * a2.y);
-  cpx<T> m2 = cpx<T>(v[0].x + c2 * a1.x + c1 * a2.x, v[0].y + c2 * a1.y + c1 * a2.y);
-  cpx<T> n1 = rot90<T, DIR>(cpx<T>(s1 * b1.x + s2 * b2.x, s1 * b1.y + s2 * b2.y));
-  cpx<T> n2 = rot90<T, DIR>(cpx<T>(s2 * b1.x - s1 * b2.x, s2 * b1.y - s1 * b2.y));
+  cpx<T> m1 = axpy(c2, a2, axpy(c1, a1, v[0]));
+  cpx<T> m2 = axpy(c1, a2, axpy(c2, a1, v[0]));
+  cpx<T> n1 = rot90<T, DIR>(axpy(s2, b2, s1 * b1));
+  cpx<T> n2 = rot90<T, DIR>(axpy(-s1, b2, s2 * b1));
   v[0] = v[0] + a1 + a2;
   v[1] = m1 + n1;
   v[4] = m1 - n1;
@@ -72,11 +72,12 @@ template <class T, int DIR> __device__ __forceinline__ void dft8(cpx<T>* v) {
     a[i + 4] = v[i] - v[i + 4];
   }
   // twiddles on the lower half: w8^i, i=0..3 (forward: exp(-i*pi*i/4))
-  a[5] = DIR < 0 ? cpx<T>(h * (a[5].x + a[5].y), h * (a[5].y - a[5].x))
-                 : cpx<T>(h * (a[5].x - a[5].y), h * (a[5].y + a[5].x));
+  //   a5 * w8   = h (a5 + rot90(a5)),   a7 * w8^3 = -h (a7 - rot90(a7))      (rot90 = * -i forward, * +i inverse)
+  // written with whole-complex operators: for T = float each line is one packed add (the rotation is an operand
+  // modifier of FADD2) + one packed multiply
+  a[5] = h * (a[5] + rot90<T, DIR>(a[5]));
   a[6] = rot90<T, DIR>(a[6]);
-  a[7] = DIR < 0 ? cpx<T>(h * (a[7].y - a[7].x), h * (-a[7].x - a[7].y))
-                 : cpx<T>(h * (-a[7].x - a[7].y), h * (a[7].x - a[7].y));
+  a[7] = (-h) * (a[7] - rot90<T, DIR>(a[7]));
   cpx<T> b[8];
   b[0] = a[0] + a[2];
   b[2] = a[0] - a[2];

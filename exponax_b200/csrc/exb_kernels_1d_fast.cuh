@@ -45,9 +45,8 @@ template <int DIR> __device__ __forceinline__ void dft16_reg(cpx<float>* v) {
     v[n1 + 12] = t[3];
   }
   // twiddles w16^(n1*k2) on v[n1 + 4*k2]; forward twiddle = (wr, -wi)
-#define EXB_MULW(a, wr, wi)                                                            \
-  a = DIR < 0 ? cpx<float>(a.x * (wr) + a.y * (wi), a.y * (wr) - a.x * (wi))           \
-              : cpx<float>(a.x * (wr) - a.y * (wi), a.y * (wr) + a.x * (wi))
+  // (a complex product with a compile-time constant: two packed instructions with immediate operands)
+#define EXB_MULW(a, wr, wi) a = a * (DIR < 0 ? cpx<float>((wr), -(wi)) : cpx<float>((wr), (wi)))
   EXB_MULW(v[1 + 4], c, s);     // w^1
   EXB_MULW(v[2 + 4], h, h);     // w^2
   EXB_MULW(v[3 + 4], s, c);     // w^3
@@ -152,8 +151,8 @@ template <int R, class S, int NINV, int NFWD> struct Fast1d {
   template <int KINDN>  // 0: k = n < N/2 (direct), 1: DC or Nyquist, 2: upper (conjugate of mode N - n)
   static __device__ __forceinline__ cpx<float> pack(cpx<float> F1, cpx<float> F2) {
     if (KINDN == 1) return cpx<float>(F1.x, F2.x);                 // irfft drops these imaginary parts
-    if (KINDN == 0) return cpx<float>(F1.x - F2.y, F1.y + F2.x);   // F1 + i F2
-    return cpx<float>(F1.x + F2.y, F2.x - F1.y);                   // conj(F1) + i conj(F2)
+    if (KINDN == 0) return F1 + mul_i(F2);                         // F1 + i F2        (one packed add each:
+    return conj(F1) + mul_i(conj(F2));                             // conj(F1) + i conj(F2)   swaps / signs are operand modifiers)
   }
 
   // Build the packed inverse lines from spectral state `src`.  NLF: apply the nonlinear
@@ -198,8 +197,8 @@ template <int R, class S, int NINV, int NFWD> struct Fast1d {
       const int pidx = (j == 0) ? (R + 1) * (R - r) : (R - j) + (R + 1) * (R - 1 - r);
       cpx<float> zk = v[r];
       cpx<float> zp = (r == 0 && j == 0) ? zk : xb[pidx];
-      X1[r] = cpx<float>(0.5f * (zk.x + zp.x), 0.5f * (zk.y - zp.y));
-      X2[r] = cpx<float>(0.5f * (zk.y + zp.y), -0.5f * (zk.x - zp.x));
+      X1[r] = 0.5f * (zk + conj(zp));              // ( zk + conj(zp)) / 2
+      X2[r] = mul_mi(0.5f * (zk - conj(zp)));      // (zk - conj(zp)) / (2 i)
     }
     X1[R / 2] = cpx<float>(v[R / 2].x, 0.f);  // Nyquist (meaningful for j == 0)
     X2[R / 2] = cpx<float>(v[R / 2].y, 0.f);
@@ -216,16 +215,13 @@ template <int R, class S, int NINV, int NFWD> struct Fast1d {
       for (int f = 0; f < NINV; ++f) fft_reg<R, +1>(z[f], xb, j, tw2);
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        float i1[NINV], i2[NINV], o1[NFWD], o2[NFWD];
+        // the two lanes of a packed line value are the same grid point of the two trajectories
+        f32x2 iv[NINV], ov[NFWD];
 #pragma unroll
-        for (int f = 0; f < NINV; ++f) {
-          i1[f] = z[f][r].x * P.inv_norm;
-          i2[f] = z[f][r].y * P.inv_norm;
-        }
-        nl_pointwise<float, S>(P, i1, o1);
-        nl_pointwise<float, S>(P, i2, o2);
+        for (int f = 0; f < NINV; ++f) iv[f] = lanes(P.inv_norm * z[f][r]);
+        nl_pointwise<float, S, f32x2>(P, iv, ov);
 #pragma unroll
-        for (int g = 0; g < NFWD; ++g) w[g][r] = cpx<float>(o1[g], o2[g]);
+        for (int g = 0; g < NFWD; ++g) w[g][r] = as_cpx(ov[g]);
       }
     }
     cpx<float> W1[NFWD][NOWN], W2[NFWD][NOWN];
@@ -456,7 +452,7 @@ __global__ void __launch_bounds__(256, 2) k1d_fast_kernel(const K1dParams<float>
       if (last) break;
       if (!spectral_carry) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) z[0][r] = cpx<float>(z[0][r].x * invN, z[0][r].y * invN);
+        for (int r = 0; r < R; ++r) z[0][r] = invN * z[0][r];
         to_state(z[0]);
         continue;
       }

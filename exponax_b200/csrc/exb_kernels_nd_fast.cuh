@@ -378,8 +378,8 @@ row_fast_kernel(const RowParams<float> p) {
       const int k = j + P * q;
       cpx<float> zk = v[q];
       cpx<float> zp = (k == 0) ? zk : ex.ld(N - k);
-      if (has1 && k <= kout) o1[k] = cpx<float>(0.5f * (zk.x + zp.x), 0.5f * (zk.y - zp.y));
-      if (has2 && k <= kout) o2[k] = cpx<float>(0.5f * (zk.y + zp.y), -0.5f * (zk.x - zp.x));
+      if (has1 && k <= kout) o1[k] = 0.5f * (zk + conj(zp));
+      if (has2 && k <= kout) o2[k] = mul_mi(0.5f * (zk - conj(zp)));
     }
     if (j == 0 && N / 2 <= kout) {
       if (has1) o1[N / 2] = cpx<float>(v[4].x, 0.f);
@@ -397,8 +397,8 @@ row_fast_kernel(const RowParams<float> p) {
       cpx<float> F2 = (has2 && k <= kin) ? i2p[k] : zero;
       cpx<float> z;
       if (k == 0 || 2 * k == N) z = cpx<float>(F1.x, F2.x);
-      else if (!upper) z = cpx<float>(F1.x - F2.y, F1.y + F2.x);
-      else z = cpx<float>(F1.x + F2.y, F2.x - F1.y);
+      else if (!upper) z = F1 + mul_i(F2);
+      else z = conj(F1) + mul_i(conj(F2));
       v[q] = z;
     }
   };
@@ -470,8 +470,8 @@ row_fast_kernel(const RowParams<float> p) {
           cpx<float> F2 = (has2 && k <= kin) ? stage[NHP + k] : zero;
           cpx<float> zz;
           if (k == 0 || 2 * k == N) zz = cpx<float>(F1.x, F2.x);
-          else if (!upper) zz = cpx<float>(F1.x - F2.y, F1.y + F2.x);
-          else zz = cpx<float>(F1.x + F2.y, F2.x - F1.y);
+          else if (!upper) zz = F1 + mul_i(F2);
+          else zz = conj(F1) + mul_i(conj(F2));
           z[q] = zz;
         }
         ex.sync();
@@ -482,11 +482,10 @@ row_fast_kernel(const RowParams<float> p) {
       fft8_run<N, +1>(z, ex, j, tw);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const cpx<float> a(z[q].x * Pn.inv_norm, z[q].y * Pn.inv_norm);  // (row r1, row r2) at point j + P*q
+        const cpx<float> a = Pn.inv_norm * z[q];  // (row r1, row r2) at point j + P*q
         auto pk = [&](int g) { return park[(g * 8 + q) * P]; };
-        auto acc = [&](int gg, cpx<float> s, float sign) {
-          wl[gg][q].x = fmaf(sign * s.x, a.x, wl[gg][q].x);
-          wl[gg][q].y = fmaf(sign * s.y, a.y, wl[gg][q].y);
+        auto acc = [&](int gg, cpx<float> s, float sign) {  // lane-wise (+-s) * a + wl: one packed FMA
+          wl[gg][q] = lane_fma(sign < 0.f ? -s : s, a, wl[gg][q]);
         };
         if (f < KST) {
           park[(f * 8 + q) * P] = a;
@@ -515,17 +514,12 @@ row_fast_kernel(const RowParams<float> p) {
     }
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      float a1[NINV], a2[NINV], o1[NFWD], o2[NFWD];
+      f32x2 iv[NINV], ov[NFWD];
 #pragma unroll
-      for (int f = 0; f < NINV; ++f) {
-        cpx<float> zz = stash[(size_t)f * N + j + P * q];
-        a1[f] = zz.x * Pn.inv_norm;
-        a2[f] = zz.y * Pn.inv_norm;
-      }
-      nl_pointwise<float, S>(Pn, a1, o1);
-      nl_pointwise<float, S>(Pn, a2, o2);
+      for (int f = 0; f < NINV; ++f) iv[f] = lanes(Pn.inv_norm * stash[(size_t)f * N + j + P * q]);
+      nl_pointwise<float, S, f32x2>(Pn, iv, ov);
 #pragma unroll
-      for (int gg = 0; gg < NFWD; ++gg) wl[gg][q] = cpx<float>(o1[gg], o2[gg]);
+      for (int gg = 0; gg < NFWD; ++gg) wl[gg][q] = as_cpx(ov[gg]);
     }
   } else {
     cpx<float> z[NINV][8];
@@ -553,8 +547,8 @@ row_fast_kernel(const RowParams<float> p) {
           cpx<float> F2 = (has2 && k <= kin) ? stage[NHP + k] : zero;
           cpx<float> zz;
           if (k == 0 || 2 * k == N) zz = cpx<float>(F1.x, F2.x);
-          else if (!upper) zz = cpx<float>(F1.x - F2.y, F1.y + F2.x);
-          else zz = cpx<float>(F1.x + F2.y, F2.x - F1.y);
+          else if (!upper) zz = F1 + mul_i(F2);
+          else zz = conj(F1) + mul_i(conj(F2));
           z[f][q] = zz;
         }
         ex.sync();  // staging buffer consumed
@@ -570,16 +564,12 @@ row_fast_kernel(const RowParams<float> p) {
     }
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      float a1[NINV], a2[NINV], o1[NFWD], o2[NFWD];
+      f32x2 iv[NINV], ov[NFWD];   // the two lanes = the same grid point of rows r1 and r2
 #pragma unroll
-      for (int f = 0; f < NINV; ++f) {
-        a1[f] = z[f][q].x * Pn.inv_norm;
-        a2[f] = z[f][q].y * Pn.inv_norm;
-      }
-      nl_pointwise<float, S>(Pn, a1, o1);
-      nl_pointwise<float, S>(Pn, a2, o2);
+      for (int f = 0; f < NINV; ++f) iv[f] = lanes(Pn.inv_norm * z[f][q]);
+      nl_pointwise<float, S, f32x2>(Pn, iv, ov);
 #pragma unroll
-      for (int gg = 0; gg < NFWD; ++gg) wl[gg][q] = cpx<float>(o1[gg], o2[gg]);
+      for (int gg = 0; gg < NFWD; ++gg) wl[gg][q] = as_cpx(ov[gg]);
     }
   }
 #pragma unroll

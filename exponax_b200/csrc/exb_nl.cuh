@@ -125,9 +125,10 @@ __device__ __forceinline__ cpx<T> nl_inv_field(const NlParams<T>& P, int f, cons
 
 // ---- pointwise products in physical space ----------------------------------------------------
 // in[f]: the n_inv inverse-transformed fields at one grid point (already scaled by 1/N^D);
-// out[g]: the n_fwd fields to be forward-transformed.
-template <class T, class S = NlDyn>
-__device__ __forceinline__ void nl_pointwise(const NlParams<T>& P, const T* in, T* out) {
+// out[g]: the n_fwd fields to be forward-transformed.  V = T (one grid point) or f32x2 (the same grid point of
+// the two rows / trajectories that share a two-for-one line: every operation is one packed instruction).
+template <class T, class S = NlDyn, class V = T>
+__device__ __forceinline__ void nl_pointwise(const NlParams<T>& P, const V* in, V* out) {
   const int C = EXB_S_C, D = EXB_S_D;
   switch (EXB_S_KIND) {
     case EXB_NL_CONVECTION: {
@@ -144,19 +145,19 @@ __device__ __forceinline__ void nl_pointwise(const NlParams<T>& P, const T* in, 
               if (c < C && d < C) out[c * C + d] = in[c] * in[d];
         }
       } else if (EXB_S_SINGLE) {
-        T s = (T)0;
+        V s = in[0] * in[1];
 #pragma unroll
-        for (int d = 0; d < 3; ++d)
-          if (d < D) s += in[0] * in[1 + d];
+        for (int d = 1; d < 3; ++d)
+          if (d < D) s = vfma(in[0], in[1 + d], s);
         out[0] = s;
       } else {
 #pragma unroll
         for (int c = 0; c < EXB_MAXC; ++c) {
           if (c < C) {
-            T s = (T)0;
+            V s = in[0] * in[C + c * D];
 #pragma unroll
-            for (int d = 0; d < 3; ++d)
-              if (d < D) s += in[d] * in[C + c * D + d];
+            for (int d = 1; d < 3; ++d)
+              if (d < D) s = vfma(in[d], in[C + c * D + d], s);
             out[c] = s;
           }
         }
@@ -167,10 +168,10 @@ __device__ __forceinline__ void nl_pointwise(const NlParams<T>& P, const T* in, 
 #pragma unroll
       for (int c = 0; c < EXB_MAXC; ++c) {
         if (c < C) {
-          T s = (T)0;
+          V s = in[c * D] * in[c * D];
 #pragma unroll
-          for (int d = 0; d < 3; ++d)
-            if (d < D) s += in[c * D + d] * in[c * D + d];
+          for (int d = 1; d < 3; ++d)
+            if (d < D) s = vfma(in[c * D + d], in[c * D + d], s);
           out[c] = s;
         }
       }
@@ -180,10 +181,10 @@ __device__ __forceinline__ void nl_pointwise(const NlParams<T>& P, const T* in, 
 #pragma unroll
       for (int c = 0; c < EXB_MAXC; ++c) {
         if (c < C) {
-          T u = in[c], pw = (T)1, acc = (T)0;
+          V u = in[c], pw = V((T)1), acc = V((T)0);
           for (int k = 0; k < P.n_poly; ++k) {  // (_polynomial.py:69-73)
-            acc += P.poly[k] * pw;
-            pw *= u;
+            acc = vfma(V(P.poly[k]), pw, acc);
+            pw = pw * u;
           }
           out[c] = acc;
         }
@@ -191,12 +192,12 @@ __device__ __forceinline__ void nl_pointwise(const NlParams<T>& P, const T* in, 
       break;
     }
     case EXB_NL_VORTICITY_2D:
-      out[0] = in[0] * in[2] + in[1] * in[3];
+      out[0] = vfma(in[1], in[3], in[0] * in[2]);
       break;
     case EXB_NL_GRAY_SCOTT: {  // feed = gen[0], kill = gen[1]   (_gray_scott.py:36-43)
-      T uvv = in[0] * (in[1] * in[1]);
-      out[0] = P.gen[0] * ((T)1 - in[0]) - uvv;
-      out[1] = -(P.gen[0] + P.gen[1]) * in[1] + uvv;
+      V uvv = in[0] * (in[1] * in[1]);
+      out[0] = V(P.gen[0]) * (V((T)1) - in[0]) - uvv;
+      out[1] = vfma(V(-(P.gen[0] + P.gen[1])), in[1], uvv);
       break;
     }
     case EXB_NL_CAHN_HILLIARD:  // (_cahn_hilliard.py:33)
@@ -204,9 +205,9 @@ __device__ __forceinline__ void nl_pointwise(const NlParams<T>& P, const T* in, 
       break;
     case EXB_NL_PROJECTED_3D: {
       // convection = velocity x curl   (in[0..2] = curl, in[3..5] = velocity)
-      out[0] = in[4] * in[2] - in[5] * in[1];
-      out[1] = in[5] * in[0] - in[3] * in[2];
-      out[2] = in[3] * in[1] - in[4] * in[0];
+      out[0] = vfma(in[4], in[2], -(in[5] * in[1]));
+      out[1] = vfma(in[5], in[0], -(in[3] * in[2]));
+      out[2] = vfma(in[3], in[1], -(in[4] * in[0]));
       break;
     }
     case EXB_NL_GENERAL: {
@@ -214,10 +215,10 @@ __device__ __forceinline__ void nl_pointwise(const NlParams<T>& P, const T* in, 
       for (int c = 0; c < EXB_MAXC; ++c) {
         if (c < C) {
           out[c] = in[c] * in[c];
-          T s = (T)0;
+          V s = in[C + c * D] * in[C + c * D];
 #pragma unroll
-          for (int d = 0; d < 3; ++d)
-            if (d < D) s += in[C + c * D + d] * in[C + c * D + d];
+          for (int d = 1; d < 3; ++d)
+            if (d < D) s = vfma(in[C + c * D + d], in[C + c * D + d], s);
           out[C + c] = s;
         }
       }
