@@ -270,8 +270,16 @@ template <class T> struct PlanImpl : exb_plan {
         long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)j / (long double)N;
         tw[j] = cpx<T>((T)cosl(a), (T)sinl(a));
       }
+      if constexpr (std::is_same<T, float>::value) {
+        // register-FFT kernels: their per-pass table, already arranged, right behind the roots (Fft8Tw<N>::fill)
+        const int extra = D >= 2 ? exb_fastnd_tw_size(N) : 0;
+        if (extra > 0) {
+          tw.resize(N + extra);
+          exb_fastnd_tw_arrange(N, tw.data(), tw.data() + N);
+        }
+      }
       twiddle_host_tmp = tw.data();
-      int rc = upload(tw.data(), sizeof(cpx<T>) * N, (void**)&d_tw);
+      int rc = upload(tw.data(), sizeof(cpx<T>) * tw.size(), (void**)&d_tw);
       twiddle_host_tmp = nullptr;
       if (rc) return rc;
     }

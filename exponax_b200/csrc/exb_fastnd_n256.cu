@@ -17,6 +17,29 @@ int exb_fastnd_row_n1024(cudaStream_t st, const RowParams<float>& p, const char*
 int exb_fastnd_col_n2048(cudaStream_t st, const ColParams<float>& p, int dir, long long grid, const char** err);
 int exb_fastnd_row_n2048(cudaStream_t st, const RowParams<float>& p, const char** err);
 
+template <int N> static void tw_arrange_t(const cpx<float>* roots, cpx<float>* out) {
+  for (int q = 0; q < Fft8Tw<N>::SIZE; ++q) out[q] = roots[Fft8Tw<N>::root_index(q)];
+}
+int exb_fastnd_tw_size(int N) {
+  switch (N) {
+    case 128: return Fft8Tw<128>::SIZE;
+    case 256: return Fft8Tw<256>::SIZE;
+    case 512: return Fft8Tw<512>::SIZE;
+    case 1024: return Fft8Tw<1024>::SIZE;
+    case 2048: return Fft8Tw<2048>::SIZE;
+  }
+  return 0;
+}
+void exb_fastnd_tw_arrange(int N, const cpx<float>* roots, cpx<float>* out) {
+  switch (N) {
+    case 128: return tw_arrange_t<128>(roots, out);
+    case 256: return tw_arrange_t<256>(roots, out);
+    case 512: return tw_arrange_t<512>(roots, out);
+    case 1024: return tw_arrange_t<1024>(roots, out);
+    case 2048: return tw_arrange_t<2048>(roots, out);
+  }
+}
+
 bool exb_fastnd_supported(int D, int N, const NlParams<float>& P) {
   const int fk = fast_kind_of(P);
   if (fk == 0) return false;

@@ -35,20 +35,18 @@ template <int N> struct Fft8Tw {
   static constexpr int T4 = T3 + N3;
   static constexpr int N4 = Cfg::NP == 4 ? (Cfg::RL - 1) * 512 : 0;
   static constexpr int SIZE = T4 + N4;
-  // roots: the N-th roots of unity exp(-2 pi i j / N) in global memory
+  // index into the N-th roots of unity exp(-2 pi i j / N) of table entry q
+  static __host__ __device__ constexpr int root_index(int q) {
+    return q < T3   ? (N / 64) * (q % 8) * (q / 8 + 1)
+           : q < T4 ? (Cfg::NP == 4 ? (N / 512) : 1) * ((q - T3) % 64) * ((q - T3) / 64 + 1)
+                    : ((q - T4) % 512) * ((q - T4) / 512 + 1);
+  }
+  // The plan uploads the table ALREADY ARRANGED right behind the N roots (exb_fastnd_tw_arrange), so a CTA fills its
+  // shared-memory copy with one coalesced pass -- the former per-CTA gather (index arithmetic + scattered loads)
+  // was 5 % of the instructions of a column-pass CTA (ncu r01j, exb_fft8.cuh:40-46).
   static __device__ __forceinline__ void fill(cpx<float>* t, const cpx<float>* __restrict__ roots) {
-    for (int q = threadIdx.x; q < SIZE; q += blockDim.x) {
-      if (q < T3) {
-        int r = q / 8 + 1, k = q % 8;
-        t[q] = roots[(N / 64) * k * r];
-      } else if (q < T4) {
-        int r = (q - T3) / 64 + 1, b = (q - T3) % 64;
-        t[q] = roots[(Cfg::NP == 4 ? (N / 512) : 1) * b * r];
-      } else {
-        int r = (q - T4) / 512 + 1, b = (q - T4) % 512;
-        t[q] = roots[b * r];
-      }
-    }
+    const cpx<float>* __restrict__ arranged = roots + N;
+    for (int q = threadIdx.x; q < SIZE; q += blockDim.x) t[q] = arranged[q];
   }
 };
 

@@ -59,7 +59,14 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------- column pass
-template <int N, int TW, class S, int NFWD, int MODE, int DIR>
+// Index bookkeeping is the expensive part of these kernels (ncu r01j: 50-60 % of the executed instructions of a
+// column pass were integer / address / control, the butterflies 20-35 %), so everything that does not depend on
+// the line entry is computed once per thread: 32-bit block decoding, a per-thread bit mask of the line entries
+// inside the dealiasing mask, base pointers + a constant entry stride (P * line_stride elements between the 8
+// entries of a thread), the wavenumber factors of the fixed axes.  ETDRK2 (the default order) gets its two stage
+// updates as compile-time variants (STG) so that the operand pointers are not re-read per mode.
+//   STG: 0 = order / stage at run time;  1 = ETDRK2 stage 0;  2 = ETDRK2 stage 1 (last)
+template <int N, int TW, class S, int NFWD, int MODE, int DIR, int STG = 0>
 __global__ void __launch_bounds__((N / 8) * TW, (MODE == COL_PLAIN ? 2048 / ((N / 8) * TW)
                                                  : (MODE == COL_INV_PRO ? 2 : (NFWD == 1 ? 3 : EXB_EPI_MULTI_MINBLOCKS))))
 col_fast_kernel(const ColParams<float> p) {
@@ -69,126 +76,183 @@ col_fast_kernel(const ColParams<float> p) {
   cpx<float>* tile = tw + Fft8Tw<N>::SIZE;
   Fft8Tw<N>::fill(tw, p.tw);
   const int w = threadIdx.x % TW, j = threadIdx.x / TW;
-  const long long ntiles = (p.inner + TW - 1) / TW;
-  long long bid = blockIdx.x;
-  // COL_FWD_EPI: the trajectory is the FASTEST block index, so the CTAs that run together read the same tile of
-  // the coefficient tables (3-D: E + c1 + c2 = 135 MB at 256^3, more than the L2 holds) once from HBM and
-  // batch - 1 times from L2 instead of re-streaming them per trajectory
-  // (only when the tables do not fit the L2 -- p.batch_fastest, set by the host: with L2-resident tables the
-  //  tile-fastest order is better, neighbouring CTAs then complete each other's DRAM pages / 128-byte lines:
-  //  c3 lost 10 % with the trajectory-fastest order, r02a)
+  const unsigned inner = (unsigned)p.inner;
+  const unsigned ntiles = (inner + TW - 1) / TW;
+  // COL_FWD_EPI: the trajectory is the FASTEST block index when the coefficient tables do not fit the L2
+  // (p.batch_fastest, set by the host: 3-D, E + c1 + c2 = 135 MB at 256^3): the CTAs that run together then read the
+  // same tile of the tables once from HBM and batch - 1 times from L2.  With L2-resident tables the tile-fastest
+  // order is better, neighbouring CTAs complete each other's DRAM pages (c3 lost 10 % the other way, r02a).
   const bool batch_fastest = (MODE == COL_FWD_EPI) && EXB_EPI_BATCH_FASTEST && p.batch_fastest;
-  const long long t = batch_fastest ? bid / p.batch : bid % ntiles;
-  bid = batch_fastest ? bid % p.batch : bid / ntiles;
-  const long long w0 = t * TW;
-  const bool act = w0 + w < p.inner;
+  const unsigned nb = (unsigned)p.batch;
+  const unsigned t = batch_fastest ? blockIdx.x / nb : blockIdx.x % ntiles;
+  const unsigned rest = batch_fastest ? blockIdx.x % nb : blockIdx.x / ntiles;
+  const unsigned w0 = t * TW;
+  const unsigned iw = w0 + w;
+  const bool act = iw < inner;
   const cpx<float> zero(0.f, 0.f);
   ExTile<TW> ex{tile + w};
   const long long ls = p.line_stride;
   const int kmax = p.P.kmax;
-  const bool prune_rows_in = (p.prune & PRUNE_IN_ROWS) && kmax >= 0;
-  const bool prune_rows_out = (p.prune & PRUNE_OUT_ROWS) && kmax >= 0;
-  // is entry i of a line inside the dealiasing mask (lines run along a full, fftfreq-ordered axis)
-  auto row_keep = [&](int i) {
-    int k = wavenumber_of(i, N);
-    return (k < 0 ? -k : k) <= kmax;
-  };
-  // are the fixed wavenumbers of this thread's column inside the mask
-  bool col_keep = act;
-  if ((p.prune & PRUNE_COLS) && kmax >= 0 && act) {
-    const long long iwc = w0 + w;
-    if (p.inner == p.P.Nh) {            // 2-D axis 0 or 3-D axis 1: inner index = last-axis wavenumber
-      col_keep = iwc <= kmax;
-    } else {                            // 3-D axis 0: inner = (i1, i2)
-      int a1 = (int)(iwc / p.P.Nh), a2 = (int)(iwc - (long long)a1 * p.P.Nh);
-      int k1 = wavenumber_of(a1 + p.P.i1_off, N);
-      col_keep = (k1 < 0 ? -k1 : k1) <= kmax && a2 <= kmax;
+  // bit q: entry i = j + P*q of a (full, fftfreq-ordered) line is inside the dealiasing mask:  q < 4 -> k = i,
+  // q >= 4 -> k = i - N  (i = N/2 is k = -N/2, always outside)
+  unsigned rowmask = 0xffu;
+  if (kmax >= 0) {
+    rowmask = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int ak = q < 4 ? j + P * q : N - (j + P * q);
+      rowmask |= (ak <= kmax ? 1u : 0u) << q;
     }
   }
+  // the fixed indices of this thread's column: 2-D axis 0 / 3-D axis 1: inner = last-axis wavenumber;
+  // 3-D axis 0: inner = (i1, i2)
+  const bool flat3 = inner != (unsigned)p.P.Nh;
+  int i1 = (int)iw, i2 = 0;
+  if (flat3) {
+    i1 = (int)(iw / (unsigned)p.P.Nh);
+    i2 = (int)(iw - (unsigned)i1 * (unsigned)p.P.Nh);
+    i1 += p.P.i1_off;
+  }
+  const int k1 = flat3 ? wavenumber_of(i1, N) : i1;  // (2-D: the last-axis index is the wavenumber)
+  const bool col_in_mask = kmax < 0 || ((k1 < 0 ? -k1 : k1) <= kmax && i2 <= kmax);
+  // are the fixed wavenumbers of this thread's column inside the mask (pruned passes only)
+  const bool col_keep = act && (!((p.prune & PRUNE_COLS) && kmax >= 0) || col_in_mask);
   __syncthreads();
   const bool any_keep = __syncthreads_or(col_keep);
+  const size_t qstride = (size_t)P * (size_t)ls;  // elements between the entries q and q + 1 of this thread
 
   if (MODE == COL_PLAIN) {
-    const long long o = bid % p.n_outer;
-    bid /= p.n_outer;
-    const size_t base = (size_t)bid * p.M + (size_t)o * p.outer_stride + w0 + w;
+    const unsigned n_outer = (unsigned)p.n_outer;
+    const unsigned o = rest % n_outer, fb = rest / n_outer;
     if (!any_keep) return;
-    // line entry i -> element offset (segmented lines: the slab all-to-all buffers are used in place)
-    auto line_off = [&](int i) -> size_t {
-      if (p.seg_len > 0) return (size_t)(i / p.seg_len) * p.seg_stride + (size_t)(i % p.seg_len) * ls;
-      return (size_t)i * ls;
-    };
+    const size_t base = (size_t)fb * p.M + (size_t)o * p.outer_stride + iw;
+    const unsigned in_mask = col_keep ? (((p.prune & PRUNE_IN_ROWS) && kmax >= 0) ? rowmask : 0xffu) : 0u;
+    const unsigned out_mask = col_keep ? (((p.prune & PRUNE_OUT_ROWS) && kmax >= 0) ? rowmask : 0xffu) : 0u;
     cpx<float> v[8];
+    if (p.seg_len > 0) {
+      // segmented lines: the slab all-to-all buffers are used in place (entry i at (i / n) * seg_stride + (i % n) * ls)
+      auto line_off = [&](int i) -> size_t { return (size_t)(i / p.seg_len) * p.seg_stride + (size_t)(i % p.seg_len) * ls; };
 #pragma unroll
-    for (int q = 0; q < 8; ++q)
-      v[q] = (col_keep && (!prune_rows_in || row_keep(j + P * q))) ? p.in[base + line_off(j + P * q)] : zero;
-    fft8_run<N, DIR>(v, ex, j, tw);
-    if (col_keep) {
+      for (int q = 0; q < 8; ++q) v[q] = ((in_mask >> q) & 1u) ? p.in[base + line_off(j + P * q)] : zero;
+      fft8_run<N, DIR>(v, ex, j, tw);
       if (p.peer) {  // the store is the transpose: segment r of the line lives on rank r
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const int i = j + P * q;
-          if (!prune_rows_out || row_keep(i))
-            p.peer_out[i / p.seg_len][base + p.peer_off + (size_t)(i % p.seg_len) * ls] = v[q];
+          if ((out_mask >> q) & 1u) p.peer_out[i / p.seg_len][base + p.peer_off + (size_t)(i % p.seg_len) * ls] = v[q];
         }
       } else {
 #pragma unroll
         for (int q = 0; q < 8; ++q)
-          if (!prune_rows_out || row_keep(j + P * q)) p.out[base + line_off(j + P * q)] = v[q];
+          if ((out_mask >> q) & 1u) p.out[base + line_off(j + P * q)] = v[q];
       }
+      return;
     }
+    const cpx<float>* __restrict__ src = p.in + base + (size_t)j * ls;
+    cpx<float>* __restrict__ dst = p.out + base + (size_t)j * ls;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = ((in_mask >> q) & 1u) ? src[q * qstride] : zero;
+    fft8_run<N, DIR>(v, ex, j, tw);
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      if ((out_mask >> q) & 1u) dst[q * qstride] = v[q];
     return;
   }
 
   const NlParams<float>& Pn = p.P;
   constexpr int C = S::C;
-  const long long b = bid;
-  const long long iw = w0 + w;
-  // spatial indices of this thread's 8 modes: axis-0 index i = j + P*q; the rest from iw
-  int i1 = (int)iw, i2 = 0;
-  if (S::D == 3) {
-    i1 = (int)(iw / Pn.Nh);
-    i2 = (int)(iw - (long long)i1 * Pn.Nh);
-    i1 += Pn.i1_off;
-  }
+  const unsigned b = rest;
+  // wavenumber factors: the derivative operator is i * kd  (_spectral.py:86-115: (2 pi / L) * k, rounded once)
+  const float kd1 = Pn.dscale * (float)k1;
+  const float kd2 = Pn.dscale * (float)i2;
+  auto kd0_of = [&](int q) { return Pn.dscale * (float)(j + P * q - (q >= 4 ? N : 0)); };
+  auto mode_of = [&](int q) {
+    ModeK<float> m;
+    m.kd[0] = kd0_of(q);
+    m.kd[1] = kd1;
+    m.kd[2] = S::D == 3 ? kd2 : 0.f;
+    m.keep = col_in_mask && ((rowmask >> q) & 1u);
+    m.is_inj = Pn.has_inj && (j + P * q) == Pn.inj_idx[0] && i1 == Pn.inj_idx[1] && (S::D < 3 || i2 == Pn.inj_idx[2]);
+    m.is_dc = q == 0 && j == 0 && k1 == 0 && i2 == 0;
+    return m;
+  };
 
   if (MODE == COL_INV_PRO) {
     if (!any_keep) return;  // every column of this tile is dealiased away: nothing is written,
                             // the consumers never read masked columns (PRUNE_* contract)
-    // the stage input is re-read for every field (L1/L2 hits: same thread, same addresses)
-    // instead of being held in registers across the field loop: keeps the kernel at <= 64
-    // registers, i.e. two 512-thread CTAs per SM
-    // (single-channel inputs are cheap enough to keep in registers: measured faster, r01g)
-    const cpx<float>* ubase = p.in + (size_t)b * C * p.M + iw;
+    const unsigned ld_mask = col_keep ? rowmask : 0u;   // pre-dealiasing: modes outside the mask enter as zeros
+    const cpx<float>* __restrict__ ubase = p.in + (size_t)b * C * p.M + iw + (size_t)j * ls;
     constexpr bool USM = (C == 1) && (EXB_INVPRO_SMEM_U != 0);
+    constexpr bool VORT = S::kind == EXB_NL_VORTICITY_2D && USM;
     constexpr int NT = P * TW;
     constexpr int TROWS = ExTile<TW>::PAD ? N + N / 8 : N;
+    // single-channel stage input: parked in a thread-private slice of shared memory across the field loop
+    // (the kernel is capped at 64 registers for two 512-thread CTAs per SM); vorticity also parks the stream
+    // function psi = w / laplacian, so the reciprocal is taken once per mode instead of once per field
     cpx<float>* ustash = tile + TROWS * TW + threadIdx.x;  // [q][thread], conflict-free
+    cpx<float>* pstash = ustash + 8 * NT;
     cpx<float> u0[USM ? 1 : 8];
     if (C == 1) {
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        cpx<float> t = (col_keep && (kmax < 0 || row_keep(j + P * q))) ? ubase[(size_t)(j + P * q) * ls] : zero;
-        if (USM) ustash[q * NT] = t;
-        else u0[q] = t;
+        const cpx<float> tq = ((ld_mask >> q) & 1u) ? ubase[q * qstride] : zero;
+        if (USM) ustash[q * NT] = tq;
+        else u0[q] = tq;
+        if (VORT) {  // (_vorticity_convection.py:70-82: laplacian = -(kd0^2 + kd1^2), its inverse := 1 at k = 0)
+          const float a = kd0_of(q);
+          const float lap = -(a * a) - (kd1 * kd1);
+          pstash[q * NT] = (lap == 0.f ? 1.f : exb_rcp(lap)) * tq;
+        }
       }
     }
     const int f_begin = p.fcount > 0 ? p.f0 : 0, f_end = p.fcount > 0 ? p.f0 + p.fcount : Pn.n_inv;
     for (int f = f_begin; f < f_end; ++f) {
       cpx<float> v[8];
+      if (VORT) {
+        // u = +d_y psi, v = -d_x psi, d_x w, d_y w: every field is  i * (+-kd) * (psi or w)
+        const cpx<float>* srcq = f < 2 ? pstash : ustash;
+        const bool use_k1 = f == 0 || f == 3;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const int i0 = j + P * q;
-        cpx<float> val = zero;
-        if (col_keep && (kmax < 0 || row_keep(i0))) {
-          ModeK<float> m = make_mode<float, S>(Pn, i0, i1, i2);
-          cpx<float> u[EXB_MAXC];
-#pragma unroll
-          for (int c = 0; c < EXB_MAXC; ++c)
-            u[c] = c < C ? (C == 1 ? (USM ? ustash[q * NT] : u0[USM ? 0 : q]) : ubase[(size_t)c * p.M + (size_t)i0 * ls]) : zero;
-          val = nl_inv_field<float, S>(Pn, f, u, m);
+        for (int q = 0; q < 8; ++q) {
+          float kd = use_k1 ? kd1 : kd0_of(q);
+          if (f == 1) kd = -kd;
+          v[q] = mul_i(kd * srcq[q * NT]);   // masked entries were parked as zeros
         }
-        v[q] = val;
+      } else if (S::kind == EXB_NL_PROJECTED_3D) {
+        // fields 0..2: curl_f = i (kd_a u_b - kd_b u_a), (a, b) = (f+1, f+2) mod 3; fields 3..5: velocity
+        const int ca = f >= 3 ? f - 3 : (f + 1) % 3, cb = (f + 2) % 3;
+        const cpx<float>* __restrict__ ua = ubase + (size_t)ca * p.M;
+        const cpx<float>* __restrict__ ub = ubase + (size_t)cb * p.M;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          cpx<float> val = zero;
+          if ((ld_mask >> q) & 1u) {
+            const cpx<float> xa = ua[q * qstride];
+            if (f >= 3) {
+              val = xa;
+            } else {
+              const cpx<float> xb = ub[q * qstride];
+              const float k0 = kd0_of(q);
+              const float ka = ca == 0 ? k0 : (ca == 1 ? kd1 : kd2), kb = cb == 0 ? k0 : (cb == 1 ? kd1 : kd2);
+              val = mul_i(ka * xb - kb * xa);
+            }
+          }
+          v[q] = val;
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          cpx<float> val = zero;
+          if ((ld_mask >> q) & 1u) {
+            ModeK<float> m = mode_of(q);
+            cpx<float> u[EXB_MAXC];
+#pragma unroll
+            for (int c = 0; c < EXB_MAXC; ++c)
+              u[c] = c < C ? (C == 1 ? (USM ? ustash[q * NT] : u0[USM ? 0 : q]) : ubase[(size_t)c * p.M + q * qstride]) : zero;
+            val = nl_inv_field<float, S>(Pn, f, u, m);
+          }
+          v[q] = val;
+        }
       }
       fft8_run<N, DIR>(v, ex, j, tw);
       if (col_keep) {
@@ -200,8 +264,9 @@ col_fast_kernel(const ColParams<float> p) {
             p.peer_out[i / p.seg_len][obase + p.peer_off + (size_t)(i % p.seg_len) * ls] = v[q];
           }
         } else {
+          cpx<float>* __restrict__ dst = p.out + obase + (size_t)j * ls;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) p.out[obase + (size_t)(j + P * q) * ls] = v[q];
+          for (int q = 0; q < 8; ++q) dst[q * qstride] = v[q];
         }
       }
     }
@@ -209,17 +274,6 @@ col_fast_kernel(const ColParams<float> p) {
   }
 
   // COL_FWD_EPI / COL_FWD_NL
-  if (MODE == COL_FWD_EPI && EXB_EPI_PREFETCH && act && (w == 0 || w == TW - 1 || iw == p.inner - 1)) {
-    // first / last lane of each row segment pulls the lines holding the stage operands into L2
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const long long mode = (long long)(j + P * q) * ls + iw;
-#pragma unroll
-      for (int c = 0; c < C; ++c)
-        etdrk_prefetch(p.K, p.stage, (long long)(p.K.E == 1 ? 0 : c) * p.K.M + mode, ((size_t)b * C + c) * p.M + mode,
-                       p.sb, c == 0 || p.K.E != 1);
-    }
-  }
   // is the (single) injection mode outside the mask?  (then masked modes are not all N(u) == 0)
   bool inj_masked = false;
   if (Pn.has_inj && kmax >= 0) {
@@ -231,61 +285,38 @@ col_fast_kernel(const ColParams<float> p) {
       }
     }
   }
+  const int order = STG ? 2 : p.K.order;
+  const int stage = STG ? STG - 1 : p.stage;
   const bool masked_skip = MODE == COL_FWD_EPI && EXB_EPI_MASKED_SKIP && kmax >= 0 && !inj_masked;
   // a tile of dealiased columns: N(u) == 0, the intermediate stages have nothing to do
-  if (masked_skip && !any_keep && p.stage != p.K.order - 1) return;
+  if (masked_skip && !any_keep && stage != order - 1) return;
   cpx<float> W[NFWD][8];
 #pragma unroll
   for (int g = 0; g < NFWD; ++g) {
-    const size_t ibase = ((size_t)b * NFWD + g) * p.M + iw;
+    const cpx<float>* __restrict__ src = p.in + ((size_t)b * NFWD + g) * p.M + iw + (size_t)j * ls;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) W[g][q] = col_keep ? p.in[ibase + (size_t)(j + P * q) * ls] : zero;
+    for (int q = 0; q < 8; ++q) W[g][q] = col_keep ? src[q * qstride] : zero;
   }
   if (any_keep) {  // masked columns only need the N = 0 update below
 #pragma unroll
     for (int g = 0; g < NFWD; ++g) fft8_run<N, DIR>(W[g], ex, j, tw);
   }
   if (!act) return;
-  if (EXB_EPI_TWO_PHASE && C == NFWD && C > 1) {
-    // phase A, registers only: N(u)_c of every mode overwrites the forward fields; phase B streams the
-    // ETDRK operands through (its loads depend on nothing, the registers of consumed modes free up)
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      ModeK<float> m = make_mode<float, S>(Pn, j + P * q, i1, i2);
-      cpx<float> wq[NFWD], n[EXB_MAXC];
-#pragma unroll
-      for (int g = 0; g < NFWD; ++g) wq[g] = W[g][q];
-      nl_from_fwd<float, S>(Pn, wq, m, n);
-#pragma unroll
-      for (int c = 0; c < C; ++c) W[c < NFWD ? c : 0][q] = n[c];
-    }
-#pragma unroll
-    for (int c = 0; c < C; ++c) {
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const long long mode = (long long)(j + P * q) * ls + iw;
-        const size_t off = ((size_t)b * C + c) * p.M + mode;
-        const cpx<float> n = W[c < NFWD ? c : 0][q];
-        if (MODE == COL_FWD_NL) {
-          p.out[off] = n;
-        } else {
-          const long long ci = (long long)(p.K.E == 1 ? 0 : c) * p.K.M + mode;
-          etdrk_update(p.K, p.stage, ci, off, n, p.sb);
-        }
-      }
-    }
-    return;
-  }
+  // element offset of (trajectory b, channel 0, entry q = 0) and of the coefficient entry; + q * qstride + c * M
+  const size_t off0 = (size_t)b * C * p.M + iw + (size_t)j * ls;
+  const size_t ci0 = iw + (size_t)j * ls;
+  const size_t cstep = p.K.E == 1 ? 0 : (size_t)p.K.M;
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
-    const int i0 = j + P * q;
-    ModeK<float> m = make_mode<float, S>(Pn, i0, i1, i2);
-    const long long mode = (long long)i0 * ls + iw;
+    const ModeK<float> m = mode_of(q);
     if (masked_skip && !m.keep) {
+      if (stage == order - 1) {
 #pragma unroll
-      for (int c = 0; c < C; ++c)
-        etdrk_update_masked(p.K, p.stage, (long long)(p.K.E == 1 ? 0 : c) * p.K.M + mode,
-                            ((size_t)b * C + c) * p.M + mode, p.sb);
+        for (int c = 0; c < C; ++c) {
+          const size_t off = off0 + q * qstride + (size_t)c * p.M;
+          p.sb.OUT[off] = p.K.exp_term[ci0 + q * qstride + c * cstep] * p.sb.U[off];
+        }
+      }
       continue;
     }
     cpx<float> wq[NFWD], n[EXB_MAXC];
@@ -294,12 +325,17 @@ col_fast_kernel(const ColParams<float> p) {
     nl_from_fwd<float, S>(Pn, wq, m, n);
 #pragma unroll
     for (int c = 0; c < C; ++c) {
-      const size_t off = ((size_t)b * C + c) * p.M + mode;
+      const size_t off = off0 + q * qstride + (size_t)c * p.M;
+      const size_t ci = ci0 + q * qstride + c * cstep;
       if (MODE == COL_FWD_NL) {
         p.out[off] = n[c];
+      } else if (STG == 1) {   // ETDRK2 stage 0 (_etdrk_2.py:96-98): a = E u + c1 N(u); keep N(u)
+        p.sb.S[0][off] = axpy(p.K.c[0][ci], n[c], p.K.exp_term[ci] * p.sb.U[off]);
+        p.sb.S[1][off] = n[c];
+      } else if (STG == 2) {   // ETDRK2 stage 1 (_etdrk_2.py:99-101): u+ = a + c2 (N(a) - N(u))
+        p.sb.OUT[off] = axpy(p.K.c[1][ci], n[c] - p.sb.S[1][off], p.sb.S[0][off]);
       } else {
-        const long long ci = (long long)(p.K.E == 1 ? 0 : c) * p.K.M + mode;
-        etdrk_update(p.K, p.stage, ci, off, n[c], p.sb);
+        etdrk_update(p.K, stage, (long long)ci, off, n[c], p.sb);
       }
     }
   }

@@ -34,6 +34,29 @@ def test_library_exports_every_declared_symbol():
     assert b"sm_100a" in nat.lib().exb_version()
 
 
+def test_xla_ffi_adapter_compiles():
+    """exb_xla_ffi.cc (the jax.ffi handlers) against the mock of xla/ffi/api/ffi.h: syntax, every exb_* call it makes
+    and the match between each handler implementation and its binding (the mock static_asserts it).  A deliberately
+    broken binding must fail, so the check is known to bite."""
+    import subprocess
+    import __graft_entry__ as g
+    g.check_xla_ffi_adapter()
+    src = open(os.path.join(ROOT, "exponax_b200", "csrc", "exb_xla_ffi.cc")).read()
+    for sym in ("exb_xla_rollout", "exb_xla_step", "exb_xla_step_fourier", "exb_xla_nonlinear_fun", "exb_xla_fft",
+                "exb_xla_ifft", "exb_xla_register_plan"):
+        assert sym in src
+    broken = src.replace('.Attr<int32_t>("flags")', "", 1)  # binding no longer matches RolloutImpl
+    assert broken != src
+    tmp = os.path.join(ROOT, "exponax_b200", "csrc", "_broken_ffi_check.cc")
+    try:
+        open(tmp, "w").write(broken)
+        r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wno-comment", "-I", os.path.join(ROOT, "tests", "mock_xla"),
+                            "-I", "/usr/local/cuda/include", tmp], capture_output=True, text=True)
+        assert r.returncode != 0 and "does not match its XLA FFI binding" in r.stderr
+    finally:
+        os.remove(tmp)
+
+
 def test_desc_struct_size_matches_header_guard():
     d = nat.ExbDesc()
     d.struct_size = 3  # wrong on purpose
