@@ -110,6 +110,10 @@ template <class T> struct PlanImpl : exb_plan {
   int D, N, Nh, C;
   long long M;     // modes per channel
   long long G;     // grid points per channel
+  int Nhp = 0;     // last-axis pitch of the internal FIELD buffers (n_inv / n_fwd fields between the passes of one
+  long long Mf = 0;  // N(u) evaluation) and their field stride: padded to a multiple of 16 complex elements (128 B) on the
+                     // fast N-D path so that every tile row is line-aligned and a tensor map can describe the buffers;
+                     // == Nh / M otherwise (generic kernels, slab plans whose buffers the caller lays out)
   int nscr;        // ETDRK scratch states
   int nranks = 1;  // slab decomposition (3-D): number of ranks, local extent of the split axis
   int nloc = 0;
@@ -311,6 +315,12 @@ template <class T> struct PlanImpl : exb_plan {
     if constexpr (std::is_same<T, float>::value) {
       fast_nd = D >= 2 && !getenv("EXB_DISABLE_FAST_ND") && exb_fastnd_supported(D, N, P);
     }
+    Nhp = Nh;
+    Mf = M;
+    if (fast_nd && nranks == 1 && !getenv("EXB_DENSE_FIELDS")) {
+      Nhp = (Nh + 15) / 16 * 16;
+      Mf = M / Nh * Nhp;
+    }
 
     if (D == 1) {
       size_t need = smem_1d(C, nslots_1d());
@@ -450,9 +460,11 @@ template <class T> struct PlanImpl : exb_plan {
     }
   }
 
+  // fields: in / out are internal field buffers (pitch Nhp, field stride Mf); otherwise dense spectral arrays
   template <int DIR>
   int col_plain(cudaStream_t st, int axis, long long batch, int nfields, const cpx<T>* in, cpx<T>* out,
-                int prune = 0, bool segmented = false, void* const* peers = nullptr, long long peer_field_off = 0) {
+                int prune = 0, bool segmented = false, void* const* peers = nullptr, long long peer_field_off = 0,
+                bool fields = false) {
     ColParams<T> p;
     memset(&p, 0, sizeof(p));
     p.prune = prune;
@@ -468,6 +480,11 @@ template <class T> struct PlanImpl : exb_plan {
     p.in = in;
     p.out = out;
     col_geom(p, axis);
+    if (fields && Nhp != Nh) {  // (3-D axis 1 only: the lines of a padded field buffer)
+      p.M = Mf;
+      p.line_stride = Nhp;
+      p.outer_stride = (long long)N * Nhp;
+    }
     if (segmented) {  // slab layout A as received from / sent to the peers: [peer][x][n][Nh]
       p.seg_len = nloc;
       p.seg_stride = (long long)nloc * nloc * Nh;
@@ -508,6 +525,8 @@ template <class T> struct PlanImpl : exb_plan {
     p.in = state;
     p.out = winv;
     col_geom(p, 0);
+    p.fpitch = Nhp;
+    p.fM = Mf;
     if (peers) {
       if (!fast_nd || nranks <= 1) return fail(EXB_EUNSUPPORTED, "peer stores need the fast N-D kernels");
       p.peer = 1;
@@ -544,6 +563,8 @@ template <class T> struct PlanImpl : exb_plan {
     p.out = nl_out;
     p.sb = sb;
     col_geom(p, 0);
+    p.fpitch = Nhp;
+    p.fM = Mf;
     {  // coefficient tables this stage reads (E or E/2 complex + one or more real tables) vs the L2 (126 MB)
       static const char* env = getenv("EXB_EPI_BATCH_FASTEST");
       const size_t table_bytes = (size_t)K.E * M * (sizeof(cpx<T>) + sizeof(T));
@@ -560,9 +581,11 @@ template <class T> struct PlanImpl : exb_plan {
   }
 
   int row_pass(cudaStream_t st, int mode, long long batch, int nin, int nout, const void* in,
-               long long in_bs, void* out, long long out_bs) {
+               long long in_bs, void* out, long long out_bs, int in_pitch = 0, int out_pitch = 0) {
     RowParams<T> p;
     memset(&p, 0, sizeof(p));
+    p.in_pitch = in_pitch;
+    p.out_pitch = out_pitch;
     p.prune = mode == ROW_NL ? (PRUNE_IN_ROWS | PRUNE_OUT_ROWS) : 0;
     p.P = P;
     p.fd = fd;
@@ -622,14 +645,14 @@ template <class T> struct PlanImpl : exb_plan {
   size_t workspace_bytes(int64_t batch) const override {
     if (D == 1 || batch <= 0) return 0;
     size_t sb = state_bytes(batch);
-    size_t fb = align_up((size_t)batch * M * sizeof(cpx<T>), 256);
+    size_t fb = align_up((size_t)batch * Mf * sizeof(cpx<T>), 256);
     return sb * (size_t)(nscr + 1) + fb * (size_t)(winv_fields() + wfwd_fields());
   }
   Ws carve(void* ws, long long batch) const {
     Ws w;
     unsigned char* p = (unsigned char*)ws;
     size_t sb = state_bytes(batch);
-    size_t fb = align_up((size_t)batch * M * sizeof(cpx<T>), 256);
+    size_t fb = align_up((size_t)batch * Mf * sizeof(cpx<T>), 256);
     for (int i = 0; i < 4; ++i) w.S[i] = nullptr;
     for (int i = 0; i < nscr; ++i) {
       w.S[i] = (cpx<T>*)p;
@@ -648,14 +671,14 @@ template <class T> struct PlanImpl : exb_plan {
     int rc = col_inv_pro(st, batch, state, w.Winv);
     if (rc) return rc;
     if (D == 3) {
-      rc = col_plain<+1>(st, 1, batch, P.n_inv, w.Winv, w.Winv, PRUNE_COLS | PRUNE_IN_ROWS);
+      rc = col_plain<+1>(st, 1, batch, P.n_inv, w.Winv, w.Winv, PRUNE_COLS | PRUNE_IN_ROWS, false, nullptr, 0, true);
       if (rc) return rc;
     }
-    rc = row_pass(st, ROW_NL, batch, P.n_inv, P.n_fwd, w.Winv, (long long)P.n_inv * M, w.Wfwd,
-                  (long long)P.n_fwd * M);
+    rc = row_pass(st, ROW_NL, batch, P.n_inv, P.n_fwd, w.Winv, (long long)P.n_inv * Mf, w.Wfwd,
+                  (long long)P.n_fwd * Mf, Nhp, Nhp);
     if (rc) return rc;
     if (D == 3) {
-      rc = col_plain<-1>(st, 1, batch, P.n_fwd, w.Wfwd, w.Wfwd, PRUNE_COLS | PRUNE_OUT_ROWS);
+      rc = col_plain<-1>(st, 1, batch, P.n_fwd, w.Wfwd, w.Wfwd, PRUNE_COLS | PRUNE_OUT_ROWS, false, nullptr, 0, true);
       if (rc) return rc;
     }
     return EXB_OK;

@@ -1,6 +1,10 @@
 // Shared body of exb_fastnd_n{256,512}.cu: instantiations + launchers for one line length.
+#include <cstdlib>
+
 #include "exb_fastnd.h"
 #include "exb_kernels_nd_fast.cuh"
+#include "exb_kernels_nd_tma.cuh"
+#include "exb_tma.h"
 #ifndef EXB_ROW16
 #define EXB_ROW16 0
 #endif
@@ -42,8 +46,94 @@ int launch_col_stg(cudaStream_t st, const ColParams<float>& p, long long grid, c
   }
   return EXB_OK;
 }
+#ifndef EXB_PLAIN_TMA
+#define EXB_PLAIN_TMA 1
+#endif
+// TMA-staged persistent COL_PLAIN pass over axis 1 of a pitch-padded 3-D field buffer (exb_kernels_nd_tma.cuh).
+// Returns EXB_OK / an error, or 1 when the configuration does not qualify (caller falls back to col_fast_kernel).
+template <int N, int TW, int DIR>
+int try_launch_plain_tma(cudaStream_t st, const ColParams<float>& p, const char** err) {
+  if constexpr (N > 256 || TW != 16) {
+    return 1;
+  } else {
+    static const bool off = getenv("EXB_PLAIN_TMA") && atoi(getenv("EXB_PLAIN_TMA")) == 0;
+    const int kmax = p.P.kmax;
+    const long long pitch = p.line_stride;
+    if (off || !EXB_PLAIN_TMA || p.seg_len > 0 || p.peer || p.in != p.out || !(p.prune & PRUNE_COLS) || kmax < 0 ||
+        2 * (kmax + 1) > N || pitch % 16 != 0 || p.outer_stride != (long long)N * pitch ||
+        p.M != (long long)N * p.outer_stride || p.inner != p.P.Nh || p.n_outer != N)
+      return 1;
+    const bool pin = (p.prune & PRUNE_IN_ROWS) != 0, pout = (p.prune & PRUNE_OUT_ROWS) != 0;
+    const uint64_t planes = (uint64_t)N * (uint64_t)p.batch * (uint64_t)p.nfields;
+    const uint64_t dims[3] = {(uint64_t)kmax + 1, (uint64_t)N, planes};
+    const uint64_t strides[3] = {0, (uint64_t)pitch * sizeof(cpx<float>), (uint64_t)p.outer_stride * sizeof(cpx<float>)};
+    const uint32_t box_in[3] = {(uint32_t)TW, (uint32_t)(pin ? kmax + 1 : N), 1};
+    const uint32_t box_out[3] = {(uint32_t)TW, (uint32_t)(pout ? kmax + 1 : N), 1};
+    CUtensorMap in_map, out_map;
+    if (exb_tma_encode(&in_map, p.in, 3, dims, strides, box_in, err)) return EXB_ECUDA;
+    if (exb_tma_encode(&out_map, p.out, 3, dims, strides, box_out, err)) return EXB_ECUDA;
+    ColTmaParams q;
+    q.tw = p.tw;
+    q.ntx = (unsigned)((kmax + 1 + TW - 1) / TW);
+    const uint64_t nblk = (uint64_t)q.ntx * planes;
+    if (nblk >= (1ull << 32)) return 1;
+    q.nblk = (unsigned)nblk;
+    q.kmax = kmax;
+    q.prune_in_rows = pin;
+    q.prune_out_rows = pout;
+    const size_t smem = (size_t)(2 * N * TW + ((Fft8Tw<N>::SIZE + 1) & ~1)) * sizeof(cpx<float>) + 16 + 128;
+    if (int rc = set_smem(col_plain_tma_kernel<N, TW, DIR>, smem, err)) return rc;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned grid = (unsigned)(nblk < 2ull * sms ? nblk : 2ull * sms);
+    col_plain_tma_kernel<N, TW, DIR><<<grid, (N / 8) * TW, smem, st>>>(in_map, out_map, q);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      *err = cudaGetErrorString(e);
+      return EXB_ECUDA;
+    }
+    return EXB_OK;
+  }
+}
+
+#ifndef EXB_INVPRO_PERSISTENT
+#define EXB_INVPRO_PERSISTENT 1
+#endif
+// persistent prologue pass of the one-channel 2-D kinds: only the tiles inside the dealiasing mask are enumerated
+template <int N, int TW, class S, int DIR>
+int launch_invpro_persistent(cudaStream_t st, const ColParams<float>& p, const char** err) {
+  const size_t smem = (size_t)(Fft8Tw<N>::SIZE + ExTile<TW>::rows(N) * TW + 2 * N * TW) * sizeof(cpx<float>);
+  if (int rc = set_smem(col_invpro_persistent_kernel<N, TW, S, DIR>, smem, err)) return rc;
+  const long long cols = p.P.kmax >= 0 ? (long long)p.P.kmax + 1 : p.inner;      // kept last-axis wavenumbers
+  const unsigned ntiles = (unsigned)((cols + TW - 1) / TW);
+  const long long nblk = (long long)ntiles * p.batch;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long grid = nblk < 2LL * sms ? nblk : 2LL * sms;
+  ColParams<float> q = p;
+  q.TW = TW;
+  col_invpro_persistent_kernel<N, TW, S, DIR><<<(unsigned)grid, (N / 8) * TW, smem, st>>>(q, (unsigned)nblk, ntiles);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    *err = cudaGetErrorString(e);
+    return EXB_ECUDA;
+  }
+  return EXB_OK;
+}
+
 template <int N, int TW, class S, int NFWD, int MODE, int DIR>
 int launch_col(cudaStream_t st, const ColParams<float>& p, long long grid, const char** err) {
+  if constexpr (MODE == COL_INV_PRO && S::C == 1 && S::D == 2 && EXB_INVPRO_PERSISTENT != 0) {
+    static const bool off = getenv("EXB_INVPRO_PERSISTENT") && atoi(getenv("EXB_INVPRO_PERSISTENT")) == 0;
+    if (!off && !p.peer && (p.prune & PRUNE_COLS) && p.inner == p.P.Nh && p.M < (1LL << 31))
+      return launch_invpro_persistent<N, TW, S, DIR>(st, p, err);
+  }
+  if constexpr (MODE == COL_PLAIN) {
+    const int rc = try_launch_plain_tma<N, TW, DIR>(st, p, err);
+    if (rc != 1) return rc;
+  }
   if constexpr (MODE == COL_FWD_EPI) {
     // ETDRK2 (the default order): stage updates with compile-time operand sets
     if (p.K.order == 2 && p.stage == 0) return launch_col_stg<N, TW, S, NFWD, MODE, DIR, 1>(st, p, grid, err);

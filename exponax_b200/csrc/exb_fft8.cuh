@@ -50,18 +50,41 @@ template <int N> struct Fft8Tw {
   }
 };
 
+// The R - 1 twiddles w^r (r = 1 .. R-1) of one butterfly.  DERIVE: only w^1, w^2, w^4 are read from the shared-memory
+// table, the others are products of two of them (w^3 = w^1 w^2, w^5 = w^1 w^4, w^6 = w^2 w^4, w^7 = w^3 w^4: at most
+// two extra roundings).  The row kernels are bound by the shared-memory pipe (88-92 % LSU wavefront utilisation,
+// 17 % of the wavefronts were twiddle loads -- ncu r02d) with the FMA pipe at 35 %: 4 loads become 8 packed FP ops.
+template <int R, int DIR, bool DERIVE>
+__device__ __forceinline__ void load_twiddles(cpx<float> (&w)[8], const cpx<float>* __restrict__ t, int stride) {
+  if (!DERIVE || R < 4) {
+#pragma unroll
+    for (int r = 1; r < R; ++r) w[r] = twd<float, DIR>(t[(r - 1) * stride]);
+    return;
+  }
+  w[1] = twd<float, DIR>(t[0]);
+  w[2] = twd<float, DIR>(t[stride]);
+  w[3] = w[1] * w[2];
+  if (R == 8) {
+    w[4] = twd<float, DIR>(t[3 * stride]);
+    w[5] = w[1] * w[4];
+    w[6] = w[2] * w[4];
+    w[7] = w[3] * w[4];
+  }
+}
+
 // last pass: radix RL with Ns = N / RL; 8/RL butterflies per thread, results stay in registers
-template <int N, int DIR, int TOFF>
+template <int N, int DIR, int TOFF, bool DERIVE>
 __device__ __forceinline__ void fft8_last_pass(cpx<float> (&v)[8], int j, const cpx<float>* __restrict__ tw) {
   constexpr int P = N / 8, RL = Fft8Cfg<N>::RL, NS = N / RL, NB = 8 / RL;
 #pragma unroll
   for (int i = 0; i < NB; ++i) {
     const int b = j + P * i;
-    cpx<float> a[RL];
+    cpx<float> a[RL], w[8];
+    load_twiddles<RL, DIR, DERIVE>(w, tw + TOFF + b, NS);
 #pragma unroll
     for (int r = 0; r < RL; ++r) {
       a[r] = v[i + NB * r];
-      if (r > 0) a[r] = a[r] * twd<float, DIR>(tw[TOFF + (r - 1) * NS + b]);
+      if (r > 0) a[r] = a[r] * w[r];
     }
     dft_small<DIR, RL>(a);
 #pragma unroll
@@ -87,8 +110,12 @@ __device__ __forceinline__ void fft8_run(cpx<float> (&v)[8], const Ex& ex, int j
   // ---- pass 2: radix 8, Ns = 8 ----
   {
     const int k = j & 7;
+    {
+      cpx<float> w[8];
+      load_twiddles<8, DIR, Ex::kDeriveTw>(w, tw + k, 8);
 #pragma unroll
-    for (int r = 1; r < 8; ++r) v[r] = v[r] * twd<float, DIR>(tw[(r - 1) * 8 + k]);
+      for (int r = 1; r < 8; ++r) v[r] = v[r] * w[r];
+    }
     dft8<float, DIR>(v);
     if (Cfg::NP == 2) return;  // N = 64: outputs already at j + 8*r
     const int j0 = (j - k) * 8 + k;
@@ -100,14 +127,18 @@ __device__ __forceinline__ void fft8_run(cpx<float> (&v)[8], const Ex& ex, int j
     for (int q = 0; q < 8; ++q) v[q] = ex.ld(j + P * q);
   }
   if (Cfg::NP == 3) {
-    fft8_last_pass<N, DIR, Tw::T3>(v, j, tw);
+    fft8_last_pass<N, DIR, Tw::T3, Ex::kDeriveTw>(v, j, tw);
     return;
   }
   // ---- pass 3 of 4: radix 8, Ns = 64 ----
   {
     const int k = j & 63;
+    {
+      cpx<float> w[8];
+      load_twiddles<8, DIR, Ex::kDeriveTw>(w, tw + Tw::T3 + k, 64);
 #pragma unroll
-    for (int r = 1; r < 8; ++r) v[r] = v[r] * twd<float, DIR>(tw[Tw::T3 + (r - 1) * 64 + k]);
+      for (int r = 1; r < 8; ++r) v[r] = v[r] * w[r];
+    }
     dft8<float, DIR>(v);
     const int j0 = (j - k) * 8 + k;
     ex.sync();
@@ -117,7 +148,7 @@ __device__ __forceinline__ void fft8_run(cpx<float> (&v)[8], const Ex& ex, int j
 #pragma unroll
     for (int q = 0; q < 8; ++q) v[q] = ex.ld(j + P * q);
   }
-  fft8_last_pass<N, DIR, Tw::T4>(v, j, tw);
+  fft8_last_pass<N, DIR, Tw::T4, Ex::kDeriveTw>(v, j, tw);
 }
 
 // exchange through a contiguous line buffer (row kernels).  Element i lives at the XOR-swizzled slot
@@ -129,7 +160,11 @@ __device__ __forceinline__ void fft8_run(cpx<float> (&v)[8], const Ex& ex, int j
 #ifndef EXB_LINE_SWIZZLE
 #define EXB_LINE_SWIZZLE 1
 #endif
+#ifndef EXB_ROW_DERIVE_TW
+#define EXB_ROW_DERIVE_TW 1
+#endif
 struct ExLine {
+  static constexpr bool kDeriveTw = EXB_ROW_DERIVE_TW != 0;   // row kernels: shared-memory-pipe bound
   cpx<float>* base;
   int sync_kind;  // 0: __syncwarp, otherwise named barrier id
   int nthreads;
@@ -148,6 +183,7 @@ struct ExLine {
 // (rows narrower than 128 B get one pad row per 8 rows so that the stride-8-row stores of
 // pass 1 spread over all banks)
 template <int TW> struct ExTile {
+  static constexpr bool kDeriveTw = false;                     // column kernels: not bound by the shared-memory pipe
   static constexpr bool PAD = TW < 16;
   static constexpr int rows(int n) { return PAD ? n + n / 8 : n; }
   cpx<float>* base;  // tile + w

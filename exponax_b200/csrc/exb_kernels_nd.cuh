@@ -37,6 +37,12 @@ template <class T> struct ColParams {
   int prune;               // fast kernels only: PRUNE_* bits (dealiased modes are never touched)
   int f0, fcount;          // COL_INV_PRO: inverse fields [f0, f0 + fcount) (fcount <= 0: all)
   int batch_fastest;       // fast COL_FWD_EPI: block index = tile * batch + trajectory (tables larger than the L2)
+  // Fast kernels: the FIELD buffers between the passes of one N(u) evaluation (n_inv inverse / n_fwd forward fields)
+  // may have a padded last-axis pitch (fpitch >= N/2+1 complex elements, a multiple of 16 = 128 B: every tile row
+  // is line-aligned and a tensor map can describe the buffer) and their own field stride fM = N^(D-1) * fpitch.
+  // State buffers and coefficient tables are always dense (pitch N/2+1, stride M).  0 = dense (generic kernels, slabs).
+  int fpitch;
+  long long fM;
   int seg_len;             // COL_PLAIN, slab transposes without pack/unpack: line entry i lives at
   long long seg_stride;    //   (i / seg_len) * seg_stride + (i % seg_len) * line_stride   (seg_len = 0: off)
   // peer output (fast kernels, COL_INV_PRO / COL_PLAIN of a slab plan): entry i of an output line is stored
@@ -201,6 +207,7 @@ template <class T> struct RowParams {
   int nin, nout;             // fields per batch element read / written
   long long rows;            // rows per field = N^(D-1)
   int prune;                 // fast kernels only: PRUNE_IN_ROWS / PRUNE_OUT_ROWS along the last axis
+  int in_pitch, out_pitch;   // fast kernels only: elements between consecutive half-complex rows (0 = dense N/2+1)
   long long batch;
   long long in_batch_stride;   // elements (of the in type) between batch elements
   long long out_batch_stride;  // elements (of the out type) between batch elements

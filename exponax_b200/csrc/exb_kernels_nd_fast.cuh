@@ -120,6 +120,13 @@ col_fast_kernel(const ColParams<float> p) {
   __syncthreads();
   const bool any_keep = __syncthreads_or(col_keep);
   const size_t qstride = (size_t)P * (size_t)ls;  // elements between the entries q and q + 1 of this thread
+  // the same for the (possibly pitch-padded) field buffers of the prologue / epilogue passes: element offset of this
+  // thread's entry q = 0 inside a field, entry stride, field stride
+  const int fpitch = p.fpitch > 0 ? p.fpitch : p.P.Nh;
+  const size_t fM = p.fpitch > 0 ? (size_t)p.fM : (size_t)p.M;
+  const size_t fls = flat3 ? (size_t)N * fpitch : (size_t)fpitch;
+  const size_t foff = (flat3 ? (size_t)(i1 - p.P.i1_off) * fpitch + i2 : (size_t)iw) + (size_t)j * fls;
+  const size_t fqstride = (size_t)P * fls;
 
   if (MODE == COL_PLAIN) {
     const unsigned n_outer = (unsigned)p.n_outer;
@@ -256,17 +263,17 @@ col_fast_kernel(const ColParams<float> p) {
       }
       fft8_run<N, DIR>(v, ex, j, tw);
       if (col_keep) {
-        const size_t obase = ((size_t)b * Pn.n_inv + f) * p.M + iw;
-        if (p.peer) {  // x-plane i of the result belongs to rank i / seg_len: store it there (NVLink)
+        if (p.peer) {  // x-plane i of the result belongs to rank i / seg_len: store it there (NVLink; dense buffers)
+          const size_t obase = ((size_t)b * Pn.n_inv + f) * p.M + iw;
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const int i = j + P * q;
             p.peer_out[i / p.seg_len][obase + p.peer_off + (size_t)(i % p.seg_len) * ls] = v[q];
           }
         } else {
-          cpx<float>* __restrict__ dst = p.out + obase + (size_t)j * ls;
+          cpx<float>* __restrict__ dst = p.out + ((size_t)b * Pn.n_inv + f) * fM + foff;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) dst[q * qstride] = v[q];
+          for (int q = 0; q < 8; ++q) dst[q * fqstride] = v[q];
         }
       }
     }
@@ -293,9 +300,9 @@ col_fast_kernel(const ColParams<float> p) {
   cpx<float> W[NFWD][8];
 #pragma unroll
   for (int g = 0; g < NFWD; ++g) {
-    const cpx<float>* __restrict__ src = p.in + ((size_t)b * NFWD + g) * p.M + iw + (size_t)j * ls;
+    const cpx<float>* __restrict__ src = p.in + ((size_t)b * NFWD + g) * fM + foff;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) W[g][q] = col_keep ? src[q * qstride] : zero;
+    for (int q = 0; q < 8; ++q) W[g][q] = col_keep ? src[q * fqstride] : zero;
   }
   if (any_keep) {  // masked columns only need the N = 0 update below
 #pragma unroll
@@ -341,6 +348,119 @@ col_fast_kernel(const ColParams<float> p) {
   }
 }
 
+// ----------------------------------------------------------- persistent prologue pass (one-channel states)
+// COL_INV_PRO for the one-channel kinds (2-D vorticity, gradient norm, polynomial) as a PERSISTENT kernel: the
+// non-persistent version spends a third of its warp-stall samples at CTA start-up (ncu r02d: waiting for the
+// twiddle table and for the first -- and only -- global loads of a CTA that lives for just n_inv transforms, with
+// 2 CTAs per SM and nothing else to run).  Here a CTA fills its tables once and walks over (tile, trajectory) pairs
+// with a stride of gridDim; the stage input of the NEXT pair is fetched with cp.async into the second half of a
+// double-buffered, thread-private stash while the transforms of the current pair run.
+template <int N, int TW, class S, int DIR>
+__global__ void __launch_bounds__((N / 8) * TW, 2) col_invpro_persistent_kernel(const ColParams<float> p, unsigned nblk,
+                                                                              unsigned ntiles) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  static_assert(S::C == 1, "one-channel states only");
+  constexpr int P = N / 8, NT = P * TW;
+  constexpr int TROWS = ExTile<TW>::PAD ? N + N / 8 : N;
+  constexpr bool VORT = S::kind == EXB_NL_VORTICITY_2D;
+  cpx<float>* tw = reinterpret_cast<cpx<float>*>(smem_raw);
+  cpx<float>* tile = tw + Fft8Tw<N>::SIZE;
+  cpx<float>* stash0 = tile + TROWS * TW + threadIdx.x;  // [buffer][q][thread]: thread-private, conflict-free
+  Fft8Tw<N>::fill(tw, p.tw);
+  const int w = threadIdx.x % TW, j = threadIdx.x / TW;
+  const unsigned inner = (unsigned)p.inner;
+  const cpx<float> zero(0.f, 0.f);
+  ExTile<TW> ex{tile + w};
+  const long long ls = p.line_stride;
+  const NlParams<float>& Pn = p.P;
+  const int kmax = Pn.kmax;
+  unsigned rowmask = 0xffu;
+  if (kmax >= 0) {
+    rowmask = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int ak = q < 4 ? j + P * q : N - (j + P * q);
+      rowmask |= (ak <= kmax ? 1u : 0u) << q;
+    }
+  }
+  const size_t qstride = (size_t)P * (size_t)ls;
+  const int fpitch = p.fpitch > 0 ? p.fpitch : Pn.Nh;           // (2-D) pitch / field stride of the output fields
+  const size_t fM = p.fpitch > 0 ? (size_t)p.fM : (size_t)p.M;
+  const size_t fqstride = (size_t)P * fpitch;
+  auto kd0_of = [&](int q) { return Pn.dscale * (float)(j + P * q - (q >= 4 ? N : 0)); };
+  // asynchronous fetch of the stage input of logical block `blk` into stash buffer `buf`
+  auto fetch = [&](unsigned blk, int buf) {
+    const unsigned t = blk % ntiles, b = blk / ntiles;
+    const unsigned iw = t * TW + w;
+    const bool keep = iw < inner && (kmax < 0 || (int)iw <= kmax);
+    const cpx<float>* __restrict__ ubase = p.in + (size_t)b * p.M + iw + (size_t)j * ls;
+    cpx<float>* st = stash0 + buf * 8 * NT;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      if (keep && ((rowmask >> q) & 1u)) cp_async8(st + q * NT, ubase + q * qstride);
+      else st[q * NT] = zero;   // pre-dealiasing: modes outside the mask enter as zeros
+    }
+    cp_async_commit();
+  };
+  int buf = 0;
+  if (blockIdx.x < nblk) fetch(blockIdx.x, 0);
+  __syncthreads();  // twiddle table
+  for (unsigned blk = blockIdx.x; blk < nblk; blk += gridDim.x, buf ^= 1) {
+    const unsigned t = blk % ntiles, b = blk / ntiles;
+    const unsigned iw = t * TW + w;
+    const int k1 = (int)iw;   // 2-D: the inner index is the last-axis wavenumber
+    const bool col_keep = iw < inner && (kmax < 0 || k1 <= kmax);
+    const float kd1 = Pn.dscale * (float)k1;
+    cp_async_wait_all();      // this thread's slice of stash[buf] has landed (nobody else reads it)
+    if (blk + gridDim.x < nblk) fetch(blk + gridDim.x, buf ^ 1);
+    const cpx<float>* us = stash0 + buf * 8 * NT;
+    const int f_begin = p.fcount > 0 ? p.f0 : 0, f_end = p.fcount > 0 ? p.f0 + p.fcount : Pn.n_inv;
+    for (int f = f_begin; f < f_end; ++f) {
+      cpx<float> v[8];
+      if (VORT) {
+        // u = +d_y psi, v = -d_x psi, d_x w, d_y w with psi = w / laplacian (:= w at k = 0): i * (+-kd) * (psi or w)
+        const bool use_k1 = f == 0 || f == 3;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float a = kd0_of(q);
+          float kd = use_k1 ? kd1 : a;
+          if (f == 1) kd = -kd;
+          cpx<float> src = us[q * NT];
+          if (f < 2) {
+            const float lap = -(a * a) - (kd1 * kd1);
+            src = (lap == 0.f ? 1.f : exb_rcp(lap)) * src;
+          }
+          v[q] = mul_i(kd * src);
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          cpx<float> val = zero;
+          if (col_keep && ((rowmask >> q) & 1u)) {
+            ModeK<float> m;
+            m.kd[0] = kd0_of(q);
+            m.kd[1] = kd1;
+            m.kd[2] = 0.f;
+            m.keep = true;
+            m.is_inj = false;
+            m.is_dc = false;
+            cpx<float> u[EXB_MAXC] = {us[q * NT], zero, zero};
+            val = nl_inv_field<float, S>(Pn, f, u, m);
+          }
+          v[q] = val;
+        }
+      }
+      fft8_run<N, DIR>(v, ex, j, tw);
+      if (col_keep) {
+        cpx<float>* __restrict__ dst = p.out + ((size_t)b * Pn.n_inv + f) * fM + iw + (size_t)j * fpitch;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) dst[q * fqstride] = v[q];
+      }
+    }
+  }
+  cp_async_wait_all();
+}
+
 // ---------------------------------------------------------------------------------- row pass
 // ROW_NL "streaming": the nonlinearities of the fast kinds are sums of products of one early and one
 // late inverse field (u . grad w, u x curl u, |grad u|^2, (u . grad) u).  The first KST physical-space
@@ -372,6 +492,7 @@ __global__ void __launch_bounds__((N / 8) * GROUPS, row_min_blocks<S, NINV, NFWD
 row_fast_kernel(const RowParams<float> p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int P = N / 8, Nh = N / 2 + 1, XB = N + N / 8;
+  const int ipitch = p.in_pitch > 0 ? p.in_pitch : Nh, opitch = p.out_pitch > 0 ? p.out_pitch : Nh;  // half-complex rows
   // ROW_NL with several inverse lines: the physical-space results of each line are parked in a
   // thread-private slice of shared memory (conflict-free, no synchronisation) instead of
   // NINV * 16 registers, which keeps the kernel at 2-3 CTAs per SM.
@@ -449,7 +570,7 @@ row_fast_kernel(const RowParams<float> p) {
 #pragma unroll
       for (int q = 0; q < 8; ++q) v[q] = cpx<float>(has1 ? a[j + P * q] : 0.f, has2 ? c[j + P * q] : 0.f);
       fft8_run<N, -1>(v, ex, j, tw);
-      unpack_store(v, out + ((size_t)f * p.rows + r1) * Nh, out + ((size_t)f * p.rows + r2) * Nh);
+      unpack_store(v, out + ((size_t)f * p.rows + r1) * opitch, out + ((size_t)f * p.rows + r2) * opitch);
     }
     return;
   }
@@ -458,7 +579,7 @@ row_fast_kernel(const RowParams<float> p) {
     float* out = (float*)p.out + (size_t)b * p.out_batch_stride;
     for (int f = 0; f < p.nin; ++f) {
       cpx<float> v[8];
-      load_packed(in + ((size_t)f * p.rows + r1) * Nh, in + ((size_t)f * p.rows + r2) * Nh, v);
+      load_packed(in + ((size_t)f * p.rows + r1) * ipitch, in + ((size_t)f * p.rows + r2) * ipitch, v);
       fft8_run<N, +1>(v, ex, j, tw);
       float* a = out + ((size_t)f * p.rows + r1) * N;
       float* c = out + ((size_t)f * p.rows + r2) * N;
@@ -482,8 +603,8 @@ row_fast_kernel(const RowParams<float> p) {
       for (int q = 0; q < 8; ++q) wl[gg][q] = zero;
     cpx<float>* park = stash + j;  // field g, point q of this thread at park[(g * 8 + q) * P]
     auto fetch = [&](int f) {      // asynchronous copy of the two half-complex rows of inverse field f
-      const cpx<float>* a = in + ((size_t)f * p.rows + r1) * Nh;
-      const cpx<float>* c = in + ((size_t)f * p.rows + r2) * Nh;
+      const cpx<float>* a = in + ((size_t)f * p.rows + r1) * ipitch;
+      const cpx<float>* c = in + ((size_t)f * p.rows + r2) * ipitch;
       for (int k = j; k < Nh && k <= kin; k += P) {
         if (has1) cp_async8(stage + k, a + k);
         if (has2) cp_async8(stage + NHP + k, c + k);
@@ -513,7 +634,7 @@ row_fast_kernel(const RowParams<float> p) {
         ex.sync();
         if (f + 1 < NINV) fetch(f + 1);
       } else {
-        load_packed(in + ((size_t)f * p.rows + r1) * Nh, in + ((size_t)f * p.rows + r2) * Nh, z);
+        load_packed(in + ((size_t)f * p.rows + r1) * ipitch, in + ((size_t)f * p.rows + r2) * ipitch, z);
       }
       fft8_run<N, +1>(z, ex, j, tw);
 #pragma unroll
@@ -543,7 +664,7 @@ row_fast_kernel(const RowParams<float> p) {
   } else if (STASH) {
     for (int f = 0; f < NINV; ++f) {
       cpx<float> z[8];
-      load_packed(in + ((size_t)f * p.rows + r1) * Nh, in + ((size_t)f * p.rows + r2) * Nh, z);
+      load_packed(in + ((size_t)f * p.rows + r1) * ipitch, in + ((size_t)f * p.rows + r2) * ipitch, z);
       fft8_run<N, +1>(z, ex, j, tw);
 #pragma unroll
       for (int q = 0; q < 8; ++q) stash[(size_t)f * N + j + P * q] = z[q];
@@ -561,8 +682,8 @@ row_fast_kernel(const RowParams<float> p) {
     cpx<float> z[NINV][8];
     if (PREFETCH) {
       auto prefetch = [&](int f) {
-        const cpx<float>* a = in + ((size_t)f * p.rows + r1) * Nh;
-        const cpx<float>* c = in + ((size_t)f * p.rows + r2) * Nh;
+        const cpx<float>* a = in + ((size_t)f * p.rows + r1) * ipitch;
+        const cpx<float>* c = in + ((size_t)f * p.rows + r2) * ipitch;
         for (int k = j; k < Nh && k <= kin; k += P) {
           if (has1) cp_async8(stage + k, a + k);
           if (has2) cp_async8(stage + NHP + k, c + k);
@@ -594,7 +715,7 @@ row_fast_kernel(const RowParams<float> p) {
     } else {
 #pragma unroll
       for (int f = 0; f < NINV; ++f) {
-        load_packed(in + ((size_t)f * p.rows + r1) * Nh, in + ((size_t)f * p.rows + r2) * Nh, z[f]);
+        load_packed(in + ((size_t)f * p.rows + r1) * ipitch, in + ((size_t)f * p.rows + r2) * ipitch, z[f]);
         fft8_run<N, +1>(z[f], ex, j, tw);
       }
     }
@@ -611,7 +732,7 @@ row_fast_kernel(const RowParams<float> p) {
 #pragma unroll
   for (int gg = 0; gg < NFWD; ++gg) {
     fft8_run<N, -1>(wl[gg], ex, j, tw);
-    unpack_store(wl[gg], out + ((size_t)gg * p.rows + r1) * Nh, out + ((size_t)gg * p.rows + r2) * Nh);
+    unpack_store(wl[gg], out + ((size_t)gg * p.rows + r1) * opitch, out + ((size_t)gg * p.rows + r2) * opitch);
   }
 }
 

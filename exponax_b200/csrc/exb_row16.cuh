@@ -41,10 +41,11 @@ __global__ void __launch_bounds__(256, 1) row16_kernel(const RowParams<float> p)
   const int kout = ((p.prune & PRUNE_OUT_ROWS) && Pn.kmax >= 0) ? Pn.kmax : N;
   const cpx<float>* in = (const cpx<float>*)p.in + (size_t)b * p.in_batch_stride;
   cpx<float>* out = (cpx<float>*)p.out + (size_t)b * p.out_batch_stride;
+  const int ipitch = p.in_pitch > 0 ? p.in_pitch : Nh, opitch = p.out_pitch > 0 ? p.out_pitch : Nh;
 
   auto fetch = [&](int f) {
-    const cpx<float>* a = in + ((size_t)f * p.rows + r1) * Nh;
-    const cpx<float>* c = in + ((size_t)f * p.rows + r2) * Nh;
+    const cpx<float>* a = in + ((size_t)f * p.rows + r1) * ipitch;
+    const cpx<float>* c = in + ((size_t)f * p.rows + r2) * ipitch;
     for (int k = j; k < Nh && k <= kin; k += P) {
       if (has1) cp_async8(stage + k, a + k);
       if (has2) cp_async8(stage + NHP + k, c + k);
@@ -107,8 +108,8 @@ __global__ void __launch_bounds__(256, 1) row16_kernel(const RowParams<float> p)
 #pragma unroll
   for (int gg = 0; gg < NFWD; ++gg) {
     fft_reg<R, -1>(wl[gg], xb, j, tw2);
-    cpx<float>* o1 = out + ((size_t)gg * p.rows + r1) * Nh;
-    cpx<float>* o2 = out + ((size_t)gg * p.rows + r2) * Nh;
+    cpx<float>* o1 = out + ((size_t)gg * p.rows + r1) * opitch;
+    cpx<float>* o2 = out + ((size_t)gg * p.rows + r2) * opitch;
     __syncwarp();
 #pragma unroll
     for (int r = R / 2; r < R; ++r) xb[slot(j + P * r)] = wl[gg][r];

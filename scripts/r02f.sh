@@ -1,0 +1,6 @@
+#!/bin/bash
+tag=${1:-r02f}
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -8 | tee gpurun_out/${tag}_tests.txt
+scripts/r02_run.sh $tag "c3 c4 readme" skip
+EXB_DENSE_FIELDS=1 scripts/r02_run.sh ${tag}_dense "c3 c4" skip
