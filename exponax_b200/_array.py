@@ -55,6 +55,12 @@ def to_device(x, rd, *, complex_=False):
         kind = "torch"
     else:
         raise TypeError(f"unsupported array type {type(x)}")
+    if t.device.index != torch.cuda.current_device():
+        # plans, workspaces and the stream belong to the CURRENT device; a tensor living on another GPU would be
+        # dereferenced by kernels running here (illegal address, or silent peer access with the tables elsewhere)
+        raise ValueError(
+            f"array lives on cuda:{t.device.index} but the current device is cuda:{torch.cuda.current_device()}; "
+            f"wrap the call in `with torch.cuda.device({t.device.index}):`")
     if t.dtype != want:
         if complex_ and not t.is_complex():
             t = t.to(real_t(rd)).to(want)

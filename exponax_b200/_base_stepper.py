@@ -89,6 +89,10 @@ class BaseStepper(ABC):
         if self._slab is not None:
             raise RuntimeError("this stepper was built inside a slab_context: use it through ex.SlabStepper")
         p = self._integrator._plan(self.num_channels, self.num_points, self.domain_extent)
+        if p is not None and not p.fused_ok():
+            # 1-D grid too large for the persistent shared-memory kernel: the stage formulas run on device arrays
+            # around the native transforms (`_step_fourier_generic`), as for user-defined nonlinear functions
+            p = None
         self._native = p is not None
         return p
 
@@ -183,14 +187,26 @@ class BaseStepper(ABC):
                                         A.ptr(out), A.ptr(ws)))
         return A.from_device(out, kind)
 
+    _GRAPH_CACHE_ENTRIES = 4
+
+    def release_graphs(self):
+        """Drop every captured CUDA graph of this stepper together with the buffers it owns."""
+        self.__dict__.pop("_graphs", None)
+
     def _rollout_graph(self, plan, t, shape, batch, n, substeps, flags):
         """Replay the launch sequence of one fused rollout from a captured CUDA graph (the library only
         enqueues on the stream it is given, so the whole call is capturable).  Pays off for N-D problems
         whose hundreds of small pass launches are launch-bound; buffers are owned by the graph entry."""
         key = (tuple(t.shape), t.dtype, n, substeps, flags, A.torch.cuda.current_device())
         cache = self.__dict__.setdefault("_graphs", {})
-        ent = cache.get(key)
+        ent = cache.pop(key, None)
+        if ent is not None:
+            cache[key] = ent          # most recently used last
         if ent is None:
+            # every entry pins a graph + its static input, full-trajectory output and workspace: keep the cache
+            # small (LRU) so that sweeping batch sizes / rollout lengths cannot exhaust device memory
+            while len(cache) >= self._GRAPH_CACHE_ENTRIES:
+                cache.pop(next(iter(cache)))
             torch = A.torch
             static_in = torch.empty_like(t)
             static_out = torch.empty(shape, dtype=t.dtype, device="cuda")

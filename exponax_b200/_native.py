@@ -74,6 +74,7 @@ SYMBOLS = {
     "exb_rollout": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_uint32,
                               C.c_void_p, C.c_void_p, C.c_void_p]),
     "exb_launch_count": (C.c_int64, [C.c_void_p]),
+    "exb_plan_fused_ok": (C.c_int, [C.c_void_p]),
     "exb_peak_fp32": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "exb_peak_smem": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "exb_slab_pass": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
@@ -208,6 +209,10 @@ class Plan:
 
     def workspace_bytes(self, batch: int) -> int:
         return int(lib().exb_workspace_bytes(self.handle, int(batch)))
+
+    def fused_ok(self) -> bool:
+        """False for 1-D grids too large for the persistent shared-memory kernel (exb_plan_fused_ok)."""
+        return bool(lib().exb_plan_fused_ok(self.handle))
 
     def launch_count(self) -> int:
         return int(lib().exb_launch_count(self.handle))

@@ -117,7 +117,12 @@ def _native_target(stepper_fn):
     if isinstance(stepper_fn, RepeatedStepper):
         sub, stepper_fn = stepper_fn.num_sub_steps, stepper_fn.stepper
     if isinstance(stepper_fn, BaseStepper) and stepper_fn._plan_available():
-        return stepper_fn, sub, vm
+        # a subclass that overrides the stepping methods must be honoured: the reference's scan calls
+        # `stepper_fn(u)` every iteration (exponax/_utils.py:167-172), the fused kernel would bypass the override
+        t = type(stepper_fn)
+        if (t.step is BaseStepper.step and t.step_fourier is BaseStepper.step_fourier
+                and t.__call__ is BaseStepper.__call__):
+            return stepper_fn, sub, vm
     return None
 
 

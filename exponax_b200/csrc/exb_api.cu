@@ -39,6 +39,7 @@ static int fail(int code, const char* fmt, ...) {
   } while (0)
 
 struct exb_plan {
+  virtual int fused_ok() const { return 1; }
   exb_desc d;
   int64_t launches = 0;
   virtual ~exb_plan() {}
@@ -323,12 +324,16 @@ template <class T> struct PlanImpl : exb_plan {
     }
 
     if (D == 1) {
+      // The persistent kernel keeps the state, the ETDRK stage buffers and the transform lines of a trajectory
+      // pair in shared memory.  Grids too large for that (f32 ETDRK2 Burgers: N > ~4000) keep their standalone
+      // transforms (exb_fft / exb_ifft need only 2 N complex values); the fused entry points then answer
+      // EXB_EUNSUPPORTED and the host runs the stage formulas around those transforms (exb_plan_fused_ok).
       size_t need = smem_1d(C, nslots_1d());
-      if ((long long)need > max_smem)
-        return fail(EXB_EUNSUPPORTED,
-                    "1-D persistent kernel needs %zu B of shared memory for N=%d (limit %d); "
-                    "larger 1-D grids are not supported yet",
-                    need, N, max_smem);
+      fused_1d_ok = (long long)need <= max_smem;
+      fused_1d_need = need;
+      if ((size_t)2 * N * sizeof(cpx<T>) > (size_t)max_smem)
+        return fail(EXB_EUNSUPPORTED, "1-D transforms need %zu B of shared memory for N=%d (limit %d)",
+                    (size_t)2 * N * sizeof(cpx<T>), N, max_smem);
       CUDA_OK(cudaFuncSetAttribute(k1d_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
     } else {
       CUDA_OK(cudaFuncSetAttribute(col_pass_kernel<T, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
@@ -402,6 +407,11 @@ template <class T> struct PlanImpl : exb_plan {
     p.flags = flags;
     if (op == OP1_ROLLOUT && fast_1d_ok()) return launch_fast(st, p);
     bool plain = (op == OP1_FFT || op == OP1_IFFT);
+    if (!plain && !fused_1d_ok)
+      return fail(EXB_EUNSUPPORTED,
+                  "the fused 1-D kernel needs %zu B of shared memory for N=%d (limit %d): use the standalone "
+                  "transforms (exb_fft / exb_ifft) with the stage formulas on the host side",
+                  fused_1d_need, N, max_smem);
     p.nslots = plain ? ch : nslots_1d();
     size_t smem = plain ? (size_t)2 * ch * N * sizeof(cpx<T>) : smem_1d(ch, p.nslots);
     long long grid = (batch + 1) / 2;
@@ -414,6 +424,9 @@ template <class T> struct PlanImpl : exb_plan {
 
   // ------------------------------------------------------------------ N-D
   bool fast_nd = false;  // set in init(): register-FFT kernels available for this (D, N, N(u))
+  bool fused_1d_ok = true;   // 1-D: state + stage buffers + transform lines fit shared memory
+  size_t fused_1d_need = 0;
+  int fused_ok() const override { return D != 1 || fused_1d_ok; }
   int fast_tw() const { return N == 512 ? 8 : (N == 1024 ? 4 : (N == 2048 ? 2 : 16)); }  // == TW of exb_fastnd_n*.cu
   int launch_col_fast(cudaStream_t st, ColParams<T>& p, int dir, long long units) {
     if constexpr (std::is_same<T, float>::value) {
@@ -544,6 +557,17 @@ template <class T> struct PlanImpl : exb_plan {
     return EXB_OK;
   }
 
+  // the dealiased modes all have N(u) == 0 unless the (single) injection mode lies outside the mask
+  bool masked_stream_ok() const {
+    if (P.kmax < 0 || getenv("EXB_NO_MASKED_STREAM")) return false;
+    if (P.has_inj) {
+      for (int d = 0; d < D; ++d) {
+        int k = d == D - 1 ? P.inj_idx[d] : wavenumber_of(P.inj_idx[d], N);
+        if ((k < 0 ? -k : k) > P.kmax) return false;
+      }
+    }
+    return true;
+  }
   int col_fwd(cudaStream_t st, long long batch, int mode, int stage, const cpx<T>* wfwd, cpx<T>* nl_out,
               const StateBufs<T>& sb) {
     ColParams<T> p;
@@ -565,6 +589,20 @@ template <class T> struct PlanImpl : exb_plan {
     col_geom(p, 0);
     p.fpitch = Nhp;
     p.fM = Mf;
+    // last stage: the dealiased modes (u+ = exp(dt L) u) go through a streaming pass instead of the tiled epilogue
+    const bool masked_stream = fast_nd && mode == COL_FWD_EPI && stage == K.order - 1 && masked_stream_ok();
+    p.masked_external = masked_stream ? 1 : 0;
+    if (masked_stream) {
+      const long long rows = M / Nh;
+      const int n1 = nranks > 1 ? nloc : N;
+      long long bchunk = batch;
+      while (rows / 8 * ((batch + bchunk - 1) / bchunk) < 4LL * sm_count && bchunk > 4) bchunk = (bchunk + 1) / 2;
+      dim3 grid((unsigned)((rows + 7) / 8), (unsigned)((batch + bchunk - 1) / bchunk));
+      etdrk_masked_linear_kernel<T><<<grid, 256, 0, st>>>(K, sb.U, sb.OUT, C, D, N, Nh, P.kmax, n1, P.i1_off, rows, batch,
+                                                         (int)bchunk);
+      ++launches;
+      CUDA_OK(cudaGetLastError());
+    }
     {  // coefficient tables this stage reads (E or E/2 complex + one or more real tables) vs the L2 (126 MB)
       static const char* env = getenv("EXB_EPI_BATCH_FASTEST");
       const size_t table_bytes = (size_t)K.E * M * (sizeof(cpx<T>) + sizeof(T));
@@ -1140,6 +1178,7 @@ int exb_rollout(exb_plan* plan, void* stream, int64_t batch, int64_t n_saved, in
   return plan->rollout((cudaStream_t)stream, batch, n_saved, substeps, flags, u0, out, ws);
 }
 int64_t exb_launch_count(const exb_plan* plan) { return plan ? plan->launches : 0; }
+int exb_plan_fused_ok(const exb_plan* plan) { return plan ? plan->fused_ok() : 0; }
 int exb_metric_sums(void* stream, int32_t dtype, int64_t nfields, int64_t npoints, const void* a, const void* b,
                     double p, double* out) {
   if (nfields < 1 || npoints < 1 || !a || !out) return fail(EXB_EINVAL, "exb_metric_sums: bad arguments");

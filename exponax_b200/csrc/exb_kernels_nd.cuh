@@ -43,6 +43,7 @@ template <class T> struct ColParams {
   // State buffers and coefficient tables are always dense (pitch N/2+1, stride M).  0 = dense (generic kernels, slabs).
   int fpitch;
   long long fM;
+  int masked_external;     // fast COL_FWD_EPI: the dealiased modes are advanced by etdrk_masked_linear_kernel, skip them
   int seg_len;             // COL_PLAIN, slab transposes without pack/unpack: line entry i lives at
   long long seg_stride;    //   (i / seg_len) * seg_stride + (i % seg_len) * line_stride   (seg_len = 0: off)
   // peer output (fast kernels, COL_INV_PRO / COL_PLAIN of a slab plan): entry i of an output line is stored
@@ -297,6 +298,48 @@ template <class T> __global__ void row_pass_kernel(const RowParams<T> p) {
     unpack2(W + (size_t)g * N, N, k, X1, X2);
     out[((size_t)g * p.rows + r1) * Nh + k] = X1;
     if (has2) out[((size_t)g * p.rows + r2) * Nh + k] = X2;
+  }
+}
+
+// Last ETDRK stage, modes OUTSIDE the dealiasing mask: u+ = exp(dt L) u (etdrk_update_masked) as a streaming pass.
+// With the 2/3 rule these are 56 % (2-D) / 70 % (3-D) of all modes; inside the tiled epilogue pass they were 128-byte
+// pieces at a line stride with the loads serialised behind 64 registers (c4 stage 1: 3.3 ms vs 1.65 ms for stage 0,
+// long_scoreboard 27 per issue -- ncu r02g).  Here a warp owns one last-axis row: the masked part of the row is
+// contiguous (the whole row when a leading wavenumber is masked, else the entries k > kmax), exp(dt L) is loaded once
+// and reused for every trajectory and channel, all loads of a thread are independent.
+template <class T>
+__global__ void __launch_bounds__(256) etdrk_masked_linear_kernel(const EtdrkCoefs<T> K, const cpx<T>* U,   // (OUT may alias U)
+                                                                 cpx<T>* OUT, int C, int D, int N, int Nh,
+                                                                 int kmax, int n1, int i1_off, long long rows,
+                                                                 long long batch, int bchunk) {
+  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const int lane = threadIdx.x & 31;
+  int i0 = (int)r, i1 = 0;
+  if (D == 3) {
+    i0 = (int)(r / n1);
+    i1 = (int)(r - (long long)i0 * n1) + i1_off;
+  }
+  int k0 = wavenumber_of(i0, N), k1 = D == 3 ? wavenumber_of(i1, N) : 0;
+  k0 = k0 < 0 ? -k0 : k0;
+  k1 = k1 < 0 ? -k1 : k1;
+  const int start = (k0 > kmax || k1 > kmax) ? 0 : kmax + 1;
+  const long long b0 = (long long)blockIdx.y * bchunk;
+  const long long b1 = b0 + bchunk < batch ? b0 + bchunk : batch;
+  for (int e = start + lane; e < Nh; e += 32) {
+    const long long mode = r * Nh + e;
+    for (int c = 0; c < C; ++c) {
+      const cpx<T> Ev = K.exp_term[(long long)(K.E == 1 ? 0 : c) * K.M + mode];
+      long long b = b0;
+      for (; b + 4 <= b1; b += 4) {
+        cpx<T> u[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) u[q] = U[((size_t)(b + q) * C + c) * K.M + mode];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) OUT[((size_t)(b + q) * C + c) * K.M + mode] = Ev * u[q];
+      }
+      for (; b < b1; ++b) OUT[((size_t)b * C + c) * K.M + mode] = Ev * U[((size_t)b * C + c) * K.M + mode];
+    }
   }
 }
 

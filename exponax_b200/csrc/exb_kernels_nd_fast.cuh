@@ -295,8 +295,10 @@ col_fast_kernel(const ColParams<float> p) {
   const int order = STG ? 2 : p.K.order;
   const int stage = STG ? STG - 1 : p.stage;
   const bool masked_skip = MODE == COL_FWD_EPI && EXB_EPI_MASKED_SKIP && kmax >= 0 && !inj_masked;
-  // a tile of dealiased columns: N(u) == 0, the intermediate stages have nothing to do
-  if (masked_skip && !any_keep && stage != order - 1) return;
+  // a tile of dealiased columns: N(u) == 0, the intermediate stages have nothing to do (and the last one neither
+  // when the streaming pass etdrk_masked_linear_kernel advances the dealiased modes)
+  const bool masked_here = stage == order - 1 && !p.masked_external;
+  if (masked_skip && !any_keep && !masked_here) return;
   cpx<float> W[NFWD][8];
 #pragma unroll
   for (int g = 0; g < NFWD; ++g) {
@@ -317,7 +319,7 @@ col_fast_kernel(const ColParams<float> p) {
   for (int q = 0; q < 8; ++q) {
     const ModeK<float> m = mode_of(q);
     if (masked_skip && !m.keep) {
-      if (stage == order - 1) {
+      if (masked_here) {
 #pragma unroll
         for (int c = 0; c < C; ++c) {
           const size_t off = off0 + q * qstride + (size_t)c * p.M;

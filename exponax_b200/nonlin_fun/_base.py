@@ -100,10 +100,22 @@ class BaseNonlinearFun(ABC):
         lead = t.shape[: -D - 1]
         batch = int(np.prod(lead)) if lead else 1
         plan = self._eval_plan(C)
+        if not plan.fused_ok():
+            # 1-D grid too large for the fused shared-memory kernel: the reference's own formulation of this
+            # function on device arrays around the native transforms (no performance claim, README "eager paths")
+            return A.from_device(self._array_call(t), kind)
         out = A.torch.empty_like(t)
         ws = sp.workspace(plan.workspace_bytes(batch))
         nat.check(nat.lib().exb_nonlinear_fun(plan.handle, A.stream_ptr(), batch, A.ptr(t), A.ptr(out), A.ptr(ws)))
         return A.from_device(out, kind)
+
+    def _array_call(self, u_hat):
+        """Array-level evaluation (torch tensors, channel axis at -D-1) with `self.fft` / `self.ifft`."""
+        raise NotImplementedError("no array-level formulation of this nonlinear function")
+
+    def _dop(self):
+        """derivative operator as a device tensor, shape (D, ..., N//2+1)."""
+        return A.torch.as_tensor(np.asarray(self.derivative_operator), device="cuda")
 
     @abstractmethod
     def __call__(self, u_hat):

@@ -1,3 +1,4 @@
+from .. import _array as A
 from .. import _native as nat
 from ._base import BaseNonlinearFun
 
@@ -27,3 +28,23 @@ class ConvectionNonlinearFun(BaseNonlinearFun):
 
     def __call__(self, u_hat):
         return self._native_call(u_hat)
+
+    def _array_call(self, u_hat):
+        """exponax/nonlin_fun/_convection.py:140-245, the four variants, on (.., C, N.., N//2+1) tensors."""
+        t, D = A.torch, self.num_spatial_dims
+        dop = self._dop()
+        cax = -D - 1
+        if self.single_channel and self.conservative:        # -s/2 * sum_d d_d F[u^2]
+            u = self.ifft(u_hat)
+            return -self.scale * 0.5 * dop.sum(dim=0, keepdim=True) * self.fft(u * u)
+        if self.single_channel:                              # -s * F[u * sum_d d_d u]
+            u = self.ifft(u_hat)
+            grad = self.ifft(dop * u_hat)                    # (.., D, N..): u_hat has one channel
+            return -self.scale * self.fft(u * grad.sum(dim=cax, keepdim=True))
+        if self.conservative:                                # -s/2 * sum_d d_d F[u_c u_d]
+            u = self.ifft(u_hat)
+            outer = u.unsqueeze(cax) * u.unsqueeze(cax - 1)  # (.., C, D, N..)
+            return -self.scale * 0.5 * (dop * self.fft(outer)).sum(dim=cax)
+        u = self.ifft(u_hat)                                 # -s * F[sum_d u_d d_d u_c]
+        grad = self.ifft(dop * u_hat.unsqueeze(cax))         # (.., C, D, N..)
+        return -self.scale * self.fft((u.unsqueeze(cax - 1) * grad).sum(dim=cax))

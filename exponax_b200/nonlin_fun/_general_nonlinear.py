@@ -35,3 +35,8 @@ class GeneralNonlinearFun(BaseNonlinearFun):
 
     def __call__(self, u_hat):
         return self._native_call(u_hat)
+
+    def _array_call(self, u_hat):
+        """exponax/nonlin_fun/_general_nonlinear.py:111-119: the sum of the three sub-functions."""
+        return (self.square_nonlinear_fun._array_call(u_hat) + self.convection_nonlinear_fun._array_call(u_hat)
+                + self.gradient_norm_nonlinear_fun._array_call(u_hat))

@@ -18,3 +18,13 @@ class GradientNormNonlinearFun(BaseNonlinearFun):
 
     def __call__(self, u_hat):
         return self._native_call(u_hat)
+
+    def _array_call(self, u_hat):
+        """exponax/nonlin_fun/_gradient_norm.py:84-101."""
+        D = self.num_spatial_dims
+        cax = -D - 1
+        grad = self.ifft(self._dop() * u_hat.unsqueeze(cax))     # (.., C, D, N..)
+        sq = (grad * grad).sum(dim=cax)
+        if self.zero_mode_fix:
+            sq = sq - sq.mean(dim=tuple(range(-D, 0)), keepdim=True)
+        return -self.scale * 0.5 * self.fft(sq)

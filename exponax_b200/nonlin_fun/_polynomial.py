@@ -15,3 +15,11 @@ class PolynomialNonlinearFun(BaseNonlinearFun):
 
     def __call__(self, u_hat):
         return self._native_call(u_hat)
+
+    def _array_call(self, u_hat):
+        """exponax/nonlin_fun/_polynomial.py:64-76."""
+        u = self.ifft(u_hat)
+        acc = 0.0 * u
+        for k, c in enumerate(self.coefficients):
+            acc = acc + c * u**k
+        return self.fft(acc)

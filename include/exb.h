@@ -253,6 +253,12 @@ int exb_fourier_sums(exb_plan *plan, void *stream, int64_t nfields, const void *
 int exb_peak_fp32(void *stream, double *tflops);
 int exb_peak_smem(void *stream, double *gbs);
 
+/* 1 when the fused entry points (exb_step, exb_step_fourier, exb_rollout, exb_nonlinear_fun) are available for
+   this plan; 0 for 1-D grids whose state + ETDRK stage buffers do not fit the shared memory of one SM: those plans
+   still serve exb_fft / exb_ifft, and the host evaluates the stage formulas (exponax/etdrk/_etdrk_{0..4}.py) and
+   the nonlinear function (exponax/nonlin_fun/*.py) around them with device-array arithmetic. */
+int exb_plan_fused_ok(const exb_plan *plan);
+
 /* number of kernel launches issued through this plan so far (bench bookkeeping) */
 int64_t exb_launch_count(const exb_plan *plan);
 

@@ -738,10 +738,36 @@ def test_large_1d_grids(N):
     assert rel(got, per_sample(ox.repeat(ost, 3), u0)) < 3e-5
 
 
-def test_1d_grid_beyond_shared_memory_is_rejected_loudly():
-    st = ex.stepper.Burgers(1, 1.0, 16384, 1e-3)
+@pytest.mark.parametrize("name,kw,N,order,x64", [
+    ("Burgers", dict(diffusivity=0.05), 8192, 2, False),                 # f32: persistent kernel fits up to N ~ 4000
+    ("KuramotoSivashinskyConservative", dict(), 6000, 2, False),         # non power of two
+    ("KortewegDeVries", dict(), 4096, 4, True),                          # f64 ETDRK4: fits up to N ~ 1600
+    ("KuramotoSivashinsky", dict(), 4096, 3, True),                      # gradient norm
+    ("FisherKPP", dict(reactivity=2.0), 8192, 2, False),                 # polynomial
+])
+def test_1d_grids_beyond_the_persistent_kernel(name, kw, N, order, x64):
+    """1-D grids whose state + stage buffers do not fit shared memory: the plan still serves
+    the native transforms (exb_plan_fused_ok == 0) and the stage formulas run on device arrays around them, as the
+    reference's own formulation does -- step, batched step and rollout vs the oracle."""
+    ex.config.update("enable_x64", x64)
+    dt_ = np.float64 if x64 else np.float32
+    L, dt = 20.0, 1e-3
+    u0 = ic(1, N, [0, 1], dtype=dt_)
+    st = getattr(ex.stepper, name)(1, L, N, dt, order=order, **kw)
+    ost = getattr(ox, name)(1, L, N, dt, order=order, dtype=dt_, **kw) if x64 else getattr(ox, name)(1, L, N, dt, order=order, **kw)
+    assert st._plan() is None and st._integrator._plan(1, N, L).fused_ok() is False
+    tol = 1e-11 if x64 else F32_STEP
+    got = host(st(dev(u0[0])))
+    assert rel(got, ost(u0[0])) < tol, rel(got, ost(u0[0]))
+    trj = host(ex.vmap(ex.rollout(st, 3, include_init=True))(dev(u0)))
+    ref = per_sample(ox.rollout(ost, 3, include_init=True), u0)
+    assert trj.shape == (2, 4, 1, N) and rel(trj, ref) < 5 * tol
+
+
+def test_1d_grid_beyond_the_transform_kernel_is_rejected_loudly():
+    st = ex.stepper.Burgers(1, 1.0, 65536, 1e-3)
     with pytest.raises(NotImplementedError, match="shared memory"):
-        st(dev(np.zeros((1, 16384), np.float32)))
+        st(dev(np.zeros((1, 65536), np.float32)))
 
 
 # ------------------------------------------------------------------ fast 1-D kernel coverage (N = 64, 256)
