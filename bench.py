@@ -82,6 +82,8 @@ def run_c5(args, w, rank, world, local_rank):
     slab.raw_exchange = not args.no_raw_exchange
     if args.no_peer_stores:
         slab.peer_stores = False
+    if args.peer_stores:
+        slab.peer_stores = True
     t_ctor = time.time() - t0
     # Taylor-Green + small-mode perturbation generated on the device, slab by slab (never on the host)
     n = N // world
@@ -573,6 +575,8 @@ def main():
     ap.add_argument("--no-raw-exchange", action="store_true", help="c5: pack / unpack copies around the all-to-all")
     ap.add_argument("--no-peer-stores", action="store_true",
                     help="c5: NCCL all-to-all transposes instead of pass kernels storing into peer memory")
+    ap.add_argument("--peer-stores", action="store_true",
+                    help="c5: pass kernels store into peer memory over NVLink instead of the NCCL all-to-all (opt-in)")
     ap.add_argument("--no-overlap", action="store_true", help="c5: do not pipeline transposes against passes")
     args = ap.parse_args()
 

@@ -15,6 +15,7 @@ from . import _distributed as distributed
 from . import etdrk, ic, metrics, nonlin_fun, stepper
 from ._base_stepper import BaseStepper
 from ._config import config
+from ._ensemble import StepperEnsemble
 from ._forced_stepper import ForcedStepper
 from ._repeated_stepper import RepeatedStepper
 from ._slab import SlabStepper
@@ -26,6 +27,7 @@ __version__ = "0.1.0"
 __all__ = [
     "BaseStepper",
     "ForcedStepper",
+    "StepperEnsemble",
     "RepeatedStepper",
     "SlabStepper",
     "build_ic_set",

@@ -157,15 +157,58 @@ class BaseStepper(ABC):
             src = out
         return A.from_device(out, kind)
 
+    def _forcing_hat(self, f, lead, n, constant, time_first):
+        """Fourier transform of a forcing + its (step, trajectory) strides in complex elements.
+        constant: f is (C, N..) [shared] or lead + (C, N..); otherwise (n, C, N..) [shared], lead + (n, C, N..)
+        (`vmap(rollout(..))`) or (n,) + lead + (C, N..) (`rollout(vmap(..))`, time_first)."""
+        tf, _ = A.to_device(f, self._dtype)
+        st = self._state_shape()
+        per = int(np.prod(self._fourier_shape()))
+        fl = tuple(tf.shape[:-len(st)])
+        if tuple(tf.shape[-len(st):]) != tuple(st):
+            raise ValueError(f"Expected a forcing with trailing shape {st}, got {tuple(tf.shape)}")
+        batch = int(np.prod(lead)) if lead else 1
+        if constant:
+            if fl == ():
+                strides = (0, 0)
+            elif fl == tuple(lead):
+                strides = (0, per)
+            else:
+                raise ValueError(f"constant forcing of shape {tuple(tf.shape)} does not match the batch shape {lead}")
+        else:
+            if fl == (n,):
+                strides = (per, 0)
+            elif fl == tuple(lead) + (n,):
+                strides = (per, n * per)
+            elif time_first and fl == (n,) + tuple(lead):
+                strides = (batch * per, per)
+            else:
+                raise ValueError(f"forcing of shape {tuple(tf.shape)}: expected a leading time axis of length {n}")
+        fh = sp.fft(tf, num_spatial_dims=self.num_spatial_dims)
+        return fh.contiguous(), strides
+
     def _rollout_batched(self, u0, n: int, *, include_init: bool, layout_tb: bool, final_only: bool,
-                         substeps: int = 1, spectral_carry: bool = False, cuda_graph: bool = False):
+                         substeps: int = 1, spectral_carry: bool = False, cuda_graph: bool = False,
+                         forcing=None, forcing_constant: bool = True):
         """Fused `rollout`/`repeat` over a batch: u0 (B.., C, N..) -> (B.., T, C, N..) /
-        (T, B.., C, N..) / (B.., C, N..)."""
+        (T, B.., C, N..) / (B.., C, N..).  `forcing`: ForcedStepper semantics, `step(u + dt f)` every step."""
         t, kind = A.to_device(u0, self._dtype)
         lead, batch = self._split_batch(t, self._state_shape())
         plan = self._plan()
         if plan is None:
             raise NotImplementedError("fused rollout needs a native nonlinear function")
+        if forcing is not None:
+            fh, (fstep, fbatch) = self._forcing_hat(forcing, lead, n, forcing_constant, layout_tb)
+            T = 1 if final_only else n + (1 if include_init else 0)
+            st = self._state_shape()
+            shape = lead + st if final_only else ((T,) + lead + st if layout_tb else lead + (T,) + st)
+            out = A.torch.empty(shape, dtype=t.dtype, device="cuda")
+            flags = ((nat.ROLLOUT_INCLUDE_INIT if include_init else 0) | (nat.ROLLOUT_LAYOUT_TB if layout_tb else 0)
+                     | (nat.ROLLOUT_FINAL_ONLY if final_only else 0))
+            ws = sp.workspace(plan.workspace_bytes(batch))
+            nat.check(nat.lib().exb_rollout_forced(plan.handle, A.stream_ptr(), batch, n, 1, flags, A.ptr(t), A.ptr(out),
+                                                   A.ptr(ws), A.ptr(fh), fstep, fbatch, float(self.dt)))
+            return A.from_device(out, kind)
         T = 1 if final_only else n + (1 if include_init else 0)
         st = self._state_shape()
         if final_only:

@@ -40,7 +40,7 @@ class ExbDesc(C.Structure):
         ("zero_mode_fix", C.c_int32),
         ("nl_scale", C.c_double),
         ("n_poly", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("table_sets", C.c_int32),
         ("poly", C.c_double * EXB_MAX_POLY),
         ("general_scales", C.c_double * 3),
         ("has_injection", C.c_int32),
@@ -52,7 +52,9 @@ class ExbDesc(C.Structure):
         ("slab_nranks", C.c_int32),
         ("slab_rank", C.c_int32),
         ("tables_on_device", C.c_int32),
-        ("reserved1", C.c_int32),
+        ("slab_cyclic", C.c_int32),
+        ("reserved2", C.c_int32),
+        ("lin_matrix", C.c_int32),
     ]
 
 
@@ -73,6 +75,8 @@ SYMBOLS = {
     "exb_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "exb_rollout": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_uint32,
                               C.c_void_p, C.c_void_p, C.c_void_p]),
+    "exb_rollout_forced": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_uint32,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_double]),
     "exb_launch_count": (C.c_int64, [C.c_void_p]),
     "exb_plan_fused_ok": (C.c_int, [C.c_void_p]),
     "exb_peak_fp32": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
@@ -83,6 +87,7 @@ SYMBOLS = {
     "exb_slab_pass_peer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                      C.POINTER(C.c_void_p)]),
     "exb_plan_nl_fields": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "exb_plan_field_pitch": (C.c_int, [C.c_void_p]),
     "exb_ic_shape": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_double, C.c_double,
                                C.c_double]),
     "exb_ic_normalize": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,
@@ -140,7 +145,7 @@ class Plan:
     """Owns one exb_plan (device tables live until the object is garbage collected)."""
 
     def __init__(self, *, D, N, C_, E, order, dtype, L, kmax, nl, exp_term, half_exp_term=None, coefs=(),
-                 slab=(1, 0)):
+                 slab=(1, 0), lin_matrix=False, table_sets=1, slab_cyclic=False):
         rd = np.float32 if dtype == np.float32 else np.float64
         cd = np.complex64 if rd == np.float32 else np.complex128
         d = ExbDesc()
@@ -171,6 +176,9 @@ class Plan:
                 d.injection_index[i] = int(idx[i])
             d.injection_value = float(inj[1])
         d.slab_nranks, d.slab_rank = int(slab[0]), int(slab[1])
+        d.lin_matrix = int(bool(lin_matrix))
+        d.slab_cyclic = int(bool(slab_cyclic))
+        d.table_sets = int(table_sets)
         self._keep = []
 
         on_device = hasattr(exp_term, "is_cuda") and exp_term.is_cuda

@@ -59,8 +59,12 @@ def transpose_a_to_b(x: torch.Tensor, group=None, out: torch.Tensor | None = Non
         return out
     if out is None:
         out = torch.empty((F, N, n, K), dtype=x.dtype, device=x.device)
+    from ._spectral import SLAB_CYCLIC
     for f in range(F):
-        send = x[f].view(n, P, n, K).permute(1, 0, 2, 3).contiguous()      # [dest][x][k1][K]
+        if SLAB_CYCLIC:   # axis-1 index i lives on rank i % P at local position i // P
+            send = x[f].view(n, n, P, K).permute(2, 0, 1, 3).contiguous()  # [dest][x][k1 local][K]
+        else:
+            send = x[f].view(n, P, n, K).permute(1, 0, 2, 3).contiguous()  # [dest][x][k1][K]
         dist.all_to_all_single(out[f].view(P, n, n, K), send, group=group)  # [src][x_src][k1][K]: x_global = src*n + x
     return out
 
@@ -77,26 +81,58 @@ def transpose_b_to_a(x: torch.Tensor, group=None, out: torch.Tensor | None = Non
         return out
     if out is None:
         out = torch.empty((F, n, N, K), dtype=x.dtype, device=x.device)
+    from ._spectral import SLAB_CYCLIC
     recv = torch.empty((P, n, n, K), dtype=x.dtype, device=x.device)
     for f in range(F):
         dist.all_to_all_single(recv, x[f].view(P, n, n, K), group=group)   # [src][x][k1_src][K]
-        out[f].view(n, P, n, K).copy_(recv.permute(1, 0, 2, 3))             # k1_global = src*n + k1
+        if SLAB_CYCLIC:
+            out[f].view(n, n, P, K).copy_(recv.permute(1, 2, 0, 3))         # k1_global = k1 * P + src
+        else:
+            out[f].view(n, P, n, K).copy_(recv.permute(1, 0, 2, 3))         # k1_global = src*n + k1
     return out
 
 
-def exchange_b_to_a_raw(x_b: torch.Tensor, out_a: torch.Tensor, group=None):
+def kept_ranks(N: int, P: int, kmax: int):
+    """ranks whose axis-1 index range [r N/P, (r+1) N/P) holds at least one wavenumber |k1| <= kmax (all when
+    kmax < 0).  With the 2/3 rule on 8 ranks, ranks 3 and 4 own nothing but dealiased modes."""
+    n = N // P
+    if kmax < 0:
+        return [True] * P
+    i = np.arange(N)
+    k = np.where(i < (N + 1) // 2, i, i - N)                 # fftfreq ordering (exponax/_spectral.py:40-41)
+    return [bool((np.abs(k[r * n:(r + 1) * n]) <= kmax).any()) for r in range(P)]
+
+
+def exchange_b_to_a_raw(x_b: torch.Tensor, out_a: torch.Tensor, group=None, kept=None):
     """All-to-all of ONE field from the spectral slab (N, n, K) straight into `out_a`, which then holds the
-    raw peer-major layout [peer][x][k1 within peer][K] (EXB_SLAB_SEGMENTED): no pack, no unpack."""
+    raw peer-major layout [peer][x][k1 within peer][K] (EXB_SLAB_SEGMENTED): no pack, no unpack.
+    `kept[r]` False: rank r's axis-1 range is entirely outside the dealiasing mask -- it neither sends nor is its
+    block received (the consumers read masked line entries as zeros without loading them)."""
     rank, P = _group_info(group)
     N, n, K = x_b.shape
-    dist.all_to_all_single(out_a.view(P, n, n, K), x_b.view(P, n, n, K), group=group)
+    if kept is None or all(kept):
+        dist.all_to_all_single(out_a.view(P, n, n, K), x_b.view(P, n, n, K), group=group)
+        return
+    src, dst = x_b.view(P, n, n, K), out_a.view(P, n, n, K)
+    empty = x_b.new_empty(0)
+    send = [src[p] if kept[rank] else empty for p in range(P)]
+    recv = [dst[p] if kept[p] else empty for p in range(P)]
+    dist.all_to_all(recv, send, group=group)
 
 
-def exchange_a_to_b_raw(x_a: torch.Tensor, out_b: torch.Tensor, group=None):
-    """Inverse of `exchange_b_to_a_raw`: raw peer-major A buffer -> spectral slab (N, n, K)."""
+def exchange_a_to_b_raw(x_a: torch.Tensor, out_b: torch.Tensor, group=None, kept=None):
+    """Inverse of `exchange_b_to_a_raw`: raw peer-major A buffer -> spectral slab (N, n, K); blocks destined to
+    ranks whose axis-1 range is dealiased away are not sent."""
     rank, P = _group_info(group)
     N, n, K = out_b.shape
-    dist.all_to_all_single(out_b.view(P, n, n, K), x_a.view(P, n, n, K), group=group)
+    if kept is None or all(kept):
+        dist.all_to_all_single(out_b.view(P, n, n, K), x_a.view(P, n, n, K), group=group)
+        return
+    src, dst = x_a.view(P, n, n, K), out_b.view(P, n, n, K)
+    empty = x_a.new_empty(0)
+    send = [src[p] if kept[p] else empty for p in range(P)]
+    recv = [dst[p] if kept[rank] else empty for p in range(P)]
+    dist.all_to_all(recv, send, group=group)
 
 
 class _ShapeOnly:
@@ -156,7 +192,8 @@ class SlabStepper:
         k_other = np.fft.fftfreq(N, 1 / N).astype(rd)
         k_last = np.fft.rfftfreq(N, 1 / N).astype(rd)
         d0 = torch.as_tensor(scale * k_other, device="cuda", dtype=td).view(N, 1, 1)
-        d1 = torch.as_tensor(scale * k_other[rank * n:(rank + 1) * n], device="cuda", dtype=td).view(1, n, 1)
+        mine = sp.slab_indices(rank, max(P, 1), N) if P > 1 else slice(None)
+        d1 = torch.as_tensor(scale * k_other[mine], device="cuda", dtype=td).view(1, n, 1)
         d2 = torch.as_tensor(scale * k_last, device="cuda", dtype=td).view(1, 1, N // 2 + 1)
         lap = -(d0 * d0) - (d1 * d1) - (d2 * d2)          # sum_d (i k_d)^2, real
         lin = (rd(diffusivity) * lap + rd(drag)).to(A.cplx_t(rd)).unsqueeze(0)
@@ -164,7 +201,9 @@ class SlabStepper:
         cutoff = dealiasing_fraction * (N // 2) - 1         # nonlin_fun/_base.py:59-71
         kmax = sp.dealias_kmax(N, cutoff, rd)
         inj = None
-        if injection_mode is not None and 0 <= injection_mode - rank * n < n and 0 < injection_mode < N // 2:
+        owned = (injection_mode is not None
+                 and (P <= 1 or injection_mode in range(N)[sp.slab_indices(rank, max(P, 1), N)]))
+        if injection_mode is not None and owned and 0 < injection_mode < N // 2:
             # (0, +k_f, 0) on channel 0, value gamma * N^3 / 2 (coef_extraction scaling), SURVEY App. B.14
             inj = ((0, int(injection_mode), 0), float(injection_scale) * N * (N / 2) * N)
         nl = _LeanNonlinearFun({"kind": nat.NL_PROJECTED_3D, "injection": inj}, kmax)
@@ -199,8 +238,14 @@ class SlabStepper:
         # A pass CTA owns an [N x TW] tile, so a remote store is TW * 8 contiguous bytes: measured +7 % at
         # 1024^3 on 2 GPUs (TW = 4: 109 vs 117 ms) but -38 % at 2048^3 on 8 GPUs (TW = 2, 16-byte NVLink writes:
         # 539 vs 391 ms) -> on by default only up to N = 1024; EXB_SLAB_PEER_STORES=1 / 0 forces it on / off.
+        # Round 2: with the compact field pitch the NCCL all-to-all ships 2/3 of the bytes and wins at every size
+        # measured (1024^3 on 2 GPUs: 76.8 ms vs 83.5 ms with peer stores) -> peer stores are opt-in.
         env = os.environ.get("EXB_SLAB_PEER_STORES", "auto")
-        self.peer_stores = env == "1" or (env != "0" and N <= 1024)
+        self.peer_stores = env == "1"
+        self.prune_peers = os.environ.get("EXB_SLAB_PRUNE_PEERS", "1") != "0"
+        from ._spectral import SLAB_CYCLIC
+        self.cyclic = bool(SLAB_CYCLIC) and self.P > 1
+        self.Kp, self.kept = self.Nh, None
 
     # ---- plan with the LOCAL slices of the coefficient tables --------------------------------
     def _local(self, arr):
@@ -209,10 +254,11 @@ class SlabStepper:
                 raise ValueError(f"stepper was built for slab {self.stepper._slab}, process group says "
                                  f"{(self.rank, self.P)}")
             return arr if hasattr(arr, "is_cuda") else np.ascontiguousarray(arr)
+        from ._spectral import slab_indices
+        sl = slab_indices(self.rank, self.P, self.N)
         if hasattr(arr, "is_cuda"):
-            return arr[:, :, self.rank * self.n:(self.rank + 1) * self.n, :].contiguous()
-        lo, hi = self.rank * self.n, (self.rank + 1) * self.n
-        return np.ascontiguousarray(arr[:, :, lo:hi, :])
+            return arr[:, :, sl, :].contiguous()
+        return np.ascontiguousarray(arr[:, :, sl, :])
 
     def plan(self):
         if self._plan is None:
@@ -225,11 +271,20 @@ class SlabStepper:
                 D=3, N=self.N, C_=self.Cn, E=it._linear_operator.shape[0], order=order, dtype=st._dtype,
                 L=st.domain_extent, kmax=nl._kmax if order > 0 else -1, nl=desc,
                 exp_term=self._local(it._exp_term), half_exp_term=None if half is None else self._local(half),
-                coefs=[self._local(c) for c in it._coef_list()], slab=(max(self.P, 1), self.rank))
+                coefs=[self._local(c) for c in it._coef_list()], slab=(max(self.P, 1), self.rank),
+                slab_cyclic=self.cyclic)
             ni, nf = C.c_int32(), C.c_int32()
             nat.check(nat.lib().exb_plan_nl_fields(self._plan.handle, C.byref(ni), C.byref(nf)))
             self.n_inv, self.n_fwd = ni.value, nf.value
             self.order = order if desc.get("kind") != nat.NL_ZERO else 0
+            # last-axis pitch of the exchanged field buffers: only the wavenumbers inside the dealiasing mask when
+            # the fast kernels run (exb_plan_field_pitch) -> every transpose ships ~2/3 of the bytes; and the ranks
+            # whose axis-1 range is dealiased away take no part in the transposes
+            self.Kp = int(nat.lib().exb_plan_field_pitch(self._plan.handle))
+            kmax = nl._kmax if order > 0 else -1
+            # (block distribution only: under the cyclic one every rank owns kept wavenumbers)
+            self.kept = (kept_ranks(self.N, self.P, kmax)
+                         if (self.Kp != self.Nh and self.prune_peers and not self.cyclic) else None)
         return self._plan
 
     def release_buffers(self):
@@ -237,15 +292,17 @@ class SlabStepper:
         self._bufs.clear()
         torch.cuda.empty_cache()
 
-    def _buf(self, name, nfields, real=False):
-        key = (name, nfields, real)
+    def _buf(self, name, nfields, real=False, fields=False):
+        """fields: an exchanged field buffer (last-axis pitch `Kp`); otherwise a dense spectral / physical slab."""
+        key = (name, nfields, real, fields)
         b = self._bufs.get(key)
         if b is None:
             rd = self.stepper._dtype
             if real:
                 b = torch.zeros((nfields, self.n, self.N, self.N), dtype=A.real_t(rd), device="cuda")
             else:
-                b = torch.zeros((nfields, self.n, self.N, self.Nh), dtype=A.cplx_t(rd), device="cuda")
+                b = torch.zeros((nfields, self.n, self.N, self.Kp if fields else self.Nh), dtype=A.cplx_t(rd),
+                                device="cuda")
             self._bufs[key] = b
         return b
 
@@ -312,7 +369,7 @@ class SlabStepper:
             # all-to-all.  Hazards: a peer overwrites my winv_a (wfwd_b) only after the barrier that follows
             # my last read of it in stream order, see DESIGN.md section 5.
             lib, h, st = nat.lib(), self.plan().handle, A.stream_ptr()
-            wfwd_a = self._buf("wfwd_a", self.n_fwd)
+            wfwd_a = self._buf("wfwd_a", self.n_fwd, fields=True)
             try:
                 for s in range(self.order):
                     si = etdrk_stage_input(self.order, s)
@@ -333,17 +390,20 @@ class SlabStepper:
                 self.peer_stores = False
         # the B-layout buffer is shared by the inverse fields and (later in the stage) the forward fields
         nb = max(self.n_inv, self.n_fwd)
-        wb = self._buf("w_b", nb)
-        winv_b = wb[:self.n_inv].view(self.n_inv, self.N, self.n, self.Nh)
-        wfwd_b = wb[:self.n_fwd].view(self.n_fwd, self.N, self.n, self.Nh)
-        winv_a = self._buf("winv_a", self.n_inv)
-        wfwd_a = self._buf("wfwd_a", self.n_fwd)
+        wb = self._buf("w_b", nb, fields=True)
+        winv_b = wb[:self.n_inv].view(self.n_inv, self.N, self.n, self.Kp)
+        wfwd_b = wb[:self.n_fwd].view(self.n_fwd, self.N, self.n, self.Kp)
+        winv_a = self._buf("winv_a", self.n_inv, fields=True)
+        wfwd_a = self._buf("wfwd_a", self.n_fwd, fields=True)
         overlap = self.overlap and self.P > 1
         # multi-rank: layout A stays in the raw all-to-all (peer-major) order for the whole N(u) evaluation --
         # the axis-1 passes address it with segmented lines, the row pass is order-agnostic
         seg = nat.SLAB_SEGMENTED if (self.raw_exchange and self.P > 1) else 0
-        b2a = exchange_b_to_a_raw if seg else (lambda xb, oa, group=None: transpose_b_to_a(xb[None], group, out=oa[None]))
-        a2b = exchange_a_to_b_raw if seg else (lambda xa, ob, group=None: transpose_a_to_b(xa[None], group, out=ob[None]))
+        kept = self.kept
+        b2a = ((lambda xb, oa, group=None: exchange_b_to_a_raw(xb, oa, group, kept)) if seg
+               else (lambda xb, oa, group=None: transpose_b_to_a(xb[None], group, out=oa[None])))
+        a2b = ((lambda xa, ob, group=None: exchange_a_to_b_raw(xa, ob, group, kept)) if seg
+               else (lambda xa, ob, group=None: transpose_a_to_b(xa[None], group, out=ob[None])))
         for s in range(self.order):
             si = etdrk_stage_input(self.order, s)
             src = uh if si < 0 else S[si]
@@ -409,7 +469,7 @@ class SlabStepper:
         try:
             import torch.distributed._symmetric_memory as symm
             group = self.group if self.group is not None else dist.group.WORLD
-            per_field = self.N * self.n * self.Nh
+            per_field = self.N * self.n * self.Kp
             rt = A.real_t(self.stepper._dtype)
 
             def make(nfields, shape):
@@ -418,8 +478,8 @@ class SlabStepper:
                 ptrs = (ctypes.c_void_p * self.P)(*[int(x) for x in hdl.buffer_ptrs])
                 return torch.view_as_complex(flat.view(-1, 2)).view((nfields,) + shape), hdl, ptrs
 
-            winv_a, hdl_inv, ptrs_inv = make(self.n_inv, (self.n, self.N, self.Nh))
-            wfwd_b, hdl_fwd, ptrs_fwd = make(self.n_fwd, (self.N, self.n, self.Nh))
+            winv_a, hdl_inv, ptrs_inv = make(self.n_inv, (self.n, self.N, self.Kp))
+            wfwd_b, hdl_fwd, ptrs_fwd = make(self.n_fwd, (self.N, self.n, self.Kp))
             peer = dict(winv_a=winv_a, hdl_inv=hdl_inv, ptrs_inv=ptrs_inv, wfwd_b=wfwd_b, hdl_fwd=hdl_fwd,
                         ptrs_fwd=ptrs_fwd)
         except Exception as e:  # noqa: BLE001 -- any failure means: no peer memory here

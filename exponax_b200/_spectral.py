@@ -7,6 +7,8 @@ Mirrors exponax/_spectral.py (function names, arguments, shapes, error messages)
 """
 from __future__ import annotations
 
+import os
+
 from typing import Literal
 
 import numpy as np
@@ -18,6 +20,17 @@ from ._config import complex_dtype, real_dtype
 
 # ---- slab context (config c5): constructors build only the LOCAL spectral slab -------------------
 _SLAB = None  # (rank, nranks): 3-D spectral arrays are restricted to axis-1 indices of this rank
+# Which axis-1 indices a rank owns: cyclic (r, r + P, r + 2P, ...; default) or block ([r N/P, (r+1) N/P)).  With a
+# dealiasing mask the cyclic distribution gives every rank the same share of the wavenumbers inside the mask -- under
+# the block distribution two of 8 ranks own nothing but dealiased modes and idle through the axis-0 passes and the
+# transposes (EXB_SLAB_CYCLIC=0 restores it; all ranks must agree).
+SLAB_CYCLIC = os.environ.get("EXB_SLAB_CYCLIC", "1") != "0"
+
+
+def slab_indices(rank: int, nranks: int, num_points: int):
+    """global axis-1 indices owned by `rank` (a slice object)."""
+    n = num_points // nranks
+    return slice(rank, None, nranks) if SLAB_CYCLIC else slice(rank * n, (rank + 1) * n)
 
 
 class slab_context:
@@ -52,8 +65,7 @@ def _slab_slice(vec, num_spatial_dims, num_points):
     rank, nranks = _SLAB
     if num_points % nranks:
         raise ValueError(f"num_points={num_points} must be divisible by the number of slab ranks ({nranks})")
-    n = num_points // nranks
-    return vec[rank * n:(rank + 1) * n]
+    return vec[slab_indices(rank, nranks, num_points)]
 
 
 def build_wavenumbers(num_spatial_dims: int, num_points: int, *, indexing: str = "ij", dtype=None):

@@ -15,6 +15,8 @@ import numpy as np
 from . import _array as A
 from ._base_stepper import BaseStepper
 from ._config import real_dtype
+from ._ensemble import StepperEnsemble
+from ._forced_stepper import ForcedStepper
 from ._repeated_stepper import RepeatedStepper
 
 
@@ -44,6 +46,10 @@ class vmap:
                 return fn._step_batched(x)
             if isinstance(fn, (_Rollout, _Repeat)):
                 return fn._call(x, batched=True)
+        elif isinstance(fn, (_Rollout, _Repeat)) and fn.takes_aux and _forced_target(fn.stepper_fn) is not None:
+            return fn._call(x, *aux, batched=True)      # forced rollouts: one fused call for the whole batch
+        elif isinstance(fn, ForcedStepper) and _forced_target(fn) is not None and len(aux) == 1:
+            return fn.step(x, aux[0])
         if hasattr(fn, "_batched"):   # functions with a native batched form (ex.get_spectrum, ex.metrics.*)
             return fn._batched(x, *aux)
         outs = [fn(x[i], *(a[i] for a in aux)) for i in range(len(x))]
@@ -116,6 +122,9 @@ def _native_target(stepper_fn):
     sub = 1
     if isinstance(stepper_fn, RepeatedStepper):
         sub, stepper_fn = stepper_fn.num_sub_steps, stepper_fn.stepper
+    if isinstance(stepper_fn, StepperEnsemble):
+        # an ensemble maps (S, C, N..) -> (S, C, N..): batched by construction, trajectories come out time-major
+        return (stepper_fn, sub, True) if stepper_fn._plan() is not None else None
     if isinstance(stepper_fn, BaseStepper) and stepper_fn._plan_available():
         # a subclass that overrides the stepping methods must be honoured: the reference's scan calls
         # `stepper_fn(u)` every iteration (exponax/_utils.py:167-172), the fused kernel would bypass the override
@@ -123,6 +132,20 @@ def _native_target(stepper_fn):
         if (t.step is BaseStepper.step and t.step_fourier is BaseStepper.step_fourier
                 and t.__call__ is BaseStepper.__call__):
             return stepper_fn, sub, vm
+    return None
+
+
+def _forced_target(stepper_fn):
+    """(base stepper, vmapped?) if `stepper_fn` is a ForcedStepper (or vmap of one) around a natively planned stepper:
+    the forcing then rides inside the fused rollout (exb_rollout_forced)."""
+    vm = False
+    if isinstance(stepper_fn, vmap):
+        vm, stepper_fn = True, stepper_fn.fn
+    if isinstance(stepper_fn, ForcedStepper) and type(stepper_fn).step is ForcedStepper.step \
+            and type(stepper_fn).__call__ is ForcedStepper.__call__:
+        tgt = _native_target(stepper_fn.stepper)
+        if tgt is not None and tgt[1] == 1 and not tgt[2] and tgt[0]._plan() is not None:
+            return tgt[0], vm
     return None
 
 
@@ -139,6 +162,12 @@ class _Rollout:
         self.spectral_carry, self.cuda_graph = spectral_carry, cuda_graph
 
     def _call(self, u_0, *aux, batched=False):
+        if self.takes_aux and len(aux) == 1 and A.torch.cuda.is_available():
+            ft = _forced_target(self.stepper_fn)
+            if ft is not None:   # ForcedStepper: the forcing is added inside the fused rollout
+                st, vm = ft
+                return st._rollout_batched(u_0, self.n, include_init=self.include_init, layout_tb=vm and not batched,
+                                           final_only=False, forcing=aux[0], forcing_constant=self.constant_aux)
         tgt = None if self.takes_aux else _native_target(self.stepper_fn)
         if tgt is not None and A.torch.cuda.is_available():
             st, sub, vm = tgt
@@ -177,6 +206,12 @@ class _Repeat:
         self.spectral_carry, self.cuda_graph = spectral_carry, cuda_graph
 
     def _call(self, u_0, *aux, batched=False):
+        if self.takes_aux and len(aux) == 1 and self.n >= 1 and A.torch.cuda.is_available():
+            ft = _forced_target(self.stepper_fn)
+            if ft is not None:
+                st, vm = ft
+                return st._rollout_batched(u_0, self.n, include_init=False, layout_tb=False, final_only=True,
+                                           forcing=aux[0], forcing_constant=self.constant_aux)
         tgt = None if self.takes_aux else _native_target(self.stepper_fn)
         if tgt is not None and self.n >= 1 and A.torch.cuda.is_available():
             st, sub, vm = tgt

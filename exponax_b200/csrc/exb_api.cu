@@ -51,9 +51,13 @@ struct exb_plan {
   virtual int step(cudaStream_t st, int64_t batch, const void* in, void* out, void* ws) = 0;
   virtual int rollout(cudaStream_t st, int64_t batch, int64_t n_saved, int substeps, unsigned flags,
                       const void* u0, void* out, void* ws) = 0;
+  virtual int rollout_forced(cudaStream_t st, int64_t batch, int64_t n_saved, int substeps, unsigned flags,
+                             const void* u0, void* out, void* ws, const void* fhat, int64_t fstep, int64_t fbatch,
+                             double scale) = 0;
   virtual int slab_pass(cudaStream_t st, int pass, int nfields, int stage, const void* in, void* out,
                         const void* U, void* OUT, void* const* S) = 0;
   virtual void nl_fields(int* ni, int* nf) const = 0;
+  virtual int field_pitch() const = 0;
   virtual int slab_inv_pro_fields(cudaStream_t st, int f0, int nf, const void* in, void* out) = 0;
   virtual int slab_pass_peer(cudaStream_t st, int pass, int f0, int nf, const void* in, void* const* peers) = 0;
   virtual int fourier_sums(cudaStream_t st, int64_t nfields, const void* xh, double p, int low, int high,
@@ -148,7 +152,12 @@ template <class T> struct PlanImpl : exb_plan {
     if (D < 1 || D > 3) return fail(EXB_EINVAL, "num_spatial_dims must be 1, 2 or 3 (got %d)", D);
     if (N < 2) return fail(EXB_EINVAL, "num_points must be >= 2 (got %d)", N);
     if (C < 1 || C > EXB_MAXC) return fail(EXB_EUNSUPPORTED, "num_channels must be in 1..%d (got %d)", EXB_MAXC, C);
-    if (desc.lin_channels != 1 && desc.lin_channels != C)
+    if (desc.lin_matrix) {
+      if (desc.lin_channels != C * C) return fail(EXB_EINVAL, "lin_matrix needs lin_channels = num_channels^2");
+      if (desc.order != 0 || desc.nl_kind != EXB_NL_ZERO)
+        return fail(EXB_EINVAL, "lin_matrix is an order-0 feature (no nonlinear function)");
+      if (desc.slab_nranks > 1) return fail(EXB_EUNSUPPORTED, "lin_matrix is not available for slab plans");
+    } else if (desc.lin_channels != 1 && desc.lin_channels != C)
       return fail(EXB_EINVAL, "lin_channels must be 1 or num_channels");
     if (desc.order < 0 || desc.order > 4) return fail(EXB_EINVAL, "order %d not implemented", desc.order);
     M = Nh;
@@ -192,7 +201,9 @@ template <class T> struct PlanImpl : exb_plan {
     P.inj_val = (T)desc.injection_value;
     P.dscale = (T)(2.0 * M_PI / desc.domain_extent);
     P.scale = (T)desc.nl_scale;
-    P.i1_off = nranks > 1 ? desc.slab_rank * (N / nranks) : 0;
+    slab_cyclic = nranks > 1 && desc.slab_cyclic;
+    P.i1_mul = slab_cyclic ? nranks : 1;
+    P.i1_off = nranks > 1 ? (slab_cyclic ? desc.slab_rank : desc.slab_rank * (N / nranks)) : 0;
     for (int i = 0; i < EXB_MAX_POLY; ++i) P.poly[i] = (T)desc.poly[i];
     for (int i = 0; i < 3; ++i) P.gen[i] = (T)desc.general_scales[i];
     {
@@ -292,8 +303,13 @@ template <class T> struct PlanImpl : exb_plan {
     memset(&K, 0, sizeof(K));
     K.order = order;
     K.E = desc.lin_channels;
+    K.lin_matrix = desc.lin_matrix ? 1 : 0;
     K.M = M;
-    const size_t ne = (size_t)K.E * M;
+    table_sets = desc.table_sets > 1 ? desc.table_sets : 1;
+    if (table_sets > 1 && nranks > 1) return fail(EXB_EUNSUPPORTED, "stepper ensembles are not available for slab plans");
+    K.tstride = table_sets > 1 ? (long long)K.E * M : 0;
+    K.trep = 1;
+    const size_t ne = (size_t)K.E * M * table_sets;
     if (!desc.exp_term) return fail(EXB_EINVAL, "exp_term is required");
     int rc = upload(desc.exp_term, ne * sizeof(cpx<T>), (void**)&K.exp_term);
     if (rc) return rc;
@@ -321,6 +337,17 @@ template <class T> struct PlanImpl : exb_plan {
     if (fast_nd && nranks == 1 && !getenv("EXB_DENSE_FIELDS")) {
       Nhp = (Nh + 15) / 16 * 16;
       Mf = M / Nh * Nhp;
+    }
+    // Slab plans: the field buffers ARE the all-to-all payload.  Their last axis only ever holds the wavenumbers
+    // inside the dealiasing mask (pruned passes never touch k > kmax), so they are laid out with the COMPACT pitch
+    // kmax + 1 (rounded up to 16): with the 2/3 rule every transpose ships 2/3 of the bytes ("prune to
+    // the mask").  The caller allocates them with exb_plan_field_pitch().
+    if (fast_nd && nranks > 1 && P.kmax >= 0 && !getenv("EXB_DENSE_FIELDS")) {
+      const int kp = (P.kmax + 1 + 15) / 16 * 16;
+      if (kp < Nh) {
+        Nhp = kp;
+        Mf = M / Nh * Nhp;
+      }
     }
 
     if (D == 1) {
@@ -369,9 +396,19 @@ template <class T> struct PlanImpl : exb_plan {
   }
 
   // ---- fast path: N = R*R, f32, one channel (exb_kernels_1d_fast.cuh) ----
+  bool slab_cyclic = false;   // slab plans: cyclic distribution of the axis-1 indices over the ranks
+  int table_sets = 1;   // stepper ensemble: number of coefficient table sets (exb_desc.table_sets)
+  // trajectories per table set for a call over `batch` trajectories (EXB_EINVAL if the batch does not divide)
+  int set_table_rep(int64_t batch) {
+    if (table_sets <= 1) return EXB_OK;
+    if (batch % table_sets) return fail(EXB_EINVAL, "batch %lld is not a multiple of the %d table sets of this ensemble plan",
+                                        (long long)batch, table_sets);
+    K.trep = batch / table_sets;
+    return EXB_OK;
+  }
   bool fast_1d_ok() const {
     if constexpr (std::is_same<T, float>::value) {
-      if (D != 1 || C != 1 || K.E != 1) return false;
+      if (D != 1 || C != 1 || K.E != 1 || table_sets > 1) return false;   // (the fast kernel shares its tables per CTA)
       if (getenv("EXB_DISABLE_FAST_1D")) return false;
       return exb_fast1d_supported(N, P, K.order);
     }
@@ -405,6 +442,10 @@ template <class T> struct PlanImpl : exb_plan {
     p.n_saved = n_saved;
     p.substeps = substeps;
     p.flags = flags;
+    p.forcing = op == OP1_ROLLOUT ? frc.f : nullptr;
+    p.fstep = frc.step;
+    p.fbatch = frc.batch;
+    p.fscale = frc.scale;
     if (op == OP1_ROLLOUT && fast_1d_ok()) return launch_fast(st, p);
     bool plain = (op == OP1_FFT || op == OP1_IFFT);
     if (!plain && !fused_1d_ok)
@@ -424,6 +465,11 @@ template <class T> struct PlanImpl : exb_plan {
 
   // ------------------------------------------------------------------ N-D
   bool fast_nd = false;  // set in init(): register-FFT kernels available for this (D, N, N(u))
+  struct Forcing {            // set for the duration of one exb_rollout_forced call
+    const cpx<T>* f = nullptr;
+    long long step = 0, batch = 0;
+    T scale = (T)0;
+  } frc;
   bool fused_1d_ok = true;   // 1-D: state + stage buffers + transform lines fit shared memory
   size_t fused_1d_need = 0;
   int fused_ok() const override { return D != 1 || fused_1d_ok; }
@@ -498,10 +544,12 @@ template <class T> struct PlanImpl : exb_plan {
       p.line_stride = Nhp;
       p.outer_stride = (long long)N * Nhp;
     }
-    if (segmented) {  // slab layout A as received from / sent to the peers: [peer][x][n][Nh]
+    if (segmented) {  // slab layout A as received from / sent to the peers: [peer][x][n][pitch]
+      const long long pitch = fields ? Nhp : Nh;
       p.seg_len = nloc;
-      p.seg_stride = (long long)nloc * nloc * Nh;
-      p.outer_stride = (long long)nloc * Nh;
+      p.seg_cyclic = slab_cyclic ? nranks : 0;
+      p.seg_stride = (long long)nloc * nloc * pitch;
+      p.outer_stride = (long long)nloc * pitch;
     }
     if (peers) {
       if (!fast_nd || !segmented) return fail(EXB_EUNSUPPORTED, "peer stores need the fast N-D kernels");
@@ -544,7 +592,7 @@ template <class T> struct PlanImpl : exb_plan {
       if (!fast_nd || nranks <= 1) return fail(EXB_EUNSUPPORTED, "peer stores need the fast N-D kernels");
       p.peer = 1;
       p.seg_len = nloc;                                      // x-planes per rank
-      p.peer_off = (long long)this->d.slab_rank * nloc * p.line_stride;   // block [me] of the peer's [src][x][k1][K] buffer
+      p.peer_off = (long long)this->d.slab_rank * nloc * nloc * Nhp;      // block [me] of the peer's [src][x][k1][pitch] buffer
       for (int r = 0; r < nranks; ++r) p.peer_out[r] = (cpx<T>*)peers[r];
     }
     if (fast_nd) return launch_col_fast(st, p, +1, batch);
@@ -598,7 +646,7 @@ template <class T> struct PlanImpl : exb_plan {
       long long bchunk = batch;
       while (rows / 8 * ((batch + bchunk - 1) / bchunk) < 4LL * sm_count && bchunk > 4) bchunk = (bchunk + 1) / 2;
       dim3 grid((unsigned)((rows + 7) / 8), (unsigned)((batch + bchunk - 1) / bchunk));
-      etdrk_masked_linear_kernel<T><<<grid, 256, 0, st>>>(K, sb.U, sb.OUT, C, D, N, Nh, P.kmax, n1, P.i1_off, rows, batch,
+      etdrk_masked_linear_kernel<T><<<grid, 256, 0, st>>>(K, sb.U, sb.OUT, C, D, N, Nh, P.kmax, n1, P.i1_off, P.i1_mul, rows, batch,
                                                          (int)bchunk);
       ++launches;
       CUDA_OK(cudaGetLastError());
@@ -723,6 +771,14 @@ template <class T> struct PlanImpl : exb_plan {
   }
 
   int step_fourier_nd(cudaStream_t st, long long batch, const cpx<T>* in, cpx<T>* out, const Ws& w) {
+    if (K.order == 0 && K.lin_matrix) {
+      long long total = batch * M;
+      int grid = (int)((total + 255) / 256 < (long long)sm_count * 16 ? (total + 255) / 256 : (long long)sm_count * 16);
+      etdrk0_matrix_kernel<T><<<grid, 256, 0, st>>>(K, C, total, in, out);
+      ++launches;
+      CUDA_OK(cudaGetLastError());
+      return EXB_OK;
+    }
     if (K.order == 0) {
       long long total = batch * C * M;
       int grid = (int)((total + 255) / 256 < (long long)sm_count * 16 ? (total + 255) / 256 : (long long)sm_count * 16);
@@ -763,10 +819,12 @@ template <class T> struct PlanImpl : exb_plan {
     if (pass == (EXB_SLAB_COL1_FWD_NL | EXB_SLAB_SEGMENTED) || pass == (EXB_SLAB_COL1_FWD | EXB_SLAB_SEGMENTED)) {
       if (f0 < 0 || nf < 1) return fail(EXB_EINVAL, "field range out of bounds");
       const int prune = pass == (EXB_SLAB_COL1_FWD_NL | EXB_SLAB_SEGMENTED) ? (PRUNE_COLS | PRUNE_OUT_ROWS) : 0;
-      return col_plain<-1>(st, 1, 1, nf, (const cpx<T>*)in, nullptr, prune, true, peers, (long long)f0 * M);
+      return col_plain<-1>(st, 1, 1, nf, (const cpx<T>*)in, nullptr, prune, true, peers, (long long)f0 * (prune ? Mf : M),
+                           prune != 0);
     }
     return fail(EXB_EINVAL, "exb_slab_pass_peer: pass must be COL0_INV_PRO or a segmented COL1_FWD pass");
   }
+  int field_pitch() const override { return Nhp; }
   void nl_fields(int* ni, int* nf) const override {
     *ni = P.n_inv;
     *nf = P.n_fwd;
@@ -789,10 +847,12 @@ template <class T> struct PlanImpl : exb_plan {
         return col_plain<-1>(st, 1, 1, nfields, (const cpx<T>*)in, (cpx<T>*)out, 0, seg);
       case EXB_SLAB_COL1_INV:
         return col_plain<+1>(st, 1, 1, nfields, (const cpx<T>*)in, (cpx<T>*)out, 0, seg);
-      case EXB_SLAB_COL1_FWD_NL:
-        return col_plain<-1>(st, 1, 1, nfields, (const cpx<T>*)in, (cpx<T>*)out, PRUNE_COLS | PRUNE_OUT_ROWS, seg);
+      case EXB_SLAB_COL1_FWD_NL:   // (field buffers: pitch exb_plan_field_pitch)
+        return col_plain<-1>(st, 1, 1, nfields, (const cpx<T>*)in, (cpx<T>*)out, PRUNE_COLS | PRUNE_OUT_ROWS, seg, nullptr,
+                             0, true);
       case EXB_SLAB_COL1_INV_NL:
-        return col_plain<+1>(st, 1, 1, nfields, (const cpx<T>*)in, (cpx<T>*)out, PRUNE_COLS | PRUNE_IN_ROWS, seg);
+        return col_plain<+1>(st, 1, 1, nfields, (const cpx<T>*)in, (cpx<T>*)out, PRUNE_COLS | PRUNE_IN_ROWS, seg, nullptr,
+                             0, true);
       case EXB_SLAB_COL0_FWD:
         return col_plain<-1>(st, 0, 1, nfields, (const cpx<T>*)in, (cpx<T>*)out);
       case EXB_SLAB_COL0_INV:
@@ -800,7 +860,8 @@ template <class T> struct PlanImpl : exb_plan {
       case EXB_SLAB_COL0_INV_PRO:
         return col_inv_pro(st, 1, (const cpx<T>*)in, (cpx<T>*)out);
       case EXB_SLAB_ROW_NL:
-        return row_pass(st, ROW_NL, 1, P.n_inv, P.n_fwd, in, (long long)P.n_inv * M, out, (long long)P.n_fwd * M);
+        return row_pass(st, ROW_NL, 1, P.n_inv, P.n_fwd, in, (long long)P.n_inv * Mf, out, (long long)P.n_fwd * Mf,
+                        Nhp, Nhp);
       case EXB_SLAB_COL0_FWD_EPI: {
         if (K.order == 0) {
           long long total = (long long)C * M;
@@ -958,6 +1019,7 @@ template <class T> struct PlanImpl : exb_plan {
 
   int step_fourier(cudaStream_t st, int64_t batch, const void* in, void* out, void* ws) override {
     if (nranks > 1) return fail(EXB_EINVAL, "slab plans only support exb_slab_pass");
+    if (int rct = set_table_rep(batch)) return rct;
     if (D == 1) return launch_1d(st, OP1_STEP_FOURIER, batch, C, in, out, 0, 1, 0);
     int rc = need_ws(ws, batch);
     if (rc) return rc;
@@ -973,6 +1035,7 @@ template <class T> struct PlanImpl : exb_plan {
               void* out, void* ws) override {
     if (nranks > 1) return fail(EXB_EINVAL, "slab plans only support exb_slab_pass");
     if (n_saved < 0 || substeps < 1) return fail(EXB_EINVAL, "n_saved must be >= 0 and substeps >= 1");
+    if (int rct = set_table_rep(batch)) return rct;
     const bool include_init = flags & EXB_ROLLOUT_INCLUDE_INIT;
     const bool layout_tb = flags & EXB_ROLLOUT_LAYOUT_TB;
     const bool final_only = flags & EXB_ROLLOUT_FINAL_ONLY;
@@ -993,6 +1056,7 @@ template <class T> struct PlanImpl : exb_plan {
       const long long nb = batch - b0 < cb ? batch - b0 : cb;
       const T* u0c = (const T*)u0 + (size_t)b0 * fsz0;
       T* outc = (T*)out + (size_t)b0 * ((final_only || layout_tb) ? fsz0 : Tn0 * fsz0);
+      forcing_b0 = b0;
       rc = rollout_nd_chunk(st, nb, batch, n_saved, substeps, flags, u0c, outc, ws);
       if (rc) return rc;
     }
@@ -1001,6 +1065,7 @@ template <class T> struct PlanImpl : exb_plan {
 
   // number of trajectories processed together (N-D).  EXB_ND_CHUNK overrides (0 = whole batch).
   long long chunk_batch(long long batch) const {
+    if (table_sets > 1) return batch;   // (table sets are indexed by the position in the whole batch)
     if (const char* e = getenv("EXB_ND_CHUNK")) {
       long long v = atoll(e);
       return v <= 0 ? batch : (v < batch ? v : batch);
@@ -1008,6 +1073,22 @@ template <class T> struct PlanImpl : exb_plan {
     return nd_chunk > 0 && nd_chunk < batch ? nd_chunk : batch;
   }
   long long nd_chunk = 0;  // set in init()
+  long long forcing_b0 = 0;  // first trajectory of the chunk being processed (forcing offset)
+
+  int rollout_forced(cudaStream_t st, int64_t batch, int64_t n_saved, int substeps, unsigned flags, const void* u0,
+                     void* out, void* ws, const void* fhat, int64_t fstep, int64_t fbatch, double scale) override {
+    if (!fhat) return rollout(st, batch, n_saved, substeps, flags, u0, out, ws);
+    if (substeps != 1) return fail(EXB_EINVAL, "a forcing needs substeps = 1 (one forcing per ETDRK step)");
+    if (flags & EXB_ROLLOUT_SPECTRAL_CARRY)
+      return fail(EXB_EINVAL, "a forcing is added to the physical-space carry: no SPECTRAL_CARRY");
+    frc.f = (const cpx<T>*)fhat;
+    frc.step = fstep;
+    frc.batch = fbatch;
+    frc.scale = (T)scale;
+    const int rc = rollout(st, batch, n_saved, substeps, flags, u0, out, ws);
+    frc = Forcing();
+    return rc;
+  }
 
   int rollout_nd_chunk(cudaStream_t st, long long batch, long long batch_total, int64_t n_saved, int substeps,
                        unsigned flags, const T* u0, T* out, void* ws) {
@@ -1045,6 +1126,14 @@ template <class T> struct PlanImpl : exb_plan {
     if (rc) return rc;
     T* phys_scratch = (T*)w.Wfwd;  // >= C*G reals per batch element (M*2 >= G)
     for (long long s = 0; s < n_saved; ++s) {
+      if (frc.f) {  // ForcedStepper: u_hat += dt * f_hat of step s
+        const long long per = (long long)C * M, total = per * batch;
+        int grid = (int)((total + 255) / 256 < (long long)sm_count * 16 ? (total + 255) / 256 : (long long)sm_count * 16);
+        add_forcing_kernel<T><<<grid, 256, 0, st>>>(w.Uh, frc.f + s * frc.step + forcing_b0 * frc.batch, per, frc.batch,
+                                                    batch, frc.scale);
+        ++launches;
+        CUDA_OK(cudaGetLastError());
+      }
       for (int sub = 0; sub < substeps; ++sub) {
         rc = step_fourier_nd(st, batch, w.Uh, w.Uh, w);
         if (rc) return rc;
@@ -1177,6 +1266,13 @@ int exb_rollout(exb_plan* plan, void* stream, int64_t batch, int64_t n_saved, in
   if (!plan) return fail(EXB_EINVAL, "null plan");
   return plan->rollout((cudaStream_t)stream, batch, n_saved, substeps, flags, u0, out, ws);
 }
+int exb_rollout_forced(exb_plan* plan, void* stream, int64_t batch, int64_t n_saved, int32_t substeps, uint32_t flags,
+                       const void* u0, void* out, void* ws, const void* forcing_hat, int64_t step_stride,
+                       int64_t batch_stride, double scale) {
+  if (!plan) return fail(EXB_EINVAL, "null plan");
+  return plan->rollout_forced((cudaStream_t)stream, batch, n_saved, substeps, flags, u0, out, ws, forcing_hat, step_stride,
+                              batch_stride, scale);
+}
 int64_t exb_launch_count(const exb_plan* plan) { return plan ? plan->launches : 0; }
 int exb_plan_fused_ok(const exb_plan* plan) { return plan ? plan->fused_ok() : 0; }
 int exb_metric_sums(void* stream, int32_t dtype, int64_t nfields, int64_t npoints, const void* a, const void* b,
@@ -1231,6 +1327,7 @@ int exb_slab_inv_pro_fields(exb_plan* plan, void* stream, int32_t field0, int32_
   if (!plan) return fail(EXB_EINVAL, "null plan");
   return plan->slab_inv_pro_fields((cudaStream_t)stream, field0, nfields, in, out);
 }
+int exb_plan_field_pitch(const exb_plan* plan) { return plan ? plan->field_pitch() : 0; }
 int exb_plan_nl_fields(const exb_plan* plan, int32_t* n_inv, int32_t* n_fwd) {
   if (!plan || !n_inv || !n_fwd) return fail(EXB_EINVAL, "null argument");
   plan->nl_fields(n_inv, n_fwd);

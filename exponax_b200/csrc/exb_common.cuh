@@ -128,18 +128,28 @@ template <class T> struct NlParams {
   T poly[8];
   T gen[3];
   T inv_norm;         // 1/N^D
-  int i1_off;         // slab decomposition (3-D): global axis-1 index of local index 0
+  int i1_off;         // slab decomposition (3-D): global axis-1 index of local index l = l * i1_mul + i1_off
+  int i1_mul;         //   block distribution: (1, rank * N/P);  cyclic: (P, rank);  single GPU: (1, 0)
 };
 
 // ETDRK coefficient tables (device pointers); E = 1 or C leading extent, M modes each.
 template <class T> struct EtdrkCoefs {
   int order;
+  int lin_matrix;   // order 0: exp_term holds a per-mode C x C matrix, entry [(i*C + j) * M + mode]
+  // stepper ensembles: trajectory b reads its tables at offset (b / trep) * tstride (tstride = E * M elements per
+  // table set, 0 = one shared set; trep = trajectories per set, filled in per launch)
+  long long tstride;
+  long long trep;
   int E;
   long long M;
   const cpx<T>* exp_term;
   const cpx<T>* half_exp;
   const T* c[6];
 };
+
+template <class T> __host__ __device__ inline long long table_offset(const EtdrkCoefs<T>& K, long long b) {
+  return K.tstride ? (b / K.trep) * K.tstride : 0;
+}
 
 __host__ __device__ inline int wavenumber_of(int idx, int N) {
   // fftfreq ordering on full axes: 0..ceil(N/2)-1, -floor(N/2)..-1  (_spectral.py:40-41)

@@ -30,6 +30,12 @@ template <class T> struct K1dParams {
   long long n_saved;
   int substeps;
   unsigned flags;
+  // ForcedStepper / aux-taking rollouts (exponax/_forced_stepper.py:61-62: step(u + dt f)): before ETDRK step i the
+  // Fourier transform of the forcing is added to the state, u_hat += fscale * f_hat[i * fstep + traj * fbatch + ...]
+  // (the transform is linear, so this IS fft(u + dt f)); forcing == nullptr: none.  substeps must be 1.
+  const cpx<T>* forcing;
+  long long fstep, fbatch;   // element strides between steps (0: constant forcing) / trajectories (0: shared)
+  T fscale;
 };
 
 template <class T> struct Ctx1d {
@@ -136,14 +142,40 @@ __device__ __forceinline__ void nl_mode_pair(Ctx1d<T>& c, const cpx<T>* W, int k
 template <class T> __device__ void etdrk_step_1d(Ctx1d<T>& c) {
   const EtdrkCoefs<T>& K = c.p.K;
   const int Nh = c.Nh, C = c.C;
+  if (K.order == 0 && K.lin_matrix) {  // per-mode C x C matrix (Wave, _wave.py:175-197)
+    for (int k = threadIdx.x; k < Nh; k += blockDim.x) {
+#pragma unroll
+      for (int tr = 0; tr < 2; ++tr) {
+        cpx<T> u[EXB_MAXC], r[EXB_MAXC];
+#pragma unroll
+        for (int ch = 0; ch < EXB_MAXC; ++ch)
+          if (ch < C) u[ch] = c.sb.U[soff(c, tr, ch, k)];
+#pragma unroll
+        for (int ci = 0; ci < EXB_MAXC; ++ci) {
+          if (ci < C) {
+            cpx<T> acc((T)0, (T)0);
+#pragma unroll
+            for (int cj = 0; cj < EXB_MAXC; ++cj)
+              if (cj < C)
+                acc = acc + K.exp_term[(long long)(ci * C + cj) * K.M + k + table_offset(K, tr ? c.t2 : c.t1)] * u[cj];
+            r[ci] = acc;
+          }
+        }
+#pragma unroll
+        for (int ch = 0; ch < EXB_MAXC; ++ch)
+          if (ch < C) c.sb.OUT[soff(c, tr, ch, k)] = r[ch];
+      }
+    }
+    __syncthreads();
+    return;
+  }
   if (K.order == 0) {  // (_etdrk_0.py:30-34)
     for (int q = threadIdx.x; q < C * Nh; q += blockDim.x) {
       int ch = q / Nh, k = q - ch * Nh;
       long long ci = (long long)(K.E == 1 ? 0 : ch) * K.M + k;
-      cpx<T> e = K.exp_term[ci];
       size_t o1 = soff(c, 0, ch, k), o2 = soff(c, 1, ch, k);
-      c.sb.OUT[o1] = e * c.sb.U[o1];
-      c.sb.OUT[o2] = e * c.sb.U[o2];
+      c.sb.OUT[o1] = K.exp_term[ci + table_offset(K, c.t1)] * c.sb.U[o1];
+      c.sb.OUT[o2] = K.exp_term[ci + (c.has2 ? table_offset(K, c.t2) : 0)] * c.sb.U[o2];
     }
     __syncthreads();
     return;
@@ -159,8 +191,8 @@ template <class T> __device__ void etdrk_step_1d(Ctx1d<T>& c) {
       for (int ch = 0; ch < EXB_MAXC; ++ch) {
         if (ch < C) {
           long long ci = (long long)(K.E == 1 ? 0 : ch) * K.M + k;
-          etdrk_update(K, s, ci, soff(c, 0, ch, k), n1[ch], c.sb);
-          etdrk_update(K, s, ci, soff(c, 1, ch, k), n2[ch], c.sb);
+          etdrk_update(K, s, ci + table_offset(K, c.t1), soff(c, 0, ch, k), n1[ch], c.sb);
+          etdrk_update(K, s, ci + (c.has2 ? table_offset(K, c.t2) : 0), soff(c, 1, ch, k), n2[ch], c.sb);
         }
       }
     }
@@ -289,6 +321,16 @@ template <class T> __global__ void k1d_kernel(const K1dParams<T> p) {
     __syncthreads();
   }
   for (long long s = 0; s < p.n_saved; ++s) {
+    if (p.forcing) {
+      const cpx<T>* f1 = p.forcing + s * p.fstep + c.t1 * p.fbatch;
+      const cpx<T>* f2 = p.forcing + s * p.fstep + c.t2 * p.fbatch;
+      for (int q = threadIdx.x; q < C * Nh; q += blockDim.x) {
+        int ch = q / Nh, k = q - ch * Nh;
+        U[soff(c, 0, ch, k)] = axpy(p.fscale, f1[q], U[soff(c, 0, ch, k)]);
+        if (c.has2) U[soff(c, 1, ch, k)] = axpy(p.fscale, f2[q], U[soff(c, 1, ch, k)]);
+      }
+      __syncthreads();
+    }
     for (int sub = 0; sub < p.substeps; ++sub) etdrk_step_1d(c);
     const bool last = (s == p.n_saved - 1);
     const bool store = !final_only || last;

@@ -441,6 +441,21 @@ __global__ void __launch_bounds__(256, 2) k1d_fast_kernel(const K1dParams<float>
 
   const float invN = p.P.inv_norm;
   for (long long s = 0; s < p.n_saved; ++s) {
+    if (p.forcing) {  // u_hat += dt * f_hat (ForcedStepper), owned modes of both trajectories
+      const cpx<float>* f1 = p.forcing + s * p.fstep + t1 * p.fbatch;
+      const cpx<float>* f2 = p.forcing + s * p.fstep + t2 * p.fbatch;
+#pragma unroll
+      for (int sl = 0; sl < R / 2; ++sl) {
+        const int k = j + R * sl;
+        if (act1) U[k] = axpy(p.fscale, f1[k], U[k]);
+        if (act2) U[lay.nhp + k] = axpy(p.fscale, f2[k], U[lay.nhp + k]);
+      }
+      if (j == 0) {
+        if (act1) U[N / 2] = axpy(p.fscale, f1[N / 2], U[N / 2]);
+        if (act2) U[lay.nhp + N / 2] = axpy(p.fscale, f2[N / 2], U[lay.nhp + N / 2]);
+      }
+      __syncwarp();
+    }
     for (int sub = 0; sub < p.substeps; ++sub) F.etdrk_step(order);
     const bool last = (s == p.n_saved - 1);
     const bool store = !final_only || last;

@@ -46,6 +46,7 @@ template <class T> struct ColParams {
   int masked_external;     // fast COL_FWD_EPI: the dealiased modes are advanced by etdrk_masked_linear_kernel, skip them
   int seg_len;             // COL_PLAIN, slab transposes without pack/unpack: line entry i lives at
   long long seg_stride;    //   (i / seg_len) * seg_stride + (i % seg_len) * line_stride   (seg_len = 0: off)
+  int seg_cyclic;          //   P > 0: cyclic axis-1 distribution, entry i at (i % P) * seg_stride + (i / P) * line_stride
   // peer output (fast kernels, COL_INV_PRO / COL_PLAIN of a slab plan): entry i of an output line is stored
   // into the buffer of rank i / seg_len -- peer_out[r] is that rank's destination buffer mapped into this
   // process (NVLink peer memory) -- at peer_off + (i % seg_len) * line_stride; the pass IS the transpose.
@@ -70,7 +71,7 @@ __device__ __forceinline__ ModeK<T> col_mode(const NlParams<T>& P, int i, long l
   if (P.D == 2) return make_mode(P, i, (int)iw, 0);
   int i1 = (int)(iw / P.Nh);
   int i2 = (int)(iw - (long long)i1 * P.Nh);
-  return make_mode(P, i, i1 + P.i1_off, i2);
+  return make_mode(P, i, i1 * P.i1_mul + P.i1_off, i2);
 }
 
 template <class T, int DIR> __global__ void col_pass_kernel(const ColParams<T> p) {
@@ -94,7 +95,9 @@ template <class T, int DIR> __global__ void col_pass_kernel(const ColParams<T> p
     cpx<T>* A = sm;
     cpx<T>* B = sm + tile;
     auto line_off = [&](int i) -> size_t {
-      if (p.seg_len > 0) return (size_t)(i / p.seg_len) * p.seg_stride + (size_t)(i % p.seg_len) * p.line_stride;
+      if (p.seg_len > 0)
+        return p.seg_cyclic ? (size_t)(i % p.seg_cyclic) * p.seg_stride + (size_t)(i / p.seg_cyclic) * p.line_stride
+                            : (size_t)(i / p.seg_len) * p.seg_stride + (size_t)(i % p.seg_len) * p.line_stride;
       return (size_t)i * p.line_stride;
     };
     for (int q = threadIdx.x; q < N * TW; q += blockDim.x) {
@@ -191,7 +194,7 @@ template <class T, int DIR> __global__ void col_pass_kernel(const ColParams<T> p
         if (p.mode == COL_FWD_NL) {
           p.out[off] = n[ch];
         } else {
-          const long long ci = (long long)(p.K.E == 1 ? 0 : ch) * p.K.M + mode;
+          const long long ci = (long long)(p.K.E == 1 ? 0 : ch) * p.K.M + mode + table_offset(p.K, b);
           if (!m.keep && !m.is_inj) etdrk_update_masked(p.K, p.stage, ci, off, p.sb);  // N(u) == 0 there
           else etdrk_update(p.K, p.stage, ci, off, n[ch], p.sb);
         }
@@ -310,7 +313,7 @@ template <class T> __global__ void row_pass_kernel(const RowParams<T> p) {
 template <class T>
 __global__ void __launch_bounds__(256) etdrk_masked_linear_kernel(const EtdrkCoefs<T> K, const cpx<T>* U,   // (OUT may alias U)
                                                                  cpx<T>* OUT, int C, int D, int N, int Nh,
-                                                                 int kmax, int n1, int i1_off, long long rows,
+                                                                 int kmax, int n1, int i1_off, int i1_mul, long long rows,
                                                                  long long batch, int bchunk) {
   const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (r >= rows) return;
@@ -318,7 +321,7 @@ __global__ void __launch_bounds__(256) etdrk_masked_linear_kernel(const EtdrkCoe
   int i0 = (int)r, i1 = 0;
   if (D == 3) {
     i0 = (int)(r / n1);
-    i1 = (int)(r - (long long)i0 * n1) + i1_off;
+    i1 = (int)(r - (long long)i0 * n1) * i1_mul + i1_off;
   }
   int k0 = wavenumber_of(i0, N), k1 = D == 3 ? wavenumber_of(i1, N) : 0;
   k0 = k0 < 0 ? -k0 : k0;
@@ -329,7 +332,13 @@ __global__ void __launch_bounds__(256) etdrk_masked_linear_kernel(const EtdrkCoe
   for (int e = start + lane; e < Nh; e += 32) {
     const long long mode = r * Nh + e;
     for (int c = 0; c < C; ++c) {
-      const cpx<T> Ev = K.exp_term[(long long)(K.E == 1 ? 0 : c) * K.M + mode];
+      const long long ci = (long long)(K.E == 1 ? 0 : c) * K.M + mode;
+      if (K.tstride) {  // stepper ensemble: one table set per group of trajectories
+        for (long long b = b0; b < b1; ++b)
+          OUT[((size_t)b * C + c) * K.M + mode] = K.exp_term[ci + table_offset(K, b)] * U[((size_t)b * C + c) * K.M + mode];
+        continue;
+      }
+      const cpx<T> Ev = K.exp_term[ci];
       long long b = b0;
       for (; b + 4 <= b1; b += 4) {
         cpx<T> u[4];
@@ -351,8 +360,47 @@ __global__ void etdrk0_kernel(const EtdrkCoefs<T> K, int C, long long total, con
   for (; i < total; i += stride) {
     long long mode = i % K.M;
     int ch = (int)((i / K.M) % C);
-    long long ci = (long long)(K.E == 1 ? 0 : ch) * K.M + mode;
+    long long ci = (long long)(K.E == 1 ? 0 : ch) * K.M + mode + table_offset(K, i / (K.M * C));
     out[i] = K.exp_term[ci] * in[i];
+  }
+}
+
+// order-0 step with a per-mode C x C matrix (Wave: exponax/stepper/_wave.py:175-197 composed into one 2 x 2 map):
+// out_i = sum_j A[i][j](mode) * in_j.  One thread per (trajectory, mode); `in` may alias `out`.
+template <class T>
+__global__ void etdrk0_matrix_kernel(const EtdrkCoefs<T> K, int C, long long total, const cpx<T>* in, cpx<T>* out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    const long long b = i / K.M, mode = i - b * K.M;
+    cpx<T> u[EXB_MAXC], r[EXB_MAXC];
+#pragma unroll
+    for (int c = 0; c < EXB_MAXC; ++c)
+      if (c < C) u[c] = in[((size_t)b * C + c) * K.M + mode];
+#pragma unroll
+    for (int ci = 0; ci < EXB_MAXC; ++ci) {
+      if (ci < C) {
+        cpx<T> acc((T)0, (T)0);
+#pragma unroll
+        for (int cj = 0; cj < EXB_MAXC; ++cj)
+          if (cj < C) acc = acc + K.exp_term[(long long)(ci * C + cj) * K.M + mode + table_offset(K, b)] * u[cj];
+        r[ci] = acc;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < EXB_MAXC; ++c)
+      if (c < C) out[((size_t)b * C + c) * K.M + mode] = r[c];
+  }
+}
+
+// ForcedStepper (exponax/_forced_stepper.py:61-62) in Fourier space: u_hat[b] += scale * f_hat[b * fbatch + ...]
+template <class T>
+__global__ void add_forcing_kernel(cpx<T>* u, const cpx<T>* f, long long per_traj, long long fbatch, long long batch, T scale) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < per_traj * batch; i += stride) {
+    const long long b = i / per_traj, r = i - b * per_traj;
+    u[i] = axpy(scale, f[b * fbatch + r], u[i]);
   }
 }
 

@@ -107,11 +107,11 @@ col_fast_kernel(const ColParams<float> p) {
   // the fixed indices of this thread's column: 2-D axis 0 / 3-D axis 1: inner = last-axis wavenumber;
   // 3-D axis 0: inner = (i1, i2)
   const bool flat3 = inner != (unsigned)p.P.Nh;
-  int i1 = (int)iw, i2 = 0;
+  int i1 = (int)iw, i2 = 0, i1l = 0;   // i1l: LOCAL axis-1 index (slabs), i1: global
   if (flat3) {
-    i1 = (int)(iw / (unsigned)p.P.Nh);
-    i2 = (int)(iw - (unsigned)i1 * (unsigned)p.P.Nh);
-    i1 += p.P.i1_off;
+    i1l = (int)(iw / (unsigned)p.P.Nh);
+    i2 = (int)(iw - (unsigned)i1l * (unsigned)p.P.Nh);
+    i1 = i1l * p.P.i1_mul + p.P.i1_off;
   }
   const int k1 = flat3 ? wavenumber_of(i1, N) : i1;  // (2-D: the last-axis index is the wavenumber)
   const bool col_in_mask = kmax < 0 || ((k1 < 0 ? -k1 : k1) <= kmax && i2 <= kmax);
@@ -124,8 +124,8 @@ col_fast_kernel(const ColParams<float> p) {
   // thread's entry q = 0 inside a field, entry stride, field stride
   const int fpitch = p.fpitch > 0 ? p.fpitch : p.P.Nh;
   const size_t fM = p.fpitch > 0 ? (size_t)p.fM : (size_t)p.M;
-  const size_t fls = flat3 ? (size_t)N * fpitch : (size_t)fpitch;
-  const size_t foff = (flat3 ? (size_t)(i1 - p.P.i1_off) * fpitch + i2 : (size_t)iw) + (size_t)j * fls;
+  const size_t fls = flat3 ? (size_t)(inner / (unsigned)p.P.Nh) * fpitch : (size_t)fpitch;  // (slabs: N/P axis-1 indices)
+  const size_t foff = (flat3 ? (size_t)i1l * fpitch + i2 : (size_t)iw) + (size_t)j * fls;
   const size_t fqstride = (size_t)P * fls;
 
   if (MODE == COL_PLAIN) {
@@ -138,7 +138,10 @@ col_fast_kernel(const ColParams<float> p) {
     cpx<float> v[8];
     if (p.seg_len > 0) {
       // segmented lines: the slab all-to-all buffers are used in place (entry i at (i / n) * seg_stride + (i % n) * ls)
-      auto line_off = [&](int i) -> size_t { return (size_t)(i / p.seg_len) * p.seg_stride + (size_t)(i % p.seg_len) * ls; };
+      // owner rank / local index of line entry i: block (i / n, i % n) or cyclic (i % P, i / P) distribution
+      auto seg_of = [&](int i) { return p.seg_cyclic ? i % p.seg_cyclic : i / p.seg_len; };
+      auto loc_of = [&](int i) { return p.seg_cyclic ? i / p.seg_cyclic : i % p.seg_len; };
+      auto line_off = [&](int i) -> size_t { return (size_t)seg_of(i) * p.seg_stride + (size_t)loc_of(i) * ls; };
 #pragma unroll
       for (int q = 0; q < 8; ++q) v[q] = ((in_mask >> q) & 1u) ? p.in[base + line_off(j + P * q)] : zero;
       fft8_run<N, DIR>(v, ex, j, tw);
@@ -146,7 +149,7 @@ col_fast_kernel(const ColParams<float> p) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const int i = j + P * q;
-          if ((out_mask >> q) & 1u) p.peer_out[i / p.seg_len][base + p.peer_off + (size_t)(i % p.seg_len) * ls] = v[q];
+          if ((out_mask >> q) & 1u) p.peer_out[seg_of(i)][base + p.peer_off + (size_t)loc_of(i) * ls] = v[q];
         }
       } else {
 #pragma unroll
@@ -263,12 +266,12 @@ col_fast_kernel(const ColParams<float> p) {
       }
       fft8_run<N, DIR>(v, ex, j, tw);
       if (col_keep) {
-        if (p.peer) {  // x-plane i of the result belongs to rank i / seg_len: store it there (NVLink; dense buffers)
-          const size_t obase = ((size_t)b * Pn.n_inv + f) * p.M + iw;
+        if (p.peer) {  // x-plane i of the result belongs to rank i / seg_len: store it there (NVLink)
+          const size_t obase = ((size_t)b * Pn.n_inv + f) * fM + (foff - (size_t)j * fls);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             const int i = j + P * q;
-            p.peer_out[i / p.seg_len][obase + p.peer_off + (size_t)(i % p.seg_len) * ls] = v[q];
+            p.peer_out[i / p.seg_len][obase + p.peer_off + (size_t)(i % p.seg_len) * fls] = v[q];
           }
         } else {
           cpx<float>* __restrict__ dst = p.out + ((size_t)b * Pn.n_inv + f) * fM + foff;
@@ -313,7 +316,7 @@ col_fast_kernel(const ColParams<float> p) {
   if (!act) return;
   // element offset of (trajectory b, channel 0, entry q = 0) and of the coefficient entry; + q * qstride + c * M
   const size_t off0 = (size_t)b * C * p.M + iw + (size_t)j * ls;
-  const size_t ci0 = iw + (size_t)j * ls;
+  const size_t ci0 = iw + (size_t)j * ls + (size_t)table_offset(p.K, (long long)b);
   const size_t cstep = p.K.E == 1 ? 0 : (size_t)p.K.M;
 #pragma unroll
   for (int q = 0; q < 8; ++q) {

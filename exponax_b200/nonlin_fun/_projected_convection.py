@@ -62,5 +62,7 @@ class ProjectedConvection3dKolmogorov(ProjectedConvection3d):
         val = float(self.injection[0][idx])
         slab = sp.current_slab() if self._slab is None else self._slab
         if slab is not None:  # the kernels compare GLOBAL mode indices
-            idx = (idx[0], idx[1] + slab[0] * (self.num_points // slab[1]), idx[2])
+            local = idx[1]
+            glob = local * slab[1] + slab[0] if sp.SLAB_CYCLIC else local + slab[0] * (self.num_points // slab[1])
+            idx = (idx[0], glob, idx[2])
         return idx, val

@@ -15,7 +15,9 @@ class Wave(BaseStepper):
     DC correction are composed ONCE at construction time into a single per-mode 2x2 matrix
     (obtained by pushing the two basis states through the reference's own sequence of operations,
     so the rounding is the reference's), and one step in Fourier space is that matrix applied to
-    `(h_hat, v_hat)`.  The transforms are the native ones.  ("next" row.)"""
+    `(h_hat, v_hat)` -- natively: the plan carries the matrix as its order-0 "linear operator"
+    (`exb_desc.lin_matrix`), so the step runs inside the fused kernels like every other stepper
+    ("next" row).  `_step_fourier_generic` is the array-level statement of the same map."""
 
     def __init__(self, num_spatial_dims: int, domain_extent: float, num_points: int, dt: float, *,
                  speed_of_sound: float = 1.0):
@@ -27,7 +29,6 @@ class Wave(BaseStepper):
                                      num_points=num_points, dtype=rd), axis=0, keepdims=True).astype(rd)
         super().__init__(num_spatial_dims=num_spatial_dims, domain_extent=domain_extent, num_points=num_points,
                          dt=dt, num_channels=2, order=0)
-        self._native = False  # `step_fourier` is overridden: not a plain diagonal ETDRK0 step
         cd = self._integrator._cd
         shape = self.wavenumber_norm.shape[1:]
         cols = []
@@ -37,6 +38,22 @@ class Wave(BaseStepper):
         # _matrix[i][j]: contribution of input channel j to output channel i
         self._matrix = np.stack([np.stack([cols[0][i], cols[1][i]]) for i in range(2)]).astype(cd)
         self._matrix_dev = {}
+        self._wave_plans = {}
+
+    def _plan(self):
+        """Native plan: an order-0 step whose per-mode factor is the composed 2 x 2 matrix (`exb_desc.lin_matrix`),
+        so `stepper(u)`, `ex.rollout` / `ex.repeat` and `RepeatedStepper` run inside the fused `exb_rollout`."""
+        from .. import _native as nat
+        dev = A.torch.cuda.current_device()
+        p = self._wave_plans.get(dev)
+        if p is None:
+            M = int(np.prod(self._matrix.shape[2:]))
+            p = self._wave_plans[dev] = nat.Plan(
+                D=self.num_spatial_dims, N=self.num_points, C_=2, E=4, order=0, dtype=self._dtype,
+                L=self.domain_extent, kmax=-1, nl={"kind": nat.NL_ZERO}, exp_term=self._matrix.reshape(4, M),
+                lin_matrix=True)
+        self._native = True
+        return p if p.fused_ok() else None
 
     # ---- the reference's sequence of operations, on host arrays (constructor only) ----------------
     def _forward_transform(self, u_hat):

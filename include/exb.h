@@ -94,7 +94,10 @@ typedef struct exb_desc {
   int32_t zero_mode_fix;     /* gradient norm / general */
   double nl_scale;           /* convection scale / gradient-norm scale / vorticity convection scale */
   int32_t n_poly;            /* polynomial: number of coefficients (<= EXB_MAX_POLY) */
-  int32_t reserved0;
+  int32_t table_sets;        /* stepper ENSEMBLES (docs/examples/performance_hints.ipynb, eqx.filter_vmap over constructor
+                                arguments): > 1 = the coefficient arrays carry a leading axis of that many table sets,
+                                (table_sets, E, modes); trajectory b of a batch uses set b / (batch / table_sets).
+                                0 or 1 = one set shared by the whole batch */
   double poly[EXB_MAX_POLY];
   double general_scales[3];  /* general: (b0, b1, b2) as in GeneralNonlinearFun.scale_list */
   /* Kolmogorov injection: constant real value added (un-masked) to channel 0 of N(u) at one
@@ -117,7 +120,14 @@ typedef struct exb_desc {
   /* non-zero: exp_term / half_exp_term / coef[] are DEVICE pointers that stay valid for the life of
      the plan (tables built on the GPU for grids whose tables do not fit the host comfortably) */
   int32_t tables_on_device;
-  int32_t reserved1;
+  int32_t slab_cyclic;       /* slab plans: 0 = rank r owns the contiguous axis-1 indices [r N/P, (r+1) N/P); 1 = rank r owns
+                                the indices r, r + P, r + 2P, ... (cyclic).  With a dealiasing mask the cyclic distribution
+                                gives every rank the same share of the wavenumbers inside the mask (block: at P = 8 two
+                                ranks own nothing but dealiased modes and sit idle in the axis-0 passes and transposes) */
+  int32_t reserved2;
+  int32_t lin_matrix;        /* order 0 only: exp_term is a per-mode C x C matrix, (C*C, modes) with entry [i*C + j] =
+                                contribution of input channel j to output channel i (lin_channels = C*C); used by the
+                                Wave stepper, whose step is a 2 x 2 map of (h, v) per mode (exponax/stepper/_wave.py:175-197) */
 } exb_desc;
 
 /* thread-local description of the last error on this thread */
@@ -160,6 +170,18 @@ int exb_step(exb_plan *plan, void *stream, int64_t batch, const void *u_in, void
 int exb_rollout(exb_plan *plan, void *stream, int64_t batch, int64_t n_saved, int32_t substeps,
                 uint32_t flags, const void *u0, void *out, void *workspace);
 
+/* exb_rollout with a forcing: ForcedStepper / aux-taking rollouts (exponax/_forced_stepper.py:61-62, 85-86:
+   `stepper.step(u + dt * f)`; exponax/_utils.py:137-163: `rollout(..., takes_aux=True)`), fused into the same
+   kernels.  `forcing_hat` = exb_fft of the forcing (the transform is linear: fft(u + dt f) = u_hat + dt f_hat),
+   complex (.., C, modes); before ETDRK step i of trajectory b the state receives
+       u_hat += scale * forcing_hat[i * step_stride + b * batch_stride + ...]        (strides in complex elements)
+   step_stride = 0: constant forcing (`constant_aux=True`); batch_stride = 0: one forcing shared by the batch;
+   scale = dt.  substeps must be 1 and SPECTRAL_CARRY must not be set.  forcing_hat == NULL: plain exb_rollout.
+   (A plan must not be driven from two host threads at the same time.) */
+int exb_rollout_forced(exb_plan *plan, void *stream, int64_t batch, int64_t n_saved, int32_t substeps,
+                       uint32_t flags, const void *u0, void *out, void *workspace, const void *forcing_hat,
+                       int64_t step_stride, int64_t batch_stride, double scale);
+
 /* ---- slab-decomposed 3-D transforms (one field too large for one GPU) ----
    One local pass of the distributed step; the caller (exponax_b200/_slab.py) performs the
    all-to-all transposes between passes with NCCL.  Layout A = physical slab (F, N/P, N, N/2+1 | N),
@@ -195,6 +217,12 @@ int exb_slab_inv_pro_fields(exb_plan *plan, void *stream, int32_t field0, int32_
    (in points at field `field0` for the COL1 pass, at the stage input for COL0_INV_PRO.) */
 int exb_slab_pass_peer(exb_plan *plan, void *stream, int32_t pass, int32_t field0, int32_t nfields,
                        const void *in, void *const *peer_out);
+/* last-axis pitch (complex elements) of the FIELD buffers the slab passes exchange: the inverse fields written by
+   COL0_INV_PRO / read by COL1_INV_NL and ROW_NL, the forward fields written by ROW_NL / COL1_FWD_NL and read by
+   COL0_FWD_EPI are (nfields, N/P, N, pitch) resp. (nfields, N, N/P, pitch).  pitch = kmax + 1 rounded up to 16 when the
+   plan runs the fast kernels with a dealiasing mask (the transposes then ship only the wavenumbers inside the mask),
+   N/2 + 1 otherwise.  State buffers (U, OUT, S) and the plain transform passes stay dense (N/2 + 1). */
+int exb_plan_field_pitch(const exb_plan *plan);
 /* number of single-field inverse / forward transforms per N(u) evaluation of this plan */
 int exb_plan_nl_fields(const exb_plan *plan, int32_t *n_inv, int32_t *n_fwd);
 

@@ -51,7 +51,7 @@ def main():
         ref = ox.repeat(getattr(ox, name)(3, L, N, dt, order=order), 3)(u0)
         single = ex.repeat(st, 3, spectral_carry=True)(torch.as_tensor(u0, device="cuda")).cpu().numpy()
         # peer-memory stores, then every combination of {pipelined, serial} x {raw all-to-all buffers, packed}
-        want_peer = slab.peer_stores
+        want_peer = True   # (opt-in in production since round 2; always exercised here)
         for peer, overlap, raw in ((True, True, True), (False, True, True), (False, True, False),
                                    (False, False, True), (False, False, False)):
             if peer and not want_peer:

@@ -92,8 +92,10 @@ def _slab_worker(rank, ws, port, q):
         n = N // ws
         g = torch.arange(F * N * N * K, dtype=torch.float32).reshape(F, N, N, K)
         g = torch.complex(g, -g)
-        a = g[:, rank * n:(rank + 1) * n].contiguous()       # physical slab: split over axis 0
-        b = g[:, :, rank * n:(rank + 1) * n].contiguous()    # spectral slab: split over axis 1
+        from exponax_b200._spectral import SLAB_CYCLIC, slab_indices
+        a = g[:, rank * n:(rank + 1) * n].contiguous()       # physical slab: split over axis 0 (contiguous x-planes)
+        b = g[:, :, slab_indices(rank, ws, N)].contiguous()  # spectral slab: split over axis 1 (cyclic by default)
+        owner = (lambda i: (i % ws, i // ws)) if SLAB_CYCLIC else (lambda i: (i // n, i % n))
         assert torch.equal(transpose_a_to_b(a), b)
         assert torch.equal(transpose_b_to_a(b), a)
         assert torch.equal(transpose_b_to_a(transpose_a_to_b(a)), a)
@@ -104,12 +106,11 @@ def _slab_worker(rank, ws, port, q):
         for f in range(F):
             raw = torch.empty_like(a[f])
             exchange_b_to_a_raw(b[f], raw)
-            seg = raw.view(ws, n, n, K)                                  # [src][x][k1_r][K]
-            assert torch.equal(seg.permute(1, 0, 2, 3).reshape(n, N, K), a[f])
             flat = raw.reshape(-1)
             for x in range(n):
-                for i in (0, n - 1, n, N - 1):
-                    off = (i // n) * (n * n * K) + x * (n * K) + (i % n) * K
+                for i in range(N):   # entry i of an axis-1 line: block [owner rank] of the buffer, local position
+                    r, loc = owner(i)
+                    off = r * (n * n * K) + x * (n * K) + loc * K
                     assert torch.equal(flat[off:off + K], a[f, x, i])
             back = torch.empty_like(b[f])
             exchange_a_to_b_raw(raw, back)

@@ -713,6 +713,14 @@ def test_wave_stepper(D, N):
     assert rel(host(ex.vmap(st)(dev(u0))), per_sample(ost, u0)) < F32_STEP
     trj = host(ex.rollout(st, 5, include_init=True)(dev(u0[0])))
     assert trj.shape == (6, 2) + (N,) * D
+    # the 2 x 2 per-mode map runs natively inside the fused rollout (exb_desc.lin_matrix), incl. sub-stepping
+    assert st._plan() is not None and ex._utils._native_target(st) is not None
+    assert rel(trj, ox.rollout(ost, 5, include_init=True)(u0[0])) < 5e-6
+    n0 = st._plan().launch_count()
+    rep = host(ex.vmap(ex.repeat(ex.RepeatedStepper(st, 4), 2))(dev(u0)))
+    assert st._plan().launch_count() > n0
+    assert rel(rep, per_sample(ox.repeat(ost, 8), u0)) < 1e-5
+    assert rel(host(st.step_fourier(dev(ox.fft(u0[0], num_spatial_dims=D)))), ox.fft(ost(u0[0]), num_spatial_dims=D)) < 5e-6
     if D == 1:
         k0 = 3
         x = np.linspace(0, L, N, endpoint=False)
@@ -753,7 +761,8 @@ def test_1d_grids_beyond_the_persistent_kernel(name, kw, N, order, x64):
     dt_ = np.float64 if x64 else np.float32
     L, dt = 20.0, 1e-3
     u0 = ic(1, N, [0, 1], dtype=dt_)
-    st = getattr(ex.stepper, name)(1, L, N, dt, order=order, **kw)
+    mod = ex.stepper.reaction if name == "FisherKPP" else ex.stepper
+    st = getattr(mod, name)(1, L, N, dt, order=order, **kw)
     ost = getattr(ox, name)(1, L, N, dt, order=order, dtype=dt_, **kw) if x64 else getattr(ox, name)(1, L, N, dt, order=order, **kw)
     assert st._plan() is None and st._integrator._plan(1, N, L).fused_ok() is False
     tol = 1e-11 if x64 else F32_STEP
@@ -920,6 +929,93 @@ def test_forced_stepper_and_aux_rollout():
     assert trj.shape == (3, 1, N) and rel(trj[-1], u) < 5e-5
     uh, fh = ox.fft(u0, num_spatial_dims=1), ox.fft(f, num_spatial_dims=1)
     assert rel(host(fs.step_fourier(dev(uh), dev(fh))), ost.step_fourier(uh + np.float32(dt) * fh)) < F32_STEP
+
+
+@pytest.mark.parametrize("name,D,N,C,kw", [
+    ("Burgers", 1, 256, 1, dict(diffusivity=0.05)),                  # fast 1-D persistent kernel
+    ("KortewegDeVries", 1, 96, 1, dict()),                           # generic 1-D kernel
+    ("KolmogorovFlowVorticity", 2, 128, 1, dict()),                  # fast 2-D passes
+    ("Burgers", 2, 24, 2, dict()),                                   # generic N-D kernels
+])
+def test_forcing_rides_inside_the_fused_rollout(name, D, N, C, kw):
+    """ForcedStepper and aux-taking rollouts (exponax/_forced_stepper.py:61-86, _utils.py:137-163) through
+    exb_rollout_forced: constant and per-step forcings, single and batched, both batch layouts, repeat; every call is
+    ONE native call (launch counter) and matches the oracle's `step(u + dt f)` loop."""
+    L, dt, n = 2 * np.pi, 0.005, 4
+    rng = np.random.default_rng(N + D)
+    u0 = ic(D, N, range(3), C=C)
+    fc = (0.3 * rng.standard_normal((3, C) + (N,) * D)).astype(np.float32)          # one constant forcing per trajectory
+    ft = (0.3 * rng.standard_normal((3, n, C) + (N,) * D)).astype(np.float32)       # per-step forcings
+    st = getattr(ex.stepper, name)(D, L, N, dt, **kw)
+    ost = getattr(ox, name)(D, L, N, dt, **kw)
+    fs = ex.ForcedStepper(st)
+    assert ex._utils._forced_target(fs) is not None
+
+    def ref_rollout(u, f_of_step, include_init=False):
+        trj = [u] if include_init else []
+        for i in range(n):
+            u = ost(u + np.float32(dt) * f_of_step(i))
+            trj.append(u)
+        return np.stack(trj)
+
+    plan = st._plan()
+    # single step, single trajectory and batched
+    assert rel(host(fs(dev(u0[0]), dev(fc[0]))), ost(u0[0] + np.float32(dt) * fc[0])) < F32_STEP
+    got = host(ex.vmap(fs)(dev(u0), dev(fc)))
+    assert rel(got, np.stack([ost(u0[b] + np.float32(dt) * fc[b]) for b in range(3)])) < F32_STEP
+    # constant forcing, unbatched, include_init
+    n0 = plan.launch_count()
+    trj = host(ex.rollout(fs, n, takes_aux=True, constant_aux=True, include_init=True)(dev(u0[0]), dev(fc[0])))
+    assert trj.shape == (n + 1, C) + (N,) * D
+    assert rel(trj, ref_rollout(u0[0], lambda i: fc[0], include_init=True)) < 5e-5
+    assert plan.launch_count() > n0                                   # went through the native plan
+    # per-step forcing, vmap(rollout): (B, n, ...) in, (B, n, ...) out
+    trj = host(ex.vmap(ex.rollout(fs, n, takes_aux=True, constant_aux=False))(dev(u0), dev(ft)))
+    ref = np.stack([ref_rollout(u0[b], lambda i, b=b: ft[b, i]) for b in range(3)])
+    assert trj.shape == ref.shape and rel(trj, ref) < 5e-5
+    # per-step forcing, rollout(vmap): time-major (n, B, ...)
+    trj = host(ex.rollout(ex.vmap(fs), n, takes_aux=True, constant_aux=False)(dev(u0), dev(np.swapaxes(ft, 0, 1).copy())))
+    assert trj.shape == (n, 3, C) + (N,) * D and rel(trj, np.swapaxes(ref, 0, 1)) < 5e-5
+    # repeat with a constant per-trajectory forcing
+    fin = host(ex.vmap(ex.repeat(fs, n, takes_aux=True, constant_aux=True))(dev(u0), dev(fc)))
+    assert rel(fin, np.stack([ref_rollout(u0[b], lambda i, b=b: fc[b])[-1] for b in range(3)])) < 5e-5
+
+
+@pytest.mark.parametrize("name,D,N,C,order,params", [
+    ("Burgers", 1, 256, 1, 2, [dict(diffusivity=0.02), dict(diffusivity=0.05), dict(diffusivity=0.1)]),
+    ("Burgers", 1, 100, 1, 4, [dict(diffusivity=0.02), dict(diffusivity=0.2)]),
+    ("KuramotoSivashinsky", 1, 128, 1, 2, [dict(second_order_scale=1.0), dict(second_order_scale=0.8), dict(second_order_scale=1.2)]),
+    ("KolmogorovFlowVorticity", 2, 128, 1, 2, [dict(diffusivity=0.001), dict(diffusivity=0.01)]),
+    ("NavierStokesVelocity", 3, 16, 3, 2, [dict(diffusivity=0.01), dict(diffusivity=0.05)]),
+    ("Diffusion", 1, 64, 1, 0, [dict(diffusivity=0.01), dict(diffusivity=0.1), dict(diffusivity=1.0)]),
+])
+def test_stepper_ensemble_per_trajectory_tables(name, D, N, C, order, params):
+    """Ensembles of steppers (the reference's eqx.filter_vmap over constructor arguments,
+    docs/examples/performance_hints.ipynb): ONE plan with per-trajectory coefficient tables; step, grouped batch,
+    time-major rollout and sub-stepped repeat vs every member's own oracle."""
+    L, dt = (60.0, 0.1) if name == "KuramotoSivashinsky" else (2 * np.pi, 0.005)
+    kw0 = {} if order == 0 else dict(order=order)
+    members = [getattr(ex.stepper, name)(D, L, N, dt, **kw0, **p) for p in params]
+    oracles = [getattr(ox, name)(D, L, N, dt, **kw0, **p) for p in params]
+    S = len(members)
+    ens = ex.StepperEnsemble(members)
+    u0 = ic(D, N, range(2 * S), C=C)
+    got = host(ens(dev(u0[:S])))
+    ref = np.stack([oracles[s](u0[s]) for s in range(S)])
+    assert rel(got, ref) < F32_STEP, rel(got, ref)
+    for s in range(S):      # and every member differs from its neighbour (the tables really are per trajectory)
+        assert rel(got[s], oracles[(s + 1) % S](u0[s])) > 10 * F32_STEP
+    # two trajectories per member: member s advances [2 s, 2 s + 2)
+    got2 = host(ens(dev(u0)))
+    ref2 = np.stack([oracles[b // 2](u0[b]) for b in range(2 * S)])
+    assert rel(got2, ref2) < F32_STEP
+    trj = host(ex.rollout(ens, 3, include_init=True)(dev(u0[:S])))
+    reft = np.stack([ox.rollout(oracles[s], 3, include_init=True)(u0[s]) for s in range(S)], axis=1)
+    assert trj.shape == (4, S, C) + (N,) * D and rel(trj, reft) < 5e-5
+    fin = host(ex.repeat(ex.RepeatedStepper(ens, 2), 2)(dev(u0[:S])))
+    assert rel(fin, np.stack([ox.repeat(oracles[s], 4)(u0[s]) for s in range(S)])) < 5e-5
+    with pytest.raises(ValueError, match="multiple of"):
+        ens(dev(u0[:S + 1]))
 
 
 def test_user_stepper_with_builtin_nonlinear_fun_runs_fused():
