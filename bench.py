@@ -84,6 +84,8 @@ def run_c5(args, w, rank, world, local_rank):
         slab.peer_stores = False
     if args.peer_stores:
         slab.peer_stores = True
+    if args.exchange:
+        slab.ce_exchange = args.exchange == "ce"
     t_ctor = time.time() - t0
     # Taylor-Green + small-mode perturbation generated on the device, slab by slab (never on the host)
     n = N // world
@@ -133,7 +135,10 @@ def run_c5(args, w, rank, world, local_rank):
         abytes = 90 * F                       # pass model per ETDRK2 step, whole field
         per_gpu = abytes / world / (total_ms / args.steps * 1e-3) / 1e9
         # all-to-all: 2 stages x (6 inverse + 3 forward) field transposes, (P-1)/P of each slab leaves the GPU
-        a2a = 2 * 9 * (N * n * (N // 2 + 1) * 8) * (world - 1) / max(world, 1)
+        # (payload = the compact field pitch: only the last-axis wavenumbers inside the dealiasing mask are shipped)
+        kp = int(getattr(slab, "Kp", N // 2 + 1))
+        a2a = 2 * 9 * (N * n * kp * 8) * (world - 1) / max(world, 1)
+        a2a_unpruned = 2 * 9 * (N * n * (N // 2 + 1) * 8) * (world - 1) / max(world, 1)
         line = {"metric": "ETDRK grid-point*steps/s", "value": N**3 * args.steps / (total_ms * 1e-3),
                 "unit": "grid-point*steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
@@ -141,13 +146,17 @@ def run_c5(args, w, rank, world, local_rank):
                 "config": {"workload": f"c5: {w['desc']}", "N": N, "D": 3, "order": 2, "channels": 3,
                            "parallelism": f"slab decomposition x{world}",
                            "carry": "spectral (step_fourier loop)",
-                           "transposes": ("fused into the pass kernels' stores over NVLink peer memory (symmetric memory) + barrier"
+                           "transposes": ("copy-engine block copies into the peers' symmetric-memory buffers (cudaMemcpyAsync over "
+                                          "NVLink on a second stream) + one barrier per transpose"
+                                          if getattr(slab, "ce_exchange", False) and getattr(slab, "_peer", None) is not None
+                                          else "fused into the pass kernels' stores over NVLink peer memory (symmetric memory) + barrier"
                                           if slab.peer_stores and getattr(slab, "_peer", None) is not None
                                           else "all_to_all_single (NCCL)" + (", pipelined per field on a second stream" if slab.overlap else "")),
                            "peer_store_fallback_reason": getattr(slab, "_peer_error", None)},
                 "roofline": {"bound": "hbm", "achieved": per_gpu, "peak": peak, "unit": "GB/s", "frac": per_gpu / peak,
                              "traffic": None, "algorithmic_bytes_per_step_all_gpus": abytes,
-                             "alltoall_bytes_per_gpu_per_step": a2a,
+                             "alltoall_bytes_per_gpu_per_step": a2a, "alltoall_bytes_unpruned": a2a_unpruned,
+                             "axis1_distribution": "cyclic" if getattr(slab, "cyclic", False) else "block",
                              "alltoall_GBs_per_gpu": a2a / (total_ms / args.steps * 1e-3) / 1e9},
                 "cpu_baseline": None, "e2e": None, "gpu_launches": int(launches), "finite": finite,
                 "spectral_energy": float(energy.item()), "ctor_seconds": t_ctor, "max_mem_gb_rank0": mem_gb}
@@ -577,6 +586,8 @@ def main():
                     help="c5: NCCL all-to-all transposes instead of pass kernels storing into peer memory")
     ap.add_argument("--peer-stores", action="store_true",
                     help="c5: pass kernels store into peer memory over NVLink instead of the NCCL all-to-all (opt-in)")
+    ap.add_argument("--exchange", default=None, choices=["nccl", "ce"],
+                    help="c5: transposes through NCCL all-to-all or as copy-engine peer copies (symmetric memory)")
     ap.add_argument("--no-overlap", action="store_true", help="c5: do not pipeline transposes against passes")
     args = ap.parse_args()
 

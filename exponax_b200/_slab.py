@@ -243,6 +243,10 @@ class SlabStepper:
         env = os.environ.get("EXB_SLAB_PEER_STORES", "auto")
         self.peer_stores = env == "1"
         self.prune_peers = os.environ.get("EXB_SLAB_PRUNE_PEERS", "1") != "0"
+        # Transposes as PEER COPIES of whole blocks into the peers' symmetric-memory buffers (cudaMemcpyAsync on a
+        # second stream: the copy engines move the data over NVLink, no SM is taken from the pass kernels that run
+        # at the same time -- NCCL's all-to-all is an SM kernel and competes with them) + one barrier per transpose.
+        self.ce_exchange = os.environ.get("EXB_SLAB_EXCHANGE", "nccl") == "ce"
         from ._spectral import SLAB_CYCLIC
         self.cyclic = bool(SLAB_CYCLIC) and self.P > 1
         self.Kp, self.kept = self.Nh, None
@@ -388,6 +392,9 @@ class SlabStepper:
                 # generic kernels (grid size without a fast instantiation): raised by the FIRST call on every
                 # rank alike, before anything was enqueued -> use the all-to-all path from now on
                 self.peer_stores = False
+        ce = self._peer_buffers() if (self.ce_exchange and self.raw_exchange and self.P > 1) else None
+        if ce is not None:
+            return self._step_fourier_ce(uh, out, S, ce)
         # the B-layout buffer is shared by the inverse fields and (later in the stage) the forward fields
         nb = max(self.n_inv, self.n_fwd)
         wb = self._buf("w_b", nb, fields=True)
@@ -459,10 +466,63 @@ class SlabStepper:
                 self._comm_stream().wait_event(done)
         return out
 
+    def _step_fourier_ce(self, uh, out, S, peer):
+        """One ETDRK step with copy-engine transposes: per field, the pass that produces it runs on the compute
+        stream while the (P - 1) block copies of the previous field travel on the copy stream; a symmetric-memory
+        barrier closes each transpose.  Buffers: winv_a / wfwd_b live in symmetric memory (written by the peers),
+        winv_b / wfwd_a are local.  Hazards as for the peer-store path: a peer overwrites my
+        winv_a (wfwd_b) only after the barrier that follows my last read of it in stream order."""
+        lib, h = nat.lib(), self.plan().handle
+        main, comm = torch.cuda.current_stream(), self._comm_stream()
+        me, P = self.rank, self.P
+        wb = self._buf("w_b", self.n_inv, fields=True)
+        winv_b = wb.view(self.n_inv, P, self.n, self.n, self.Kp)          # [field][x-block of rank p][x][k1][K]
+        wfwd_a = self._buf("wfwd_a", self.n_fwd, fields=True)
+        wfwd_a_blk = wfwd_a.view(self.n_fwd, P, self.n, self.n, self.Kp)   # raw order [k1-owner p][x][k1 local][K]
+        winv_a, wfwd_b = peer["winv_a"], peer["wfwd_b"]
+        for s in range(self.order):
+            si = etdrk_stage_input(self.order, s)
+            src = uh if si < 0 else S[si]
+            for f in range(self.n_inv):
+                nat.check(lib.exb_slab_inv_pro_fields(h, main.cuda_stream, f, 1, A.ptr(src), A.ptr(wb)))
+                ready = torch.cuda.Event()
+                ready.record(main)
+                with torch.cuda.stream(comm):
+                    comm.wait_event(ready)
+                    for d in range(P):                                   # my x-block for rank p -> its winv_a[f][me]
+                        p = (me + d) % P
+                        peer["remote_inv"][p][f, me].copy_(winv_b[f, p], non_blocking=True)
+            with torch.cuda.stream(comm):
+                peer["hdl_inv"].barrier(channel=0)
+                done = torch.cuda.Event()
+                done.record(comm)
+            main.wait_event(done)
+            self._pass(nat.SLAB_COL1_INV_NL | nat.SLAB_SEGMENTED, self.n_inv, winv_a, winv_a)
+            self._pass(nat.SLAB_ROW_NL, self.n_inv, winv_a, wfwd_a)
+            for g in range(self.n_fwd):
+                self._pass(nat.SLAB_COL1_FWD_NL | nat.SLAB_SEGMENTED, 1, wfwd_a[g], wfwd_a[g])
+                ready = torch.cuda.Event()
+                ready.record(main)
+                with torch.cuda.stream(comm):
+                    comm.wait_event(ready)
+                    for d in range(P):                                   # my k1-block of rank p -> its wfwd_b[g][me]
+                        p = (me + d) % P
+                        peer["remote_fwd"][p][g, me].copy_(wfwd_a_blk[g, p], non_blocking=True)
+            with torch.cuda.stream(comm):
+                peer["hdl_fwd"].barrier(channel=0)
+                done = torch.cuda.Event()
+                done.record(comm)
+            main.wait_event(done)
+            self._pass(nat.SLAB_COL0_FWD_EPI, self.n_fwd, wfwd_b, None, stage=s, U=uh, OUT=out, S=S)
+            fin = torch.cuda.Event()
+            fin.record(main)
+            comm.wait_event(fin)     # the next stage's copies overwrite the peers' buffers only after everyone's barrier
+        return out
+
     def _peer_buffers(self):
         """winv_a (n_inv fields, layout A) and wfwd_b (n_fwd fields, layout B) in symmetric memory + the peers'
         base pointers; None (and peer_stores switched off on EVERY rank) if symmetric memory is unavailable."""
-        if getattr(self, "_peer", None) is not None or not self.peer_stores:
+        if getattr(self, "_peer", None) is not None or not (self.peer_stores or self.ce_exchange):
             return getattr(self, "_peer", None)
         import ctypes
         ok, peer = 1, None
@@ -482,12 +542,23 @@ class SlabStepper:
             wfwd_b, hdl_fwd, ptrs_fwd = make(self.n_fwd, (self.N, self.n, self.Kp))
             peer = dict(winv_a=winv_a, hdl_inv=hdl_inv, ptrs_inv=ptrs_inv, wfwd_b=wfwd_b, hdl_fwd=hdl_fwd,
                         ptrs_fwd=ptrs_fwd)
+
+            def remote(hdl, nfields):
+                # every rank's buffer mapped into this process, viewed [field][block of rank q][n][n][Kp]
+                out = []
+                for r in range(self.P):
+                    t = hdl.get_buffer(r, (nfields * per_field * 2,), rt)
+                    out.append(torch.view_as_complex(t.view(-1, 2)).view(nfields, self.P, self.n, self.n, self.Kp))
+                return out
+
+            peer["remote_inv"] = remote(hdl_inv, self.n_inv)
+            peer["remote_fwd"] = remote(hdl_fwd, self.n_fwd)
         except Exception as e:  # noqa: BLE001 -- any failure means: no peer memory here
             ok, self._peer_error = 0, repr(e)
         flag = torch.tensor([ok], device="cuda", dtype=torch.int32)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)     # all ranks take the same path
         if int(flag.item()) == 0:
-            self.peer_stores, peer = False, None
+            self.peer_stores, self.ce_exchange, peer = False, False, None
         self._peer = peer
         return peer
 

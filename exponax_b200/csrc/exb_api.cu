@@ -616,8 +616,12 @@ template <class T> struct PlanImpl : exb_plan {
     }
     return true;
   }
+  // can the ETDRK2 epilogue of this plan run the next evaluation's prologue pass in the same launch?
+  bool can_fuse_prologue() const {
+    return fast_nd && D == 2 && C == 1 && K.order == 2 && nranks == 1 && masked_stream_ok() && !getenv("EXB_NO_FUSE");
+  }
   int col_fwd(cudaStream_t st, long long batch, int mode, int stage, const cpx<T>* wfwd, cpx<T>* nl_out,
-              const StateBufs<T>& sb) {
+              const StateBufs<T>& sb, cpx<T>* fuse_winv = nullptr) {
     ColParams<T> p;
     memset(&p, 0, sizeof(p));
     p.P = P;
@@ -637,6 +641,10 @@ template <class T> struct PlanImpl : exb_plan {
     col_geom(p, 0);
     p.fpitch = Nhp;
     p.fM = Mf;
+    if (fuse_winv && mode == COL_FWD_EPI) {
+      p.fuse_next = 1;
+      p.out = fuse_winv;
+    }
     // last stage: the dealiased modes (u+ = exp(dt L) u) go through a streaming pass instead of the tiled epilogue
     const bool masked_stream = fast_nd && mode == COL_FWD_EPI && stage == K.order - 1 && masked_stream_ok();
     p.masked_external = masked_stream ? 1 : 0;
@@ -753,8 +761,9 @@ template <class T> struct PlanImpl : exb_plan {
   }
 
   // N(state) -> forward fields in w.Wfwd (all passes except the final forward column pass)
-  int nl_front_nd(cudaStream_t st, long long batch, const cpx<T>* state, const Ws& w) {
-    int rc = col_inv_pro(st, batch, state, w.Winv);
+  // have_winv: the inverse fields of `state` were already produced by the previous (fused) epilogue pass
+  int nl_front_nd(cudaStream_t st, long long batch, const cpx<T>* state, const Ws& w, bool have_winv = false) {
+    int rc = have_winv ? EXB_OK : col_inv_pro(st, batch, state, w.Winv);
     if (rc) return rc;
     if (D == 3) {
       rc = col_plain<+1>(st, 1, batch, P.n_inv, w.Winv, w.Winv, PRUNE_COLS | PRUNE_IN_ROWS, false, nullptr, 0, true);
@@ -770,7 +779,10 @@ template <class T> struct PlanImpl : exb_plan {
     return EXB_OK;
   }
 
-  int step_fourier_nd(cudaStream_t st, long long batch, const cpx<T>* in, cpx<T>* out, const Ws& w) {
+  // have_winv: the previous step's last epilogue already ran this step's first prologue pass (fused);
+  // want_next: another step follows directly on `out` (no physical-space round trip in between) -> fuse its prologue
+  int step_fourier_nd(cudaStream_t st, long long batch, const cpx<T>* in, cpx<T>* out, const Ws& w,
+                      bool have_winv = false, bool want_next = false) {
     if (K.order == 0 && K.lin_matrix) {
       long long total = batch * M;
       int grid = (int)((total + 255) / 256 < (long long)sm_count * 16 ? (total + 255) / 256 : (long long)sm_count * 16);
@@ -791,13 +803,18 @@ template <class T> struct PlanImpl : exb_plan {
     sb.U = in;
     sb.OUT = out;
     for (int i = 0; i < 4; ++i) sb.S[i] = w.S[i];
+    const bool fuse = can_fuse_prologue();
+    bool fused_prev = have_winv && fuse;
     for (int s = 0; s < K.order; ++s) {
       int si = etdrk_stage_input(K.order, s);
       const cpx<T>* src = si < 0 ? in : w.S[si];
-      int rc = nl_front_nd(st, batch, src, w);
+      int rc = nl_front_nd(st, batch, src, w, fused_prev);
       if (rc) return rc;
-      rc = col_fwd(st, batch, COL_FWD_EPI, s, w.Wfwd, nullptr, sb);
+      // (the row pass has consumed Winv by the time the epilogue of the same stage overwrites it: stream order)
+      const bool fuse_this = fuse && (s < K.order - 1 || want_next);
+      rc = col_fwd(st, batch, COL_FWD_EPI, s, w.Wfwd, nullptr, sb, fuse_this ? w.Winv : nullptr);
       if (rc) return rc;
+      fused_prev = fuse_this;
     }
     return EXB_OK;
   }
@@ -1125,6 +1142,7 @@ template <class T> struct PlanImpl : exb_plan {
     rc = fft_nd(st, batch, C, (const T*)u0, fsz, w.Uh);
     if (rc) return rc;
     T* phys_scratch = (T*)w.Wfwd;  // >= C*G reals per batch element (M*2 >= G)
+    bool have_winv = false;
     for (long long s = 0; s < n_saved; ++s) {
       if (frc.f) {  // ForcedStepper: u_hat += dt * f_hat of step s
         const long long per = (long long)C * M, total = per * batch;
@@ -1135,8 +1153,15 @@ template <class T> struct PlanImpl : exb_plan {
         CUDA_OK(cudaGetLastError());
       }
       for (int sub = 0; sub < substeps; ++sub) {
-        rc = step_fourier_nd(st, batch, w.Uh, w.Uh, w);
+        // the next ETDRK step starts from this step's spectral result when another sub-step follows, or (spectral
+        // carry) when the next saved step does without the physical-space round trip; a forcing changes the state
+        // in between, so no fusion across it
+        const bool more_sub = sub + 1 < substeps;
+        const bool more_saved = s + 1 < n_saved && spectral_carry && (final_only) && !frc.f;
+        const bool want_next = more_sub || more_saved;
+        rc = step_fourier_nd(st, batch, w.Uh, w.Uh, w, have_winv, want_next);
         if (rc) return rc;
+        have_winv = want_next && can_fuse_prologue();
       }
       const bool last = s == n_saved - 1;
       const bool store = !final_only || last;

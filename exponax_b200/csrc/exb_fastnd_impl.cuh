@@ -29,16 +29,16 @@ template <class K> int set_smem(K kernel, size_t smem, const char** err) {
   return EXB_OK;
 }
 
-template <int N, int TW, class S, int NFWD, int MODE, int DIR, int STG = 0>
+template <int N, int TW, class S, int NFWD, int MODE, int DIR, int STG = 0, int FUSE = 0>
 int launch_col_stg(cudaStream_t st, const ColParams<float>& p, long long grid, const char** err) {
   constexpr bool usm = MODE == COL_INV_PRO && S::C == 1 && EXB_INVPRO_SMEM_U != 0;  // parked stage input
-  constexpr int nstash = usm ? (S::kind == EXB_NL_VORTICITY_2D ? 2 : 1) : 0;          // (+ the stream function)
+  constexpr int nstash = FUSE ? 1 : (usm ? (S::kind == EXB_NL_VORTICITY_2D ? 2 : 1) : 0);  // (+ the stream function)
   const size_t smem = (size_t)(Fft8Tw<N>::SIZE + ExTile<TW>::rows(N) * TW + nstash * N * TW) * sizeof(cpx<float>);
   // (set on every launch: the attribute is per device, and a process may drive several devices)
-  if (int rc = set_smem(col_fast_kernel<N, TW, S, NFWD, MODE, DIR, STG>, smem, err)) return rc;
+  if (int rc = set_smem(col_fast_kernel<N, TW, S, NFWD, MODE, DIR, STG, FUSE>, smem, err)) return rc;
   ColParams<float> q = p;
   q.TW = TW;
-  col_fast_kernel<N, TW, S, NFWD, MODE, DIR, STG><<<(unsigned)grid, (N / 8) * TW, smem, st>>>(q);
+  col_fast_kernel<N, TW, S, NFWD, MODE, DIR, STG, FUSE><<<(unsigned)grid, (N / 8) * TW, smem, st>>>(q);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     *err = cudaGetErrorString(e);
@@ -136,6 +136,11 @@ int launch_col(cudaStream_t st, const ColParams<float>& p, long long grid, const
   }
   if constexpr (MODE == COL_FWD_EPI) {
     // ETDRK2 (the default order): stage updates with compile-time operand sets
+    if constexpr (S::C == 1 && S::D == 2) {
+      // + the next evaluation's prologue pass fused in (p.fuse_next, set by the host when a step follows directly)
+      if (p.fuse_next && p.K.order == 2 && p.stage == 0) return launch_col_stg<N, TW, S, NFWD, MODE, DIR, 1, 1>(st, p, grid, err);
+      if (p.fuse_next && p.K.order == 2 && p.stage == 1) return launch_col_stg<N, TW, S, NFWD, MODE, DIR, 2, 1>(st, p, grid, err);
+    }
     if (p.K.order == 2 && p.stage == 0) return launch_col_stg<N, TW, S, NFWD, MODE, DIR, 1>(st, p, grid, err);
     if (p.K.order == 2 && p.stage == 1) return launch_col_stg<N, TW, S, NFWD, MODE, DIR, 2>(st, p, grid, err);
   }

@@ -44,6 +44,8 @@ template <class T> struct ColParams {
   int fpitch;
   long long fM;
   int masked_external;     // fast COL_FWD_EPI: the dealiased modes are advanced by etdrk_masked_linear_kernel, skip them
+  int fuse_next;           // fast COL_FWD_EPI (ETDRK2, one-channel 2-D kinds): also run the NEXT evaluation's prologue
+                           //   pass on the value this pass produces; `out` = inverse-field buffer
   int seg_len;             // COL_PLAIN, slab transposes without pack/unpack: line entry i lives at
   long long seg_stride;    //   (i / seg_len) * seg_stride + (i % seg_len) * line_stride   (seg_len = 0: off)
   int seg_cyclic;          //   P > 0: cyclic axis-1 distribution, entry i at (i % P) * seg_stride + (i / P) * line_stride

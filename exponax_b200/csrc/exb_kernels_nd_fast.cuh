@@ -58,6 +58,61 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// One-channel 2-D prologue + inverse axis-0 transforms of the fields [f_begin, f_end) for the column owned by this
+// thread row: the stage input sits in a thread-private stash `us[q * NT]` (zeros at dealiased entries).  Shared by
+// the persistent prologue kernel and by the FUSED epilogue (col_fast_kernel<.., FUSE = 1>).
+template <int N, int TW, class S, class Ex>
+__device__ __forceinline__ void invpro_fields_1ch(const NlParams<float>& Pn, const cpx<float>* us, int NT, int j, bool col_keep,
+                                                  unsigned rowmask, float kd1, int f_begin, int f_end, const Ex& ex,
+                                                  const cpx<float>* tw, cpx<float>* dst0, size_t fM, size_t fqstride) {
+  constexpr int P = N / 8;
+  constexpr bool VORT = S::kind == EXB_NL_VORTICITY_2D;
+  const cpx<float> zero(0.f, 0.f);
+  auto kd0_of = [&](int q) { return Pn.dscale * (float)(j + P * q - (q >= 4 ? N : 0)); };
+  for (int f = f_begin; f < f_end; ++f) {
+    cpx<float> v[8];
+    if (VORT) {
+      // u = +d_y psi, v = -d_x psi, d_x w, d_y w with psi = w / laplacian (:= w at k = 0): i * (+-kd) * (psi or w)
+      const bool use_k1 = f == 0 || f == 3;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float a = kd0_of(q);
+        float kd = use_k1 ? kd1 : a;
+        if (f == 1) kd = -kd;
+        cpx<float> src = us[q * NT];
+        if (f < 2) {
+          const float lap = -(a * a) - (kd1 * kd1);
+          src = (lap == 0.f ? 1.f : exb_rcp(lap)) * src;
+        }
+        v[q] = mul_i(kd * src);
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        cpx<float> val = zero;
+        if (col_keep && ((rowmask >> q) & 1u)) {
+          ModeK<float> m;
+          m.kd[0] = kd0_of(q);
+          m.kd[1] = kd1;
+          m.kd[2] = 0.f;
+          m.keep = true;
+          m.is_inj = false;
+          m.is_dc = false;
+          cpx<float> u[EXB_MAXC] = {us[q * NT], zero, zero};
+          val = nl_inv_field<float, S>(Pn, f, u, m);
+        }
+        v[q] = val;
+      }
+    }
+    fft8_run<N, +1>(v, ex, j, tw);
+    if (col_keep) {
+      cpx<float>* __restrict__ dst = dst0 + (size_t)f * fM;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) dst[q * fqstride] = v[q];
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------- column pass
 // Index bookkeeping is the expensive part of these kernels (ncu r01j: 50-60 % of the executed instructions of a
 // column pass were integer / address / control, the butterflies 20-35 %), so everything that does not depend on
@@ -66,9 +121,14 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // entries of a thread), the wavenumber factors of the fixed axes.  ETDRK2 (the default order) gets its two stage
 // updates as compile-time variants (STG) so that the operand pointers are not re-read per mode.
 //   STG: 0 = order / stage at run time;  1 = ETDRK2 stage 0;  2 = ETDRK2 stage 1 (last)
-template <int N, int TW, class S, int NFWD, int MODE, int DIR, int STG = 0>
+//   FUSE (ETDRK2 epilogue of a one-channel 2-D kind): the value this pass produces -- stage 0: a = E u + c1 N(u),
+//        stage 1: u+ -- is exactly the input of the NEXT evaluation's prologue pass, for the same column, held by
+//        the same thread at the same line entries.  It is parked in a thread-private stash and the n_inv inverse
+//        transforms of the next N(u) run right here (p.out = the inverse-field buffer): one launch, one read of the
+//        stage input and the start-up latency of the prologue pass less per stage.
+template <int N, int TW, class S, int NFWD, int MODE, int DIR, int STG = 0, int FUSE = 0>
 __global__ void __launch_bounds__((N / 8) * TW, (MODE == COL_PLAIN ? 2048 / ((N / 8) * TW)
-                                                 : (MODE == COL_INV_PRO ? 2 : (NFWD == 1 ? 3 : EXB_EPI_MULTI_MINBLOCKS))))
+                                                 : (MODE == COL_INV_PRO ? 2 : (FUSE ? 2 : (NFWD == 1 ? 3 : EXB_EPI_MULTI_MINBLOCKS)))))
 col_fast_kernel(const ColParams<float> p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int P = N / 8;
@@ -313,13 +373,18 @@ col_fast_kernel(const ColParams<float> p) {
 #pragma unroll
     for (int g = 0; g < NFWD; ++g) fft8_run<N, DIR>(W[g], ex, j, tw);
   }
-  if (!act) return;
+  if (!act && !FUSE) return;
   // element offset of (trajectory b, channel 0, entry q = 0) and of the coefficient entry; + q * qstride + c * M
   const size_t off0 = (size_t)b * C * p.M + iw + (size_t)j * ls;
   const size_t ci0 = iw + (size_t)j * ls + (size_t)table_offset(p.K, (long long)b);
   const size_t cstep = p.K.E == 1 ? 0 : (size_t)p.K.M;
+  constexpr int NTF = P * TW;
+  constexpr int TROWSF = ExTile<TW>::PAD ? N + N / 8 : N;
+  cpx<float>* fstash = tile + TROWSF * TW + threadIdx.x;   // FUSE: next stage input [q][thread], thread-private
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
+    if (FUSE) fstash[q * NTF] = zero;                       // dealiased / inactive entries enter the prologue as zeros
+    if (!act) continue;
     const ModeK<float> m = mode_of(q);
     if (masked_skip && !m.keep) {
       if (masked_here) {
@@ -342,14 +407,25 @@ col_fast_kernel(const ColParams<float> p) {
       if (MODE == COL_FWD_NL) {
         p.out[off] = n[c];
       } else if (STG == 1) {   // ETDRK2 stage 0 (_etdrk_2.py:96-98): a = E u + c1 N(u); keep N(u)
-        p.sb.S[0][off] = axpy(p.K.c[0][ci], n[c], p.K.exp_term[ci] * p.sb.U[off]);
+        const cpx<float> a = axpy(p.K.c[0][ci], n[c], p.K.exp_term[ci] * p.sb.U[off]);
+        p.sb.S[0][off] = a;
         p.sb.S[1][off] = n[c];
+        if (FUSE && m.keep) fstash[q * NTF] = a;
       } else if (STG == 2) {   // ETDRK2 stage 1 (_etdrk_2.py:99-101): u+ = a + c2 (N(a) - N(u))
-        p.sb.OUT[off] = axpy(p.K.c[1][ci], n[c] - p.sb.S[1][off], p.sb.S[0][off]);
+        const cpx<float> un = axpy(p.K.c[1][ci], n[c] - p.sb.S[1][off], p.sb.S[0][off]);
+        p.sb.OUT[off] = un;
+        if (FUSE && m.keep) fstash[q * NTF] = un;
       } else {
         etdrk_update(p.K, stage, (long long)ci, off, n[c], p.sb);
       }
     }
+  }
+  if constexpr (FUSE != 0) {
+    // the next evaluation's prologue pass for this column tile (one-channel 2-D kinds; tiles of dealiased columns
+    // write nothing, exactly like the stand-alone pass)
+    if (!any_keep) return;
+    invpro_fields_1ch<N, TW, S>(Pn, fstash, NTF, j, col_keep, rowmask, kd1, 0, Pn.n_inv, ex, tw,
+                                p.out + (size_t)b * Pn.n_inv * fM + foff, fM, fqstride);
   }
 }
 
@@ -420,48 +496,8 @@ __global__ void __launch_bounds__((N / 8) * TW, 2) col_invpro_persistent_kernel(
     if (blk + gridDim.x < nblk) fetch(blk + gridDim.x, buf ^ 1);
     const cpx<float>* us = stash0 + buf * 8 * NT;
     const int f_begin = p.fcount > 0 ? p.f0 : 0, f_end = p.fcount > 0 ? p.f0 + p.fcount : Pn.n_inv;
-    for (int f = f_begin; f < f_end; ++f) {
-      cpx<float> v[8];
-      if (VORT) {
-        // u = +d_y psi, v = -d_x psi, d_x w, d_y w with psi = w / laplacian (:= w at k = 0): i * (+-kd) * (psi or w)
-        const bool use_k1 = f == 0 || f == 3;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float a = kd0_of(q);
-          float kd = use_k1 ? kd1 : a;
-          if (f == 1) kd = -kd;
-          cpx<float> src = us[q * NT];
-          if (f < 2) {
-            const float lap = -(a * a) - (kd1 * kd1);
-            src = (lap == 0.f ? 1.f : exb_rcp(lap)) * src;
-          }
-          v[q] = mul_i(kd * src);
-        }
-      } else {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          cpx<float> val = zero;
-          if (col_keep && ((rowmask >> q) & 1u)) {
-            ModeK<float> m;
-            m.kd[0] = kd0_of(q);
-            m.kd[1] = kd1;
-            m.kd[2] = 0.f;
-            m.keep = true;
-            m.is_inj = false;
-            m.is_dc = false;
-            cpx<float> u[EXB_MAXC] = {us[q * NT], zero, zero};
-            val = nl_inv_field<float, S>(Pn, f, u, m);
-          }
-          v[q] = val;
-        }
-      }
-      fft8_run<N, DIR>(v, ex, j, tw);
-      if (col_keep) {
-        cpx<float>* __restrict__ dst = p.out + ((size_t)b * Pn.n_inv + f) * fM + iw + (size_t)j * fpitch;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) dst[q * fqstride] = v[q];
-      }
-    }
+    invpro_fields_1ch<N, TW, S>(Pn, us, NT, j, col_keep, rowmask, kd1, f_begin, f_end, ex, tw,
+                                p.out + (size_t)b * Pn.n_inv * fM + iw + (size_t)j * fpitch, fM, fqstride);
   }
   cp_async_wait_all();
 }

@@ -52,17 +52,21 @@ def main():
         single = ex.repeat(st, 3, spectral_carry=True)(torch.as_tensor(u0, device="cuda")).cpu().numpy()
         # peer-memory stores, then every combination of {pipelined, serial} x {raw all-to-all buffers, packed}
         want_peer = True   # (opt-in in production since round 2; always exercised here)
-        for peer, overlap, raw in ((True, True, True), (False, True, True), (False, True, False),
+        # (peer = "ce": transposes as copy-engine block copies into the peers' symmetric-memory buffers)
+        for peer, overlap, raw in (("ce", True, True), (True, True, True), (False, True, True), (False, True, False),
                                    (False, False, True), (False, False, False)):
             if peer and not want_peer:
                 continue
             if True:
-                slab.peer_stores, slab.overlap, slab.raw_exchange = peer, overlap, raw
+                slab.ce_exchange = peer == "ce"
+                slab.peer_stores, slab.overlap, slab.raw_exchange = peer is True, overlap, raw
                 got = slab.gather(slab.repeat(slab.scatter(u0), 3)).cpu().numpy()
-                if peer:
+                if peer == "ce":
+                    report[f"{name}_N{N}_ce_active"] = bool(slab.ce_exchange and getattr(slab, "_peer", None) is not None)
+                if peer is True:
                     report[f"{name}_N{N}_peer_active"] = bool(slab.peer_stores and getattr(slab, "_peer", None) is not None)
                     report[f"{name}_N{N}_peer_error"] = getattr(slab, "_peer_error", None)
-                tag = f"{name}_N{N}_peer{int(peer)}_ov{int(overlap)}_raw{int(raw)}"
+                tag = f"{name}_N{N}_peer{peer if peer == 'ce' else int(peer)}_ov{int(overlap)}_raw{int(raw)}"
                 report[f"{tag}_vs_oracle"] = rel(got, ref)
                 report[f"{tag}_vs_single_gpu"] = rel(got, single)
                 assert rel(got, ref) < 5e-5, report
