@@ -77,6 +77,7 @@ SYMBOLS = {
                               C.c_void_p, C.c_void_p, C.c_void_p]),
     "exb_rollout_forced": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_uint32,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_double]),
+    "exb_leray": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_double]),
     "exb_launch_count": (C.c_int64, [C.c_void_p]),
     "exb_plan_fused_ok": (C.c_int, [C.c_void_p]),
     "exb_peak_fp32": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),

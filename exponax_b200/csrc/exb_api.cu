@@ -64,6 +64,7 @@ struct exb_plan {
                            double order, double domain_extent, double* out) = 0;
   virtual int derivative(cudaStream_t st, int64_t nfields, const void* uh, void* out, int order,
                          double domain_extent) = 0;
+  virtual int leray(cudaStream_t st, int64_t nfields, const void* uh, void* out, double domain_extent) = 0;
   virtual int spectrum(cudaStream_t st, int64_t nfields, const void* uh, void* out, int power, int average,
                        void* counts) = 0;
   virtual int ic_shape(cudaStream_t st, int64_t nfields, void* uh, int kind, double param, double domain_extent,
@@ -969,6 +970,18 @@ template <class T> struct PlanImpl : exb_plan {
     return EXB_OK;
   }
 
+  int leray(cudaStream_t st, int64_t nfields, const void* uh, void* out, double domain_extent) override {
+    if (nranks > 1) return fail(EXB_EINVAL, "slab plans only support exb_slab_pass");
+    if (nfields < 1 || !uh || !out) return fail(EXB_EINVAL, "exb_leray: bad arguments");
+    if (!(domain_extent > 0)) return fail(EXB_EINVAL, "exb_leray: domain_extent must be > 0");
+    const long long total = (long long)nfields * M;
+    leray_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        (const cpx<T>*)uh, (cpx<T>*)out, D, N, Nh, M, total, (T)(6.283185307179586476925286766559 / domain_extent));
+    CUDA_OK(cudaGetLastError());
+    ++launches;
+    return EXB_OK;
+  }
+
   int derivative(cudaStream_t st, int64_t nfields, const void* uh, void* out, int order,
                  double domain_extent) override {
     if (nranks > 1) return fail(EXB_EINVAL, "slab plans only support exb_slab_pass");
@@ -1327,6 +1340,10 @@ int exb_fourier_sums(exb_plan* plan, void* stream, int64_t nfields, const void* 
                      int32_t high, double derivative_order, double domain_extent, double* out) {
   if (!plan) return fail(EXB_EINVAL, "null plan");
   return plan->fourier_sums((cudaStream_t)stream, nfields, x_hat, p, low, high, derivative_order, domain_extent, out);
+}
+int exb_leray(exb_plan* plan, void* stream, int64_t nfields, const void* u_hat, void* out_hat, double domain_extent) {
+  if (!plan) return fail(EXB_EINVAL, "null plan");
+  return plan->leray((cudaStream_t)stream, nfields, u_hat, out_hat, domain_extent);
 }
 int exb_derivative(exb_plan* plan, void* stream, int64_t nfields, const void* u_hat, void* out_hat, int32_t order,
                    double domain_extent) {

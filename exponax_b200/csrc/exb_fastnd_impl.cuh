@@ -5,8 +5,10 @@
 #include "exb_kernels_nd_fast.cuh"
 #include "exb_kernels_nd_tma.cuh"
 #include "exb_tma.h"
+// 16-points-per-thread row pass for N = 256 (one shared-memory exchange per transform, exb_row16.cuh): the row pass
+// is bound by the shared-memory pipe; measured on c4 +4.5 % (round-1 code, r02_first) / +1.6 % (final code, r02s)
 #ifndef EXB_ROW16
-#define EXB_ROW16 0
+#define EXB_ROW16 1
 #endif
 #if EXB_ROW16
 #include "exb_row16.cuh"

@@ -66,6 +66,9 @@ template <int R, int DIR> __device__ __forceinline__ void dft_reg(cpx<float>* v)
   if (R == 8) dft8<float, DIR>(v);
 }
 
+#ifndef EXB_1D_DERIVE_TW
+#define EXB_1D_DERIVE_TW 0
+#endif
 // N = R*R point FFT of the line held as v[r] = x[j + R*r] by the R threads j of a group.
 // On return v[r] = X[j + R*r].  xb: per-pair exchange buffer ((R+1)*R complex, padded).
 template <int R, int DIR>
@@ -75,12 +78,30 @@ __device__ __forceinline__ void fft_reg_body(cpx<float> (&v)[R], cpx<float>* xb,
 #pragma unroll
   for (int p = 0; p < R; ++p) xb[(R + 1) * j + xidx<R>(p)] = v[p];  // pad(R*j + X-index)
   __syncwarp();
+#if EXB_1D_DERIVE_TW
+  {
+    // inter-pass twiddles w^(r j), r = 1 .. R-1: only the powers of two are read from shared memory, the others are
+    // products of at most 3 of them (the shared-memory pipe carries 17 % twiddle loads, the FMA pipe has headroom)
+    cpx<float> w[R];
+#pragma unroll
+    for (int b = 1; b < R; b <<= 1) w[b] = twd<float, DIR>(tw2[b * R + j]);
+#pragma unroll
+    for (int r = 3; r < R; ++r)
+      if (r & (r - 1)) w[r] = w[r & (r - 1)] * w[r & -r];          // r = (r without its lowest bit) + lowest bit
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      cpx<float> t = xb[j + (R + 1) * r];
+      v[r] = r > 0 ? t * w[r] : t;
+    }
+  }
+#else
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     cpx<float> t = xb[j + (R + 1) * r];                             // pad(j + R*r)
     if (r > 0) t = t * twd<float, DIR>(tw2[r * R + j]);
     v[r] = t;
   }
+#endif
   dft_reg<R, DIR>(v);
   if (R == 16) {
     cpx<float> o[R];
@@ -93,6 +114,12 @@ __device__ __forceinline__ void fft_reg_body(cpx<float> (&v)[R], cpx<float>* xb,
 
 #ifndef EXB_1D_CTA_SYNC
 #define EXB_1D_CTA_SYNC 1
+#endif
+#ifndef EXB_1D_SPLIT_BAR
+#define EXB_1D_SPLIT_BAR 0
+#endif
+#ifndef EXB_1D_SKEW_NS
+#define EXB_1D_SKEW_NS 0
 #endif
 
 // The step body calls the transform from five places; inlined everywhere it is > 64 KB of code and the
@@ -323,7 +350,22 @@ template <int R, class S, int NINV, int NFWD> struct Fast1d {
       // No data is shared between warps: the barrier only keeps the warps of the CTA at the same place of
       // the (fully unrolled, > 64 KB) step body, so that they share instruction-cache lines instead of
       // each streaming the body from L2 on its own (ncu r01: `no_instruction` was the top stall reason).
+#if EXB_1D_SPLIT_BAR
+      // two half-CTA barriers (even / odd warps) instead of one: the halves drift apart, so that the FMA-pipe phases
+      // (butterflies) of one half overlap the shared-memory phases (exchanges, state updates) of the other
+      {
+        const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        const int half = warp & 1, cnt = ((nw + 1 - half) >> 1) * 32;
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "r"(cnt) : "memory");
+      }
+#else
       __syncthreads();
+#endif
+#if EXB_1D_SKEW_NS
+      // de-phase the odd warps by a fraction of a transform: the butterflies of one half then overlap the exchanges
+      // of the other instead of all warps saturating the FMA pipe and the shared-memory pipe in turns
+      if ((threadIdx.x >> 5) & 1) __nanosleep(EXB_1D_SKEW_NS);
+#endif
 #endif
     }
   }

@@ -1,11 +1,12 @@
-// EXPERIMENTAL -- compiled only with -DEXB_ROW16=1 (scripts/build_variant.sh row16 -DEXB_ROW16=1), NOT part of
-// the default library and not yet run on a GPU.  Round-2 A/B candidate for the N = 256 row pass (config c4).
+// 16-points-per-thread row pass for N = 256 (config c4), the default since round 2 (-DEXB_ROW16=0 restores the
+// 8-points-per-thread row_fast_kernel for this size).
 //
-// Why: the r01j captures show the ROW_NL pass bound by the shared-memory pipe (88-89 % LSU wavefront
-// utilisation): an 8-points-per-thread line FFT exchanges every point twice (three radix passes).  With 16
-// points per thread N = 256 = 16 x 16 needs ONE exchange (the 1-D kernel's fft_reg<16>), the twiddle loads per
-// point halve too; the price is 2x the registers per thread (1 CTA of 256 threads per SM, 16 row pairs in
-// flight per SM as before).  Same math, same streaming accumulation, same pruning as row_fast_kernel.
+// Why: the ROW_NL pass is bound by the shared-memory pipe (86-92 % LSU wavefront utilisation): an 8-points-per-thread
+// line FFT exchanges every point twice (three radix passes).  With 16 points per thread N = 256 = 16 x 16 needs ONE
+// exchange (the 1-D kernel's fft_reg<16>), the twiddle loads per point halve too; the price is 2x the registers per
+// thread (1 CTA of 256 threads per SM, 16 row pairs in flight per SM as before).  Same math, same streaming
+// accumulation, same pruning as row_fast_kernel; covered by every 3-D test at N = 256 (tests/test_gpu_parity.py:
+// test_full_size_c4_navier_stokes_256_benchmarked_instantiation) and the 2-D fast-kind tests at N = 256.
 #pragma once
 #include "exb_kernels_1d_fast.cuh"
 #include "exb_kernels_nd_fast.cuh"

@@ -116,4 +116,34 @@ __global__ void derivative_kernel(const cpx<T>* __restrict__ uh, cpx<T>* __restr
   }
 }
 
+// Leray projection of a D-channel spectral field (exponax/nonlin_fun/_leray.py:114-136, the default order 2):
+//   div = sum_d (i kd_d) u_d,   p = -inv_lap * div  (inv_lap = 1 / sum_d (i kd_d)^2, := 0 at k = 0),   out_c = u_c + i kd_c p
+// one thread per mode, all D channels; `out` may alias `uh`.
+template <class T>
+__global__ void leray_kernel(const cpx<T>* uh, cpx<T>* out, int D, int N, int Nh, long long M, long long total,
+                             T two_pi_over_L) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long f = i / M, m = i - f * M;
+  T kd[3] = {(T)0, (T)0, (T)0};
+  kd[D - 1] = two_pi_over_L * (T)(int)(m % Nh);
+  long long rest = m / Nh;
+  for (int d = D - 2; d >= 0; --d) {
+    kd[d] = two_pi_over_L * (T)wavenumber_of((int)(rest % N), N);
+    rest /= N;
+  }
+  cpx<T> u[3];
+  cpx<T> s((T)0, (T)0);
+  T lap = (T)0;
+  for (int d = 0; d < D; ++d) {
+    u[d] = uh[((size_t)f * D + d) * M + m];
+    s = s + kd[d] * u[d];
+    lap -= kd[d] * kd[d];
+  }
+  const cpx<T> div = mul_i(s);
+  const T inv = lap != (T)0 ? (T)1 / lap : (T)0;
+  const cpx<T> p = (-inv) * div;
+  for (int d = 0; d < D; ++d) out[((size_t)f * D + d) * M + m] = u[d] + mul_i(kd[d] * p);
+}
+
 }  // namespace exb

@@ -263,6 +263,13 @@ int exb_metric_sums(void *stream, int32_t dtype, int64_t nfields, int64_t npoint
 int exb_derivative(exb_plan *plan, void *stream, int64_t nfields, const void *u_hat, void *out_hat,
                    int32_t order, double domain_extent);
 
+/* exponax.nonlin_fun.Leray.__call__ (exponax/nonlin_fun/_leray.py:114-136, order 2) on its own: the projection of a
+   D-channel spectral field onto its divergence-free part, u_hat / out_hat: (nfields, D, N.., N/2+1) of this plan's
+   grid (D = the plan's number of spatial dimensions); out_hat may alias u_hat.  Inside the projected-convection
+   nonlinearity the same arithmetic is fused into the epilogue of the forward transform. */
+int exb_leray(exb_plan *plan, void *stream, int64_t nfields, const void *u_hat, void *out_hat,
+              double domain_extent);
+
 /* Fourier-space aggregation behind exponax.metrics.fourier_* / H1_* (metrics/_fourier.py:15-140), applied to
    x_hat = exb_fft(x), x_hat: (nfields, N.., N/2+1) complex of this plan's grid.  Per field and derivative
    component d:  out[f * ncomp + d] = sum_modes band * (|x_hat| * |2 pi k_d / domain_extent|^order)^p / recon

@@ -17,8 +17,8 @@ agg = collections.OrderedDict()
 for d in byid.values():
     nm = d["name"].replace("exb::", "")
     nm = re.sub(r"NlS<\(int\)(\d), \(int\)-?\d, \(int\)\d, \(int\)\d>", r"S\1", nm)
-    nm = re.sub(r"\(int\)", "", nm)[:70]
-    if not ("fast" in nm or "pass" in nm or "k1d" in nm or "etdrk" in nm or "copy_b" in nm):
+    nm = re.sub(r"\(int\)", "", nm)[:86]
+    if not ("fast" in nm or "pass" in nm or "k1d" in nm or "etdrk" in nm or "copy_b" in nm or "col_" in nm or "forcing" in nm):
         continue
     key = (nm, round(d.get("dram__bytes_read.sum", 0) / 2e7), round(d.get("dram__bytes_write.sum", 0) / 2e7))
     a = agg.setdefault(key, [0, 0.0, 0.0, 0.0]); a[0] += 1; a[1] += d["us"]

@@ -64,3 +64,28 @@ def test_product_arm_fails_loudly_without_a_gpu():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "c1", "--steps", "1",
                           "--warmup", "1"], capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert out.returncode != 0          # no silent CPU fallback
+
+
+def test_cufft_comparator_restates_the_reference_step():
+    """bench.py's "library FFT on the same GPU" comparator (baseline/cufft_standin.py: torch.fft + unfused eager ops)
+    must compute the reference's ETDRK2 step -- checked here against the oracle with torch on the CPU."""
+    import torch
+    import exponax_b200 as ex
+    from baseline.cufft_standin import CufftEtdrk2
+    from oracle import exponax_np as ox
+
+    def rel(a, b):
+        return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+    rng = np.random.default_rng(0)
+    for name, D, N, C, kw in (("Burgers", 1, 64, 1, dict(diffusivity=0.1)), ("KolmogorovFlowVorticity", 2, 32, 1, {}),
+                              ("NavierStokesVelocity", 3, 16, 3, {})):
+        st = getattr(ex.stepper, name)(D, 2 * np.pi, N, 0.01, **kw)
+        ost = getattr(ox, name)(D, 2 * np.pi, N, 0.01, **kw)
+        u0 = (0.3 * rng.standard_normal((2, C) + (N,) * D)).astype(np.float32)
+        cf = CufftEtdrk2(st, device="cpu")
+        assert rel(cf.step(torch.as_tensor(u0)).numpy(), np.stack([ost(u) for u in u0])) < 2e-6
+        assert rel(cf.repeat(torch.as_tensor(u0), 2, substeps=2).numpy(), np.stack([ox.repeat(ost, 4)(u) for u in u0])) < 5e-6
+        trj = cf.rollout(torch.as_tensor(u0), 3).numpy()
+        assert trj.shape == (2, 3, C) + (N,) * D
+        assert rel(trj, np.stack([ox.rollout(ost, 3)(u) for u in u0])) < 5e-6

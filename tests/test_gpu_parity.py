@@ -1018,6 +1018,29 @@ def test_stepper_ensemble_per_trajectory_tables(name, D, N, C, order, params):
         ens(dev(u0[:S + 1]))
 
 
+@pytest.mark.parametrize("D,N", [(2, 32), (3, 16), (3, 24)])
+def test_standalone_leray_projection(D, N):
+    """exponax/nonlin_fun/_leray.py:114-136 on its own (exb_leray): vs the oracle, divergence-free, idempotent,
+    identity on solenoidal fields (the reference's tests/test_nonlinear_funs.py:415-517), batched."""
+    L = 2 * np.pi
+    rng = np.random.default_rng(D * 100 + N)
+    u = rng.standard_normal((3, D) + (N,) * D).astype(np.float32)
+    uh = ox.fft(u, num_spatial_dims=D)
+    dop = ox.build_derivative_operator(D, L, N)
+    ler = ex.nonlin_fun.Leray(D, N, derivative_operator=ex.spectral.build_derivative_operator(D, L, N))
+    oler = ox.Leray(D, N, derivative_operator=dop)
+    plan = ex.spectral._plain_plan(D, N, np.float32)
+    n0 = plan.launch_count()
+    got = host(ler(dev(uh)))
+    assert plan.launch_count() == n0 + 1                       # one native kernel
+    ref = np.stack([oler(x) for x in uh])
+    assert rel(got, ref) < 2e-6
+    div = np.sum(dop * got, axis=1)
+    assert np.abs(div).max() / np.abs(got).max() < 1e-5
+    assert rel(host(ler(dev(got))), got) < 2e-6                # idempotent
+    assert rel(host(ler(dev(uh[0]))), ref[0]) < 2e-6           # unbatched call
+
+
 def test_user_stepper_with_builtin_nonlinear_fun_runs_fused():
     """A user subclass of BaseStepper that only changes the linear operator (the reference's extension
     protocol, docs/examples/creating_your_own_solvers_1d.ipynb) still runs on the fused kernels."""
