@@ -23,7 +23,7 @@ int launch_fast_t(cudaStream_t st, const K1dParams<float>& p, int nscr, int max_
   const long long npairs_all = (p.batch + 1) / 2;
   const int pair_bytes_est = (nstate * 2 * (((NNh + 1) / 2) * 2) + (R + 1) * R) * 8;
   // shared memory per SM: 228 KB minus 2 x (coefficient/twiddle tables + 1 KB system reserve)
-  int max_pairs_sm = (228 * 1024 - 2 * (R * R * 8 + NNh * 40 + 256 + 1024)) / pair_bytes_est;
+  int max_pairs_sm = (228 * 1024 - 2 * (R * R * 8 + NNh * 52 + 256 + 1024)) / pair_bytes_est;
   max_pairs_sm -= max_pairs_sm % (2 * gpw);
   if (max_pairs_sm > 16 * gpw) max_pairs_sm = 16 * gpw;                 // register bound: 16 warps/SM
   if (max_pairs_sm < 2 * gpw) max_pairs_sm = 2 * gpw;
@@ -45,6 +45,8 @@ int launch_fast_t(cudaStream_t st, const K1dParams<float>& p, int nscr, int max_
   lay.off_exp = take(NNh * 8);
   lay.off_hexp = take(NNh * 8);
   for (int i = 0; i < 6; ++i) lay.off_c[i] = take(NNh * 4);
+  lay.off_mk = take(NNh * 8);
+  lay.off_h = take(NNh * 4);
   lay.nstate = nstate;
   (void)nscr;
   lay.nhp = (NNh + 1) / 2 * 2;

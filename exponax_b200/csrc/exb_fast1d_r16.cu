@@ -8,6 +8,7 @@ int exb_launch_fast1d_r16(cudaStream_t st, const K1dParams<float>& p, int nscr, 
 bool exb_fast1d_supported(int N, const NlParams<float>& P, int order) {
   if (N != 256 && N != 64) return false;
   if (P.D != 1 || P.C != 1) return false;
+  if (P.has_inj) return false;   // (no 1-D stepper injects; the generic kernel handles it)
   if (order == 0) return true;
   switch (P.kind) {
     case EXB_NL_CONVECTION:

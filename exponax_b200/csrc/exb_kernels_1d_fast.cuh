@@ -23,6 +23,8 @@ struct FastLayout {
   int off_exp;       // cpx[Nh]
   int off_hexp;      // cpx[Nh]
   int off_c[6];      // float[Nh] each
+  int off_h;         // float[Nh]: mask * post-factor / 2 of the nonlinear function (see unpack_scaled)
+  int off_mk;        // float2[Nh]: (keep / N, keep * kd / N) -- pre-dealiasing mask, derivative scale and 1/N of the inverse transform
   int off_pairs;     // start of per-pair storage
   int pair_bytes;    // bytes per pair
   int nstate;        // spectral state arrays per pair (1 + scratch)
@@ -113,7 +115,7 @@ __device__ __forceinline__ void fft_reg_body(cpx<float> (&v)[R], cpx<float>* xb,
 }
 
 #ifndef EXB_1D_CTA_SYNC
-#define EXB_1D_CTA_SYNC 1
+#define EXB_1D_CTA_SYNC 0
 #endif
 #ifndef EXB_1D_SPLIT_BAR
 #define EXB_1D_SPLIT_BAR 0
@@ -122,20 +124,40 @@ __device__ __forceinline__ void fft_reg_body(cpx<float> (&v)[R], cpx<float>* xb,
 #define EXB_1D_SKEW_NS 0
 #endif
 
-// The step body calls the transform from five places; inlined everywhere it is > 64 KB of code and the
-// warps stall on instruction fetch.  EXB_1D_FFT_CALL=1 makes the transform a real function: the line
-// travels by value (the ABI keeps the 2R floats in registers both ways, no stack traffic), the body
-// exists once per direction.
+// The step body calls the transform from five places.  Round 1 (scalar FP32, per-trajectory masks and selects in the
+// line builders) the inlined body was > 64 KB and the warps stalled on instruction fetch, so the transform was a real
+// function (EXB_1D_FFT_CALL=1: the line travels by value in registers) and a CTA barrier per stage kept the warps on
+// the same instruction-cache lines (EXB_1D_CTA_SYNC=1).  With packed FP32 and the lean line builders the inlined
+// step is small enough: measured on B200 (c2, profiles/r02v_c2_lean_1d.md) call + barrier 1.51e11, inlined + barrier
+// 1.62e11, inlined without the barrier 1.70e11 grid-point*steps/s -- the call's argument marshalling (about 60 MOVs
+// between two transforms) and the barrier's phase-locking of the warps cost more than the instruction fetch.
 #ifndef EXB_1D_FFT_CALL
-#define EXB_1D_FFT_CALL 1
+#define EXB_1D_FFT_CALL 0
 #endif
 #ifndef EXB_1D_FFT_UNIFY
 #define EXB_1D_FFT_UNIFY 1
 #endif
-template <int R> struct RegLine { cpx<float> v[R]; };
+// The line crosses the call as R 64-bit values (one register pair per complex point): passed as 2R scalar floats,
+// every pair is re-formed with two MOVs in front of its first packed instruction (32 of the body's 293 instructions).
+template <int R> struct RegLine { unsigned long long q[R]; };
+__device__ __forceinline__ unsigned long long pair_of(cpx<float> a) {
+  unsigned long long q;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(q) : "f"(a.x), "f"(a.y));
+  return q;
+}
+__device__ __forceinline__ cpx<float> cpx_of(unsigned long long q) {
+  cpx<float> a;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a.x), "=f"(a.y) : "l"(q));
+  return a;
+}
 template <int R, int DIR>
 __device__ __noinline__ RegLine<R> fft_reg_call(RegLine<R> a, cpx<float>* xb, int j, const cpx<float>* tw2) {
-  fft_reg_body<R, DIR>(a.v, xb, j, tw2);
+  cpx<float> v[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) v[r] = cpx_of(a.q[r]);
+  fft_reg_body<R, DIR>(v, xb, j, tw2);
+#pragma unroll
+  for (int r = 0; r < R; ++r) a.q[r] = pair_of(v[r]);
   return a;
 }
 template <int R, int DIR>
@@ -146,10 +168,13 @@ __device__ __forceinline__ void fft_reg(cpx<float> (&v)[R], cpx<float>* xb, int 
   constexpr bool CONJ = (EXB_1D_FFT_UNIFY != 0) && DIR > 0;
   RegLine<R> a;
 #pragma unroll
-  for (int r = 0; r < R; ++r) a.v[r] = CONJ ? cpx<float>(v[r].x, -v[r].y) : v[r];
+  for (int r = 0; r < R; ++r) a.q[r] = pair_of(CONJ ? cpx<float>(v[r].x, -v[r].y) : v[r]);
   a = fft_reg_call<R, CONJ ? -1 : DIR>(a, xb, j, tw2);
 #pragma unroll
-  for (int r = 0; r < R; ++r) v[r] = CONJ ? cpx<float>(a.v[r].x, -a.v[r].y) : a.v[r];
+  for (int r = 0; r < R; ++r) {
+    const cpx<float> t = cpx_of(a.q[r]);
+    v[r] = CONJ ? cpx<float>(t.x, -t.y) : t;
+  }
 #else
   fft_reg_body<R, DIR>(v, xb, j, tw2);
 #endif
@@ -169,6 +194,8 @@ template <int R, class S, int NINV, int NFWD> struct Fast1d {
   const cpx<float>* sE;
   const cpx<float>* sEh;
   const float* sc[6];
+  const float2* sMK;
+  const float* sH;
 
   __device__ Fast1d(const K1dParams<float>& p_, const FastLayout& l_) : p(p_), lay(l_) {}
 
@@ -210,6 +237,44 @@ template <int R, class S, int NINV, int NFWD> struct Fast1d {
     for (int r = R / 2 + 1; r < R; ++r) elem(r, N - (j + R * r), 2);
   }
 
+  // Inverse-transform inputs of the nonlinear function (C = 1, D = 1): every field is mask(k) * {1 | i kd} * u_hat, the
+  // same factor for both trajectories of the pair, so the packed line is factor * (u1 + i u2) -- one packed add and one
+  // packed multiply per point instead of per-trajectory masks, derivatives and selects.  The factor also carries the
+  // 1/N of the inverse transform (N is a power of two here: scaling before or after the FFT is bit-identical).
+  static __device__ __forceinline__ constexpr bool field_is_derivative(int f) {
+    return (S::kind == EXB_NL_CONVECTION && !(S::var & 1) && f >= 1) || S::kind == EXB_NL_GRADIENT_NORM ||
+           (S::kind == EXB_NL_GENERAL && f >= 1);
+  }
+  template <int NL>
+  __device__ __forceinline__ void build_lines_nl(const cpx<float>* src, cpx<float> (&z)[NL][R]) const {
+    // upper: n > N/2, the value is the conjugate of mode k = N - n.  edge: for j == 0 this slot is the DC / Nyquist
+    // mode, of which irfft keeps the real part only
+    auto elem = [&](int r, int k, bool upper, bool edge) {
+      const cpx<float> u1 = src[k], u2 = src[lay.nhp + k];
+      const float2 t = sMK[k];
+      const cpx<float> z0 = upper ? conj(u1) + mul_i(conj(u2)) : u1 + mul_i(u2);
+#pragma unroll
+      for (int f = 0; f < NL; ++f) {
+        cpx<float> v;
+        if (field_is_derivative(f)) {
+          const cpx<float> w = t.y * z0;                 // i kd w (lower), conj(i kd) w (upper)
+          v = upper ? mul_mi(w) : mul_i(w);
+          if (edge && j == 0) v = cpx<float>(-t.y * u1.y, -t.y * u2.y);   // Re(i kd u)
+        } else {
+          v = t.x * z0;
+          if (edge && j == 0) v = cpx<float>(t.x * u1.x, t.x * u2.x);
+        }
+        z[f][r] = v;
+      }
+    };
+    elem(0, j, false, true);
+#pragma unroll
+    for (int r = 1; r < R / 2; ++r) elem(r, j + R * r, false, false);
+    elem(R / 2, j == 0 ? N / 2 : N / 2 - j, true, true);
+#pragma unroll
+    for (int r = R / 2 + 1; r < R; ++r) elem(r, N - (j + R * r), true, false);
+  }
+
   // Two-for-one split of a forward-transformed line held in registers: for every owned mode slot
   // (k = j + R*slot, slot < R/2; slot R/2 = Nyquist, valid for j == 0 only) X1, X2.
   __device__ __forceinline__ void unpack_owned(const cpx<float> (&v)[R], cpx<float> (&X1)[NOWN],
@@ -231,13 +296,45 @@ template <int R, class S, int NINV, int NFWD> struct Fast1d {
     X2[R / 2] = cpx<float>(v[R / 2].y, 0.f);
   }
 
+  // Nonlinear functions whose post-processing is ONE real factor per mode, c(k) = mask(k) * {-scale | 1 | -scale / 2}:
+  // the factor rides on the 1/2 of the two-for-one split (h = c / 2 is exact, the product rounds exactly as
+  // c * (sum / 2) did), so N(u) of both trajectories is two packed multiplies per mode on top of the split.
+  static constexpr bool kRealPost =
+      NFWD == 1 && ((S::kind == EXB_NL_CONVECTION && S::var >= 0 && !(S::var & 1)) || S::kind == EXB_NL_POLYNOMIAL ||
+                    S::kind == EXB_NL_GRADIENT_NORM);
+  static __device__ __forceinline__ float post_factor_half(const NlParams<float>& P, int k) {
+    if (P.kmax >= 0 && k > P.kmax) return 0.f;
+    if (S::kind == EXB_NL_POLYNOMIAL) return 0.5f;
+    if (S::kind == EXB_NL_GRADIENT_NORM) return (P.zero_mode_fix && k == 0) ? 0.f : -0.25f * P.scale;
+    return -0.5f * P.scale;
+  }
+  __device__ __forceinline__ void unpack_scaled(const cpx<float> (&v)[R], cpx<float> (&n1)[NOWN],
+                                                cpx<float> (&n2)[NOWN]) const {
+    __syncwarp();
+#pragma unroll
+    for (int r = R / 2; r < R; ++r) xb[j + (R + 1) * r] = v[r];
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < R / 2; ++r) {
+      const int pidx = (j == 0) ? (R + 1) * (R - r) : (R - j) + (R + 1) * (R - 1 - r);
+      const float h = sH[j + R * r];
+      cpx<float> zk = v[r];
+      cpx<float> zp = (r == 0 && j == 0) ? zk : xb[pidx];
+      n1[r] = h * (zk + conj(zp));
+      n2[r] = mul_mi(h * (zk - conj(zp)));
+    }
+    const float c = 2.f * sH[N / 2];
+    n1[R / 2] = c * cpx<float>(v[R / 2].x, 0.f);  // Nyquist (meaningful for j == 0)
+    n2[R / 2] = c * cpx<float>(v[R / 2].y, 0.f);
+  }
+
   // N(src) -> per owned mode, both trajectories
   __device__ __forceinline__ void eval_nl(const cpx<float>* src, cpx<float> (&n1)[NOWN], cpx<float> (&n2)[NOWN]) const {
     const NlParams<float>& P = p.P;
     cpx<float> w[NFWD][R];
     {
       cpx<float> z[NINV][R];
-      build_lines<NINV, true>(src, z);
+      build_lines_nl<NINV>(src, z);
 #pragma unroll
       for (int f = 0; f < NINV; ++f) fft_reg<R, +1>(z[f], xb, j, tw2);
 #pragma unroll
@@ -245,11 +342,16 @@ template <int R, class S, int NINV, int NFWD> struct Fast1d {
         // the two lanes of a packed line value are the same grid point of the two trajectories
         f32x2 iv[NINV], ov[NFWD];
 #pragma unroll
-        for (int f = 0; f < NINV; ++f) iv[f] = lanes(P.inv_norm * z[f][r]);
+        for (int f = 0; f < NINV; ++f) iv[f] = lanes(z[f][r]);   // 1/N is in the line factors
         nl_pointwise<float, S, f32x2>(P, iv, ov);
 #pragma unroll
         for (int g = 0; g < NFWD; ++g) w[g][r] = as_cpx(ov[g]);
       }
+    }
+    if constexpr (kRealPost) {
+      fft_reg<R, -1>(w[0], xb, j, tw2);
+      unpack_scaled(w[0], n1, n2);
+      return;
     }
     cpx<float> W1[NFWD][NOWN], W2[NFWD][NOWN];
 #pragma unroll
@@ -301,49 +403,117 @@ template <int R, class S, int NINV, int NFWD> struct Fast1d {
       cpx<float>* S1 = state(lay.nstate > 2 ? 2 : 0);
       cpx<float>* S2 = state(lay.nstate > 3 ? 3 : 0);
       cpx<float>* S3 = state(lay.nstate > 4 ? 4 : 0);
+      // One (order, stage) dispatch per stage, not per mode; per owned mode the coefficients are read once for both
+      // trajectories and every load precedes the stores (the compiler cannot reorder them across the aliasing stores).
+      auto for_owned = [&](auto&& fn) {
 #pragma unroll
-      for (int sl = 0; sl < NOWN; ++sl) {
-        const int k = sl < R / 2 ? j + R * sl : N / 2;
-        if (sl < R / 2 || j == 0) {
-#pragma unroll
-          for (int tr = 0; tr < 2; ++tr) {
-            const int o = tr * nhp + k;
-            const cpx<float> n = tr == 0 ? n1[sl] : n2[sl];
-            if (order == 1) {
-              U[o] = sE[k] * U[o] + sc[0][k] * n;
-            } else if (order == 2) {
-              if (s == 0) {
-                U[o] = sE[k] * U[o] + sc[0][k] * n;
-                S0[o] = n;
-              } else {
-                U[o] = U[o] + sc[1][k] * (n - S0[o]);
-              }
-            } else if (order == 3) {
-              if (s == 0) {
-                S0[o] = sEh[k] * U[o] + sc[0][k] * n;
-                S1[o] = n;
-              } else if (s == 1) {
-                S0[o] = sE[k] * U[o] + sc[1][k] * (2.f * n - S1[o]);
-                S2[o] = n;
-              } else {
-                U[o] = sE[k] * U[o] + sc[2][k] * S1[o] + sc[3][k] * S2[o] + sc[4][k] * n;
-              }
-            } else {
-              if (s == 0) {
-                S0[o] = sEh[k] * U[o] + sc[0][k] * n;
-                S1[o] = n;
-              } else if (s == 1) {
-                S2[o] = sEh[k] * U[o] + sc[1][k] * n;
-                S3[o] = n;
-              } else if (s == 2) {
-                S2[o] = sEh[k] * S0[o] + sc[2][k] * (2.f * n - S1[o]);
-                S3[o] = S3[o] + n;
-              } else {
-                U[o] = sE[k] * U[o] + sc[3][k] * S1[o] + sc[4][k] * (2.f * S3[o]) + sc[5][k] * n;
-              }
-            }
-          }
+        for (int sl = 0; sl < NOWN; ++sl) {
+          const int k = sl < R / 2 ? j + R * sl : N / 2;
+          if (sl < R / 2 || j == 0) fn(k, nhp + k, n1[sl], n2[sl]);
         }
+      };
+      switch (order * 4 + s) {
+        case 4:   // ETDRK1 (_etdrk_1.py:78-82)
+          for_owned([&](int a, int b, cpx<float> na, cpx<float> nb) {
+            const cpx<float> e = sE[a];
+            const float c0 = sc[0][a];
+            const cpx<float> ua = U[a], ub = U[b];
+            U[a] = e * ua + c0 * na;
+            U[b] = e * ub + c0 * nb;
+          });
+          break;
+        case 8:   // ETDRK2 (_etdrk_2.py:91-102), a overwrites u
+          for_owned([&](int a, int b, cpx<float> na, cpx<float> nb) {
+            const cpx<float> e = sE[a];
+            const float c0 = sc[0][a];
+            const cpx<float> ua = U[a], ub = U[b];
+            U[a] = e * ua + c0 * na;
+            S0[a] = na;
+            U[b] = e * ub + c0 * nb;
+            S0[b] = nb;
+          });
+          break;
+        case 9:
+          for_owned([&](int a, int b, cpx<float> na, cpx<float> nb) {
+            const float c1 = sc[1][a];
+            const cpx<float> ua = U[a], ub = U[b], pa = S0[a], pb = S0[b];
+            U[a] = ua + c1 * (na - pa);
+            U[b] = ub + c1 * (nb - pb);
+          });
+          break;
+        case 12:  // ETDRK3 (_etdrk_3.py:191-212)
+          for_owned([&](int a, int b, cpx<float> na, cpx<float> nb) {
+            const cpx<float> eh = sEh[a];
+            const float c0 = sc[0][a];
+            const cpx<float> ua = U[a], ub = U[b];
+            S0[a] = eh * ua + c0 * na;
+            S1[a] = na;
+            S0[b] = eh * ub + c0 * nb;
+            S1[b] = nb;
+          });
+          break;
+        case 13:
+          for_owned([&](int a, int b, cpx<float> na, cpx<float> nb) {
+            const cpx<float> e = sE[a];
+            const float c1 = sc[1][a];
+            const cpx<float> ua = U[a], ub = U[b], pa = S1[a], pb = S1[b];
+            S0[a] = e * ua + c1 * (2.f * na - pa);
+            S2[a] = na;
+            S0[b] = e * ub + c1 * (2.f * nb - pb);
+            S2[b] = nb;
+          });
+          break;
+        case 14:
+          for_owned([&](int a, int b, cpx<float> na, cpx<float> nb) {
+            const cpx<float> e = sE[a];
+            const float c2 = sc[2][a], c3 = sc[3][a], c4 = sc[4][a];
+            const cpx<float> ua = U[a], ub = U[b], pa = S1[a], pb = S1[b], qa = S2[a], qb = S2[b];
+            U[a] = e * ua + c2 * pa + c3 * qa + c4 * na;
+            U[b] = e * ub + c2 * pb + c3 * qb + c4 * nb;
+          });
+          break;
+        case 16:  // ETDRK4 (_etdrk_4.py:198-224)
+          for_owned([&](int a, int b, cpx<float> na, cpx<float> nb) {
+            const cpx<float> eh = sEh[a];
+            const float c0 = sc[0][a];
+            const cpx<float> ua = U[a], ub = U[b];
+            S0[a] = eh * ua + c0 * na;
+            S1[a] = na;
+            S0[b] = eh * ub + c0 * nb;
+            S1[b] = nb;
+          });
+          break;
+        case 17:
+          for_owned([&](int a, int b, cpx<float> na, cpx<float> nb) {
+            const cpx<float> eh = sEh[a];
+            const float c1 = sc[1][a];
+            const cpx<float> ua = U[a], ub = U[b];
+            S2[a] = eh * ua + c1 * na;
+            S3[a] = na;
+            S2[b] = eh * ub + c1 * nb;
+            S3[b] = nb;
+          });
+          break;
+        case 18:
+          for_owned([&](int a, int b, cpx<float> na, cpx<float> nb) {
+            const cpx<float> eh = sEh[a];
+            const float c2 = sc[2][a];
+            const cpx<float> aa = S0[a], ab = S0[b], pa = S1[a], pb = S1[b], qa = S3[a], qb = S3[b];
+            S2[a] = eh * aa + c2 * (2.f * na - pa);
+            S3[a] = qa + na;
+            S2[b] = eh * ab + c2 * (2.f * nb - pb);
+            S3[b] = qb + nb;
+          });
+          break;
+        default:  // 19
+          for_owned([&](int a, int b, cpx<float> na, cpx<float> nb) {
+            const cpx<float> e = sE[a];
+            const float c3 = sc[3][a], c4 = sc[4][a], c5 = sc[5][a];
+            const cpx<float> ua = U[a], ub = U[b], pa = S1[a], pb = S1[b], qa = S3[a], qb = S3[b];
+            U[a] = e * ua + c3 * pa + c4 * (2.f * qa) + c5 * na;
+            U[b] = e * ub + c3 * pb + c4 * (2.f * qb) + c5 * nb;
+          });
+          break;
       }
       __syncwarp();
 #if EXB_1D_CTA_SYNC
@@ -392,6 +562,10 @@ __global__ void __launch_bounds__(256, 2) k1d_fast_kernel(const K1dParams<float>
       if (p.K.half_exp) eh[q] = p.K.half_exp[q];
       for (int i = 0; i < 6; ++i)
         if (p.K.c[i]) ((float*)(smem_raw + lay.off_c[i]))[q] = p.K.c[i][q];
+      const bool keep = !(p.P.kmax >= 0 && q > p.P.kmax);
+      ((float*)(smem_raw + lay.off_h))[q] = F1::post_factor_half(p.P, q);
+      ((float2*)(smem_raw + lay.off_mk))[q] =
+          keep ? make_float2(p.P.inv_norm, (p.P.dscale * (float)q) * p.P.inv_norm) : make_float2(0.f, 0.f);
     }
   }
   __syncthreads();
@@ -409,6 +583,8 @@ __global__ void __launch_bounds__(256, 2) k1d_fast_kernel(const K1dParams<float>
   F.sE = (const cpx<float>*)(smem_raw + lay.off_exp);
   F.sEh = (const cpx<float>*)(smem_raw + lay.off_hexp);
   for (int i = 0; i < 6; ++i) F.sc[i] = (const float*)(smem_raw + lay.off_c[i]);
+  F.sMK = (const float2*)(smem_raw + lay.off_mk);
+  F.sH = (const float*)(smem_raw + lay.off_h);
   const int order = p.K.order;
 
   const long long t1 = 2ll * group, t2 = t1 + 1;
@@ -505,11 +681,11 @@ __global__ void __launch_bounds__(256, 2) k1d_fast_kernel(const K1dParams<float>
       cpx<float> z[1][R];
       F.template build_lines<1, false>(U, z);
       fft_reg<R, +1>(z[0], F.xb, j, F.tw2);
-      if (store) store_phys(z[0], final_only ? 0 : s + (include_init ? 1 : 0), invN);
+#pragma unroll
+      for (int r = 0; r < R; ++r) z[0][r] = invN * z[0][r];    // one packed scaling serves the snapshot and the carry
+      if (store) store_phys(z[0], final_only ? 0 : s + (include_init ? 1 : 0), 1.0f);
       if (last) break;
       if (!spectral_carry) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) z[0][r] = invN * z[0][r];
         to_state(z[0]);
         continue;
       }
