@@ -68,8 +68,10 @@ template <int R, int DIR> __device__ __forceinline__ void dft_reg(cpx<float>* v)
   if (R == 8) dft8<float, DIR>(v);
 }
 
+// (round 2, lean kernel: the shared-memory pipe is the busiest unit (ncu 87 %), so deriving 11 of the 15 inter-pass
+// twiddles from w, w^2, w^4, w^8 pays: c2 1.73e11 -> 1.79e11; with the round-1 kernel, issue-bound, it was a loss)
 #ifndef EXB_1D_DERIVE_TW
-#define EXB_1D_DERIVE_TW 0
+#define EXB_1D_DERIVE_TW 1
 #endif
 // N = R*R point FFT of the line held as v[r] = x[j + R*r] by the R threads j of a group.
 // On return v[r] = X[j + R*r].  xb: per-pair exchange buffer ((R+1)*R complex, padded).
@@ -114,6 +116,9 @@ __device__ __forceinline__ void fft_reg_body(cpx<float> (&v)[R], cpx<float>* xb,
   }
 }
 
+#ifndef EXB_1D_SHFL_UNPACK
+#define EXB_1D_SHFL_UNPACK 1
+#endif
 #ifndef EXB_1D_CTA_SYNC
 #define EXB_1D_CTA_SYNC 0
 #endif
@@ -275,20 +280,43 @@ template <int R, class S, int NINV, int NFWD> struct Fast1d {
     for (int r = R / 2 + 1; r < R; ++r) elem(r, N - (j + R * r), true, false);
   }
 
-  // Two-for-one split of a forward-transformed line held in registers: for every owned mode slot
-  // (k = j + R*slot, slot < R/2; slot R/2 = Nyquist, valid for j == 0 only) X1, X2.
-  __device__ __forceinline__ void unpack_owned(const cpx<float> (&v)[R], cpx<float> (&X1)[NOWN],
-                                               cpx<float> (&X2)[NOWN]) const {
+  // Z[N - k] for the owned mode k = j + R*r: it lives in the registers of thread (R - j) % R of the same group, slot
+  // R - 1 - r (for j == 0 in the thread's own slot R - r), so the two-for-one split needs no shared-memory round trip:
+  // two shuffles per mode instead of a 64-bit store + load (the shared-memory pipe is this kernel's busiest unit; the
+  // staggered j == 0 row also cost a 2-way bank conflict on every partner load).
+  __device__ __forceinline__ cpx<float> partner_of(const cpx<float> (&v)[R], int r) const {
+#if EXB_1D_SHFL_UNPACK
+    const int src = ((threadIdx.x & 31) & ~(R - 1)) | ((R - j) & (R - 1));
+    const cpx<float> send = v[R - 1 - r];
+    cpx<float> t;
+    t.x = __shfl_sync(0xffffffffu, send.x, src);
+    t.y = __shfl_sync(0xffffffffu, send.y, src);
+    const cpx<float> own = r == 0 ? v[0] : v[R - r];
+    return j == 0 ? own : t;
+#else
+    const int pidx = (j == 0) ? (R + 1) * (R - r) : (R - j) + (R + 1) * (R - 1 - r);
+    return (r == 0 && j == 0) ? v[r] : xb[pidx];
+#endif
+  }
+  __device__ __forceinline__ void stage_partners(const cpx<float> (&v)[R]) const {
+#if !EXB_1D_SHFL_UNPACK
     __syncwarp();
 #pragma unroll
     for (int r = R / 2; r < R; ++r) xb[j + (R + 1) * r] = v[r];  // upper half: partners of the owned modes
     __syncwarp();
+#endif
+  }
+
+  // Two-for-one split of a forward-transformed line held in registers: for every owned mode slot
+  // (k = j + R*slot, slot < R/2; slot R/2 = Nyquist, valid for j == 0 only) X1, X2.
+  __device__ __forceinline__ void unpack_owned(const cpx<float> (&v)[R], cpx<float> (&X1)[NOWN],
+                                               cpx<float> (&X2)[NOWN]) const {
+    stage_partners(v);
 #pragma unroll
     for (int r = 0; r < R / 2; ++r) {
       // partner of k = j + R*r is n' = N - k = (R - j) + R*(R - 1 - r)  (j > 0);  N - R*r = R*(R - r) (j == 0)
-      const int pidx = (j == 0) ? (R + 1) * (R - r) : (R - j) + (R + 1) * (R - 1 - r);
       cpx<float> zk = v[r];
-      cpx<float> zp = (r == 0 && j == 0) ? zk : xb[pidx];
+      cpx<float> zp = partner_of(v, r);
       X1[r] = 0.5f * (zk + conj(zp));              // ( zk + conj(zp)) / 2
       X2[r] = mul_mi(0.5f * (zk - conj(zp)));      // (zk - conj(zp)) / (2 i)
     }
@@ -310,16 +338,12 @@ template <int R, class S, int NINV, int NFWD> struct Fast1d {
   }
   __device__ __forceinline__ void unpack_scaled(const cpx<float> (&v)[R], cpx<float> (&n1)[NOWN],
                                                 cpx<float> (&n2)[NOWN]) const {
-    __syncwarp();
-#pragma unroll
-    for (int r = R / 2; r < R; ++r) xb[j + (R + 1) * r] = v[r];
-    __syncwarp();
+    stage_partners(v);
 #pragma unroll
     for (int r = 0; r < R / 2; ++r) {
-      const int pidx = (j == 0) ? (R + 1) * (R - r) : (R - j) + (R + 1) * (R - 1 - r);
       const float h = sH[j + R * r];
       cpx<float> zk = v[r];
-      cpx<float> zp = (r == 0 && j == 0) ? zk : xb[pidx];
+      cpx<float> zp = partner_of(v, r);
       n1[r] = h * (zk + conj(zp));
       n2[r] = mul_mi(h * (zk - conj(zp)));
     }
