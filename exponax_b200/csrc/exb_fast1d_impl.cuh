@@ -21,7 +21,7 @@ int launch_fast_t(cudaStream_t st, const K1dParams<float>& p, int nscr, int max_
   static const int nstate_of_order[5] = {1, 1, 2, 4, 5};
   const int nstate = nstate_of_order[p.K.order];
   const long long npairs_all = (p.batch + 1) / 2;
-  const int pair_bytes_est = (nstate * 2 * (((NNh + 1) / 2) * 2) + (R + 1) * R) * 8;
+  const int pair_bytes_est = (nstate * (NN + 2) + (R + 1) * R) * 8;   // packed state arrays + exchange buffer
   // shared memory per SM: 228 KB minus 2 x (coefficient/twiddle tables + 1 KB system reserve)
   int max_pairs_sm = (228 * 1024 - 2 * (R * R * 8 + NNh * 52 + 256 + 1024)) / pair_bytes_est;
   max_pairs_sm -= max_pairs_sm % (2 * gpw);
@@ -50,7 +50,7 @@ int launch_fast_t(cudaStream_t st, const K1dParams<float>& p, int nscr, int max_
   lay.nstate = nstate;
   (void)nscr;
   lay.nhp = (NNh + 1) / 2 * 2;
-  lay.pair_bytes = (lay.nstate * 2 * lay.nhp + (R + 1) * R) * 8;
+  lay.pair_bytes = (lay.nstate * (NN + 2) + (R + 1) * R) * 8;
   lay.off_pairs = take(0);
   size_t smem = (size_t)off + (size_t)groups * lay.pair_bytes;
   if ((long long)smem > max_smem) {

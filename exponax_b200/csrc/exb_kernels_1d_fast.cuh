@@ -23,12 +23,12 @@ struct FastLayout {
   int off_exp;       // cpx[Nh]
   int off_hexp;      // cpx[Nh]
   int off_c[6];      // float[Nh] each
-  int off_h;         // float[Nh]: mask * post-factor / 2 of the nonlinear function (see unpack_scaled)
+  int off_h;         // float[Nh]: mask * real post-factor of the nonlinear function (Fast1d::post_factor)
   int off_mk;        // float2[Nh]: (keep / N, keep * kd / N) -- pre-dealiasing mask, derivative scale and 1/N of the inverse transform
   int off_pairs;     // start of per-pair storage
   int pair_bytes;    // bytes per pair
   int nstate;        // spectral state arrays per pair (1 + scratch)
-  int nhp;           // padded Nh (complex elements) per trajectory
+  int nhp;           // (unused since the packed-state layout: a state array is N + 2 complex values)
 };
 
 // ---- in-register DFTs; output position p holds X[xidx<R>(p)] --------------------------------
@@ -116,9 +116,6 @@ __device__ __forceinline__ void fft_reg_body(cpx<float> (&v)[R], cpx<float>* xb,
   }
 }
 
-#ifndef EXB_1D_SHFL_UNPACK
-#define EXB_1D_SHFL_UNPACK 1
-#endif
 #ifndef EXB_1D_CTA_SYNC
 #define EXB_1D_CTA_SYNC 0
 #endif
@@ -185,180 +182,111 @@ __device__ __forceinline__ void fft_reg(cpx<float> (&v)[R], cpx<float>* xb, int 
 #endif
 }
 
+// ---- the pair as ONE complex trajectory -------------------------------------------------------------------------
+// z = x1 + i x2 has the spectrum Z[n] = X1[n] + i X2[n], n = 0 .. N-1, and because X1, X2 are spectra of real signals,
+// Z[N - k] = conj(X1[k]) + i conj(X2[k]).  Every operation of the step is complex-linear per mode with coefficients
+// that satisfy c(-k) = conj(c(k)) (real PDE operators: polynomials in i k with real coefficients), so the ETDRK update,
+// the derivative / mask factors and the post-processing of the nonlinear function act on Z[n] directly:
+//     Z+[k]     = e(k) Z[k]           + c0(k) f(k) W[k]          (n = k <= N/2)
+//     Z+[N - k] = conj(e(k)) Z[N - k] + c0(k) conj(f(k)) W[N - k]
+// where W is the forward transform of the packed pointwise product.  The two-for-one split (and its inverse, the
+// packing of the inverse-transform inputs) never happens: the state IS the packed spectrum.  Thread j of the group
+// owns n = j + R*r, r = 0 .. R-1 -- exactly the elements its registers hold after the forward transform and must hold
+// before the inverse one, so every state access is thread-private (no partner exchange, no __syncwarp, no selects).
+// The one exception is the Nyquist mode: within a step U1[N/2], U2[N/2] are genuinely complex (odd-derivative
+// operators) while irfft keeps their real parts only, so they cannot share one complex slot; lane j == 0 carries them
+// as two extra values behind Z (slots N, N+1) and the packed slot N/2 is overridden wherever a line is built.
+// (The DC slot needs nothing: Im U[0] is exactly zero throughout -- e(0) and f(0) are real -- so Z[0] = (U1[0], U2[0]).)
 template <int R, class S, int NINV, int NFWD> struct Fast1d {
   static constexpr int N = R * R;
   static constexpr int Nh = N / 2 + 1;
-  static constexpr int NOWN = R / 2 + 1;  // modes owned per thread: k = j + R*r (r < R/2) [+ N/2 for j == 0]
+  static constexpr int ZS = N + 2;   // complex values per state array: Z[0 .. N-1], U1[N/2], U2[N/2]
 
   const K1dParams<float>& p;
   const FastLayout& lay;
   const cpx<float>* tw2;
-  cpx<float>* st;   // pair state base: [array][traj][nhp]
+  cpx<float>* st;   // pair state base: [array][ZS]
   cpx<float>* xb;   // exchange buffer
   int j;            // thread index within the pair group
   const cpx<float>* sE;
   const cpx<float>* sEh;
   const float* sc[6];
   const float2* sMK;
-  const float* sH;
+  const float* sC;
 
   __device__ Fast1d(const K1dParams<float>& p_, const FastLayout& l_) : p(p_), lay(l_) {}
 
-  __device__ __forceinline__ cpx<float>* state(int a) const { return st + (size_t)a * 2 * lay.nhp; }
-
-  // packed line element n from the half-complex fields F1, F2 of the two trajectories
-  template <int KINDN>  // 0: k = n < N/2 (direct), 1: DC or Nyquist, 2: upper (conjugate of mode N - n)
-  static __device__ __forceinline__ cpx<float> pack(cpx<float> F1, cpx<float> F2) {
-    if (KINDN == 1) return cpx<float>(F1.x, F2.x);                 // irfft drops these imaginary parts
-    if (KINDN == 0) return F1 + mul_i(F2);                         // F1 + i F2        (one packed add each:
-    return conj(F1) + mul_i(conj(F2));                             // conj(F1) + i conj(F2)   swaps / signs are operand modifiers)
+  __device__ __forceinline__ cpx<float>* state(int a) const { return st + (size_t)a * ZS; }
+  // slot r of this thread: line / state index n, index k = |wavenumber| into the coefficient tables, and whether the
+  // slot is a negative wavenumber (coefficients conjugated)
+  __device__ __forceinline__ int nidx(int r) const { return j + R * r; }
+  __device__ __forceinline__ int kidx(int r) const { return r < R / 2 ? j + R * r : N - (j + R * r); }
+  static __device__ __forceinline__ constexpr bool upper(int r) { return r >= R / 2; }
+  // c(+-k) * u for a table coefficient c(k)
+  static __device__ __forceinline__ cpx<float> cmul(cpx<float> c, cpx<float> u, bool up) {
+    return up ? mul_conj(u, c) : c * u;
   }
 
-  // Build the packed inverse lines from spectral state `src`.  NLF: apply the nonlinear
-  // function's prologue (mask, i*k, ...); otherwise the plain state (output transform).
-  template <int NL, bool NLF>
-  __device__ __forceinline__ void build_lines(const cpx<float>* src, cpx<float> (&z)[NL][R]) const {
-    const NlParams<float>& P = p.P;
-    auto elem = [&](int r, int k, int kindn) {
-      cpx<float> u1[EXB_MAXC], u2[EXB_MAXC];
-      u1[0] = src[k];
-      u2[0] = src[lay.nhp + k];
-      u1[1] = u1[2] = u2[1] = u2[2] = cpx<float>(0.f, 0.f);
-      ModeK<float> m = make_mode<float, S>(P, k, 0, 0);
+  // inverse-transform input of the plain state (snapshots)
+  __device__ __forceinline__ void build_plain(const cpx<float>* src, cpx<float> (&z)[R]) const {
 #pragma unroll
-      for (int f = 0; f < NL; ++f) {
-        cpx<float> F1 = NLF ? nl_inv_field<float, S>(P, f, u1, m) : u1[0];
-        cpx<float> F2 = NLF ? nl_inv_field<float, S>(P, f, u2, m) : u2[0];
-        z[f][r] = kindn == 0 ? pack<0>(F1, F2) : (kindn == 1 ? pack<1>(F1, F2) : pack<2>(F1, F2));
-      }
-    };
-    // r = 0: n = j (DC for j == 0)
-    elem(0, j, j == 0 ? 1 : 0);
-#pragma unroll
-    for (int r = 1; r < R / 2; ++r) elem(r, j + R * r, 0);
-    // r = R/2: n = N/2 + j: Nyquist for j == 0, otherwise the conjugate of mode N/2 - j
-    elem(R / 2, j == 0 ? N / 2 : N / 2 - j, j == 0 ? 1 : 2);
-#pragma unroll
-    for (int r = R / 2 + 1; r < R; ++r) elem(r, N - (j + R * r), 2);
+    for (int r = 0; r < R; ++r) z[r] = src[nidx(r)];
+    if (j == 0) z[R / 2] = cpx<float>(src[N].x, src[N + 1].x);       // irfft keeps Re U[N/2]
   }
 
-  // Inverse-transform inputs of the nonlinear function (C = 1, D = 1): every field is mask(k) * {1 | i kd} * u_hat, the
-  // same factor for both trajectories of the pair, so the packed line is factor * (u1 + i u2) -- one packed add and one
-  // packed multiply per point instead of per-trajectory masks, derivatives and selects.  The factor also carries the
-  // 1/N of the inverse transform (N is a power of two here: scaling before or after the FFT is bit-identical).
+  // Inverse-transform inputs of the nonlinear function (C = 1, D = 1): every field is mask(k) * {1 | i kd} * u_hat, so
+  // the packed line is factor(+-k) * Z[n]: one shared-memory read of the state, one of the factor pair (which also
+  // carries the 1/N of the inverse transform -- N is a power of two, scaling before or after is bit-identical) and one
+  // packed multiply per field and point.
   static __device__ __forceinline__ constexpr bool field_is_derivative(int f) {
     return (S::kind == EXB_NL_CONVECTION && !(S::var & 1) && f >= 1) || S::kind == EXB_NL_GRADIENT_NORM ||
            (S::kind == EXB_NL_GENERAL && f >= 1);
   }
   template <int NL>
-  __device__ __forceinline__ void build_lines_nl(const cpx<float>* src, cpx<float> (&z)[NL][R]) const {
-    // upper: n > N/2, the value is the conjugate of mode k = N - n.  edge: for j == 0 this slot is the DC / Nyquist
-    // mode, of which irfft keeps the real part only
-    auto elem = [&](int r, int k, bool upper, bool edge) {
-      const cpx<float> u1 = src[k], u2 = src[lay.nhp + k];
-      const float2 t = sMK[k];
-      const cpx<float> z0 = upper ? conj(u1) + mul_i(conj(u2)) : u1 + mul_i(u2);
+  __device__ __forceinline__ void build_nl(const cpx<float>* src, cpx<float> (&z)[NL][R]) const {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const cpx<float> z0 = src[nidx(r)];
+      const float2 t = sMK[kidx(r)];
 #pragma unroll
       for (int f = 0; f < NL; ++f) {
-        cpx<float> v;
         if (field_is_derivative(f)) {
-          const cpx<float> w = t.y * z0;                 // i kd w (lower), conj(i kd) w (upper)
-          v = upper ? mul_mi(w) : mul_i(w);
-          if (edge && j == 0) v = cpx<float>(-t.y * u1.y, -t.y * u2.y);   // Re(i kd u)
+          const cpx<float> w = t.y * z0;                   // (+-i kd) Z
+          z[f][r] = upper(r) ? mul_mi(w) : mul_i(w);
         } else {
-          v = t.x * z0;
-          if (edge && j == 0) v = cpx<float>(t.x * u1.x, t.x * u2.x);
+          z[f][r] = t.x * z0;
         }
-        z[f][r] = v;
       }
-    };
-    elem(0, j, false, true);
-#pragma unroll
-    for (int r = 1; r < R / 2; ++r) elem(r, j + R * r, false, false);
-    elem(R / 2, j == 0 ? N / 2 : N / 2 - j, true, true);
-#pragma unroll
-    for (int r = R / 2 + 1; r < R; ++r) elem(r, N - (j + R * r), true, false);
-  }
-
-  // Z[N - k] for the owned mode k = j + R*r: it lives in the registers of thread (R - j) % R of the same group, slot
-  // R - 1 - r (for j == 0 in the thread's own slot R - r), so the two-for-one split needs no shared-memory round trip:
-  // two shuffles per mode instead of a 64-bit store + load (the shared-memory pipe is this kernel's busiest unit; the
-  // staggered j == 0 row also cost a 2-way bank conflict on every partner load).
-  __device__ __forceinline__ cpx<float> partner_of(const cpx<float> (&v)[R], int r) const {
-#if EXB_1D_SHFL_UNPACK
-    const int src = ((threadIdx.x & 31) & ~(R - 1)) | ((R - j) & (R - 1));
-    const cpx<float> send = v[R - 1 - r];
-    cpx<float> t;
-    t.x = __shfl_sync(0xffffffffu, send.x, src);
-    t.y = __shfl_sync(0xffffffffu, send.y, src);
-    const cpx<float> own = r == 0 ? v[0] : v[R - r];
-    return j == 0 ? own : t;
-#else
-    const int pidx = (j == 0) ? (R + 1) * (R - r) : (R - j) + (R + 1) * (R - 1 - r);
-    return (r == 0 && j == 0) ? v[r] : xb[pidx];
-#endif
-  }
-  __device__ __forceinline__ void stage_partners(const cpx<float> (&v)[R]) const {
-#if !EXB_1D_SHFL_UNPACK
-    __syncwarp();
-#pragma unroll
-    for (int r = R / 2; r < R; ++r) xb[j + (R + 1) * r] = v[r];  // upper half: partners of the owned modes
-    __syncwarp();
-#endif
-  }
-
-  // Two-for-one split of a forward-transformed line held in registers: for every owned mode slot
-  // (k = j + R*slot, slot < R/2; slot R/2 = Nyquist, valid for j == 0 only) X1, X2.
-  __device__ __forceinline__ void unpack_owned(const cpx<float> (&v)[R], cpx<float> (&X1)[NOWN],
-                                               cpx<float> (&X2)[NOWN]) const {
-    stage_partners(v);
-#pragma unroll
-    for (int r = 0; r < R / 2; ++r) {
-      // partner of k = j + R*r is n' = N - k = (R - j) + R*(R - 1 - r)  (j > 0);  N - R*r = R*(R - r) (j == 0)
-      cpx<float> zk = v[r];
-      cpx<float> zp = partner_of(v, r);
-      X1[r] = 0.5f * (zk + conj(zp));              // ( zk + conj(zp)) / 2
-      X2[r] = mul_mi(0.5f * (zk - conj(zp)));      // (zk - conj(zp)) / (2 i)
     }
-    X1[R / 2] = cpx<float>(v[R / 2].x, 0.f);  // Nyquist (meaningful for j == 0)
-    X2[R / 2] = cpx<float>(v[R / 2].y, 0.f);
+    if (j == 0) {
+      const cpx<float> u1 = src[N], u2 = src[N + 1];
+      const float2 t = sMK[N / 2];
+#pragma unroll
+      for (int f = 0; f < NL; ++f)
+        z[f][R / 2] = field_is_derivative(f) ? cpx<float>(-t.y * u1.y, -t.y * u2.y)   // Re(i kd U)
+                                             : cpx<float>(t.x * u1.x, t.x * u2.x);
+    }
   }
 
-  // Nonlinear functions whose post-processing is ONE real factor per mode, c(k) = mask(k) * {-scale | 1 | -scale / 2}:
-  // the factor rides on the 1/2 of the two-for-one split (h = c / 2 is exact, the product rounds exactly as
-  // c * (sum / 2) did), so N(u) of both trajectories is two packed multiplies per mode on top of the split.
+  // Nonlinear functions whose post-processing is ONE real factor per mode, c(k) = mask(k) * {-scale | 1 | -scale / 2}
   static constexpr bool kRealPost =
       NFWD == 1 && ((S::kind == EXB_NL_CONVECTION && S::var >= 0 && !(S::var & 1)) || S::kind == EXB_NL_POLYNOMIAL ||
                     S::kind == EXB_NL_GRADIENT_NORM);
-  static __device__ __forceinline__ float post_factor_half(const NlParams<float>& P, int k) {
+  static __device__ __forceinline__ float post_factor(const NlParams<float>& P, int k) {
     if (P.kmax >= 0 && k > P.kmax) return 0.f;
-    if (S::kind == EXB_NL_POLYNOMIAL) return 0.5f;
-    if (S::kind == EXB_NL_GRADIENT_NORM) return (P.zero_mode_fix && k == 0) ? 0.f : -0.25f * P.scale;
-    return -0.5f * P.scale;
-  }
-  __device__ __forceinline__ void unpack_scaled(const cpx<float> (&v)[R], cpx<float> (&n1)[NOWN],
-                                                cpx<float> (&n2)[NOWN]) const {
-    stage_partners(v);
-#pragma unroll
-    for (int r = 0; r < R / 2; ++r) {
-      const float h = sH[j + R * r];
-      cpx<float> zk = v[r];
-      cpx<float> zp = partner_of(v, r);
-      n1[r] = h * (zk + conj(zp));
-      n2[r] = mul_mi(h * (zk - conj(zp)));
-    }
-    const float c = 2.f * sH[N / 2];
-    n1[R / 2] = c * cpx<float>(v[R / 2].x, 0.f);  // Nyquist (meaningful for j == 0)
-    n2[R / 2] = c * cpx<float>(v[R / 2].y, 0.f);
+    if (S::kind == EXB_NL_POLYNOMIAL) return 1.f;
+    if (S::kind == EXB_NL_GRADIENT_NORM) return (P.zero_mode_fix && k == 0) ? 0.f : -0.5f * P.scale;
+    return -P.scale;
   }
 
-  // N(src) -> per owned mode, both trajectories
-  __device__ __forceinline__ void eval_nl(const cpx<float>* src, cpx<float> (&n1)[NOWN], cpx<float> (&n2)[NOWN]) const {
+  // N(src): the packed nonlinear term at the thread's R slots, plus the two Nyquist values (meaningful for j == 0)
+  __device__ __forceinline__ void eval_nl(const cpx<float>* src, cpx<float> (&npk)[R], cpx<float>& ny1,
+                                          cpx<float>& ny2) const {
     const NlParams<float>& P = p.P;
     cpx<float> w[NFWD][R];
     {
       cpx<float> z[NINV][R];
-      build_lines_nl<NINV>(src, z);
+      build_nl<NINV>(src, z);
 #pragma unroll
       for (int f = 0; f < NINV; ++f) fft_reg<R, +1>(z[f], xb, j, tw2);
 #pragma unroll
@@ -372,194 +300,131 @@ template <int R, class S, int NINV, int NFWD> struct Fast1d {
         for (int g = 0; g < NFWD; ++g) w[g][r] = as_cpx(ov[g]);
       }
     }
+#pragma unroll
+    for (int g = 0; g < NFWD; ++g) fft_reg<R, -1>(w[g], xb, j, tw2);
     if constexpr (kRealPost) {
-      fft_reg<R, -1>(w[0], xb, j, tw2);
-      unpack_scaled(w[0], n1, n2);
-      return;
-    }
-    cpx<float> W1[NFWD][NOWN], W2[NFWD][NOWN];
 #pragma unroll
-    for (int g = 0; g < NFWD; ++g) {
-      fft_reg<R, -1>(w[g], xb, j, tw2);
-      unpack_owned(w[g], W1[g], W2[g]);
-    }
+      for (int r = 0; r < R; ++r) npk[r] = sC[kidx(r)] * w[0][r];
+      const float c = sC[N / 2];
+      ny1 = c * cpx<float>(w[0][R / 2].x, 0.f);
+      ny2 = c * cpx<float>(w[0][R / 2].y, 0.f);
+    } else {
+      // the post-processing (nl_from_fwd) is complex-linear in the transformed fields with coefficients that are
+      // polynomials in i kd: evaluated at -kd for the negative-wavenumber slots it acts on the packed values as is
+      auto post = [&](int k, bool up, bool nyq, int lane, int r, cpx<float>& out) {
+        ModeK<float> m;
+        m.kd[0] = (up ? -1.f : 1.f) * (P.dscale * (float)k);
+        m.kd[1] = m.kd[2] = 0.f;
+        m.keep = !(P.kmax >= 0 && k > P.kmax);
+        m.is_inj = false;
+        m.is_dc = k == 0;
+        cpx<float> wa[NFWD], a[EXB_MAXC];
 #pragma unroll
-    for (int sl = 0; sl < NOWN; ++sl) {
-      const int k = sl < R / 2 ? j + R * sl : N / 2;
-      ModeK<float> m = make_mode<float, S>(P, k, 0, 0);
-      cpx<float> wa[NFWD], wb[NFWD], a[EXB_MAXC], b[EXB_MAXC];
+        for (int g = 0; g < NFWD; ++g)
+          wa[g] = nyq ? cpx<float>(lane == 0 ? w[g][r].x : w[g][r].y, 0.f) : w[g][r];
+        nl_from_fwd<float, S>(P, wa, m, a);
+        out = a[0];
+      };
 #pragma unroll
-      for (int g = 0; g < NFWD; ++g) {
-        wa[g] = W1[g][sl];
-        wb[g] = W2[g][sl];
-      }
-      nl_from_fwd<float, S>(P, wa, m, a);
-      nl_from_fwd<float, S>(P, wb, m, b);
-      n1[sl] = a[0];
-      n2[sl] = b[0];
+      for (int r = 0; r < R; ++r) post(kidx(r), upper(r), false, 0, r, npk[r]);
+      post(N / 2, false, true, 0, R / 2, ny1);
+      post(N / 2, false, true, 1, R / 2, ny2);
     }
   }
 
   // one ETDRK step on the shared-memory state (array 0); stage formulas: exponax/etdrk/_etdrk_{0..4}.py
   __device__ __forceinline__ void etdrk_step(int order) {
-    cpx<float>* U = state(0);
-    const int nhp = lay.nhp;
+    cpx<float>* __restrict__ U = state(0);
     if (order == 0) {
 #pragma unroll
-      for (int sl = 0; sl < NOWN; ++sl) {
-        const int k = sl < R / 2 ? j + R * sl : N / 2;
-        if (sl < R / 2 || j == 0) {
-          cpx<float> e = sE[k];
-          U[k] = e * U[k];
-          U[nhp + k] = e * U[nhp + k];
-        }
+      for (int r = 0; r < R; ++r) U[nidx(r)] = cmul(sE[kidx(r)], U[nidx(r)], upper(r));
+      if (j == 0) {
+        const cpx<float> e = sE[N / 2];
+        U[N] = e * U[N];
+        U[N + 1] = e * U[N + 1];
       }
-      __syncwarp();
       return;
     }
     for (int s = 0; s < order; ++s) {
       // order 2 runs in place (a overwrites u): 2 state arrays instead of 3
       const int si = order == 2 ? -1 : etdrk_stage_input(order, s);
       const cpx<float>* src = si < 0 ? U : state(1 + si);
-      cpx<float> n1[NOWN], n2[NOWN];
-      eval_nl(src, n1, n2);
-      cpx<float>* S0 = state(lay.nstate > 1 ? 1 : 0);
-      cpx<float>* S1 = state(lay.nstate > 2 ? 2 : 0);
-      cpx<float>* S2 = state(lay.nstate > 3 ? 3 : 0);
-      cpx<float>* S3 = state(lay.nstate > 4 ? 4 : 0);
-      // One (order, stage) dispatch per stage, not per mode; per owned mode the coefficients are read once for both
-      // trajectories and every load precedes the stores (the compiler cannot reorder them across the aliasing stores).
-      auto for_owned = [&](auto&& fn) {
+      cpx<float> npk[R], ny1, ny2;
+      eval_nl(src, npk, ny1, ny2);
+      cpx<float>* __restrict__ S0 = state(lay.nstate > 1 ? 1 : 0);
+      cpx<float>* __restrict__ S1 = state(lay.nstate > 2 ? 2 : 0);
+      cpx<float>* __restrict__ S2 = state(lay.nstate > 3 ? 3 : 0);
+      cpx<float>* __restrict__ S3 = state(lay.nstate > 4 ? 4 : 0);
+      // One (order, stage) dispatch per stage; fn(i, k, up, n): state slot i, table index k, conjugated coefficients,
+      // packed nonlinear term.  The Nyquist pair of lane 0 goes through the same formulas (positive wavenumber).
+      auto for_slots = [&](auto&& fn) {
 #pragma unroll
-        for (int sl = 0; sl < NOWN; ++sl) {
-          const int k = sl < R / 2 ? j + R * sl : N / 2;
-          if (sl < R / 2 || j == 0) fn(k, nhp + k, n1[sl], n2[sl]);
+        for (int r = 0; r < R; ++r) fn(nidx(r), kidx(r), upper(r), npk[r]);
+        if (j == 0) {
+          fn(N, N / 2, false, ny1);
+          fn(N + 1, N / 2, false, ny2);
         }
       };
       switch (order * 4 + s) {
         case 4:   // ETDRK1 (_etdrk_1.py:78-82)
-          for_owned([&](int a, int b, cpx<float> na, cpx<float> nb) {
-            const cpx<float> e = sE[a];
-            const float c0 = sc[0][a];
-            const cpx<float> ua = U[a], ub = U[b];
-            U[a] = e * ua + c0 * na;
-            U[b] = e * ub + c0 * nb;
-          });
+          for_slots([&](int i, int k, bool up, cpx<float> n) { U[i] = cmul(sE[k], U[i], up) + sc[0][k] * n; });
           break;
         case 8:   // ETDRK2 (_etdrk_2.py:91-102), a overwrites u
-          for_owned([&](int a, int b, cpx<float> na, cpx<float> nb) {
-            const cpx<float> e = sE[a];
-            const float c0 = sc[0][a];
-            const cpx<float> ua = U[a], ub = U[b];
-            U[a] = e * ua + c0 * na;
-            S0[a] = na;
-            U[b] = e * ub + c0 * nb;
-            S0[b] = nb;
+          for_slots([&](int i, int k, bool up, cpx<float> n) {
+            U[i] = cmul(sE[k], U[i], up) + sc[0][k] * n;
+            S0[i] = n;
           });
           break;
         case 9:
-          for_owned([&](int a, int b, cpx<float> na, cpx<float> nb) {
-            const float c1 = sc[1][a];
-            const cpx<float> ua = U[a], ub = U[b], pa = S0[a], pb = S0[b];
-            U[a] = ua + c1 * (na - pa);
-            U[b] = ub + c1 * (nb - pb);
-          });
+          for_slots([&](int i, int k, bool up, cpx<float> n) { U[i] = U[i] + sc[1][k] * (n - S0[i]); });
           break;
         case 12:  // ETDRK3 (_etdrk_3.py:191-212)
-          for_owned([&](int a, int b, cpx<float> na, cpx<float> nb) {
-            const cpx<float> eh = sEh[a];
-            const float c0 = sc[0][a];
-            const cpx<float> ua = U[a], ub = U[b];
-            S0[a] = eh * ua + c0 * na;
-            S1[a] = na;
-            S0[b] = eh * ub + c0 * nb;
-            S1[b] = nb;
+          for_slots([&](int i, int k, bool up, cpx<float> n) {
+            S0[i] = cmul(sEh[k], U[i], up) + sc[0][k] * n;
+            S1[i] = n;
           });
           break;
         case 13:
-          for_owned([&](int a, int b, cpx<float> na, cpx<float> nb) {
-            const cpx<float> e = sE[a];
-            const float c1 = sc[1][a];
-            const cpx<float> ua = U[a], ub = U[b], pa = S1[a], pb = S1[b];
-            S0[a] = e * ua + c1 * (2.f * na - pa);
-            S2[a] = na;
-            S0[b] = e * ub + c1 * (2.f * nb - pb);
-            S2[b] = nb;
+          for_slots([&](int i, int k, bool up, cpx<float> n) {
+            S0[i] = cmul(sE[k], U[i], up) + sc[1][k] * (2.f * n - S1[i]);
+            S2[i] = n;
           });
           break;
         case 14:
-          for_owned([&](int a, int b, cpx<float> na, cpx<float> nb) {
-            const cpx<float> e = sE[a];
-            const float c2 = sc[2][a], c3 = sc[3][a], c4 = sc[4][a];
-            const cpx<float> ua = U[a], ub = U[b], pa = S1[a], pb = S1[b], qa = S2[a], qb = S2[b];
-            U[a] = e * ua + c2 * pa + c3 * qa + c4 * na;
-            U[b] = e * ub + c2 * pb + c3 * qb + c4 * nb;
+          for_slots([&](int i, int k, bool up, cpx<float> n) {
+            U[i] = cmul(sE[k], U[i], up) + sc[2][k] * S1[i] + sc[3][k] * S2[i] + sc[4][k] * n;
           });
           break;
         case 16:  // ETDRK4 (_etdrk_4.py:198-224)
-          for_owned([&](int a, int b, cpx<float> na, cpx<float> nb) {
-            const cpx<float> eh = sEh[a];
-            const float c0 = sc[0][a];
-            const cpx<float> ua = U[a], ub = U[b];
-            S0[a] = eh * ua + c0 * na;
-            S1[a] = na;
-            S0[b] = eh * ub + c0 * nb;
-            S1[b] = nb;
+          for_slots([&](int i, int k, bool up, cpx<float> n) {
+            S0[i] = cmul(sEh[k], U[i], up) + sc[0][k] * n;
+            S1[i] = n;
           });
           break;
         case 17:
-          for_owned([&](int a, int b, cpx<float> na, cpx<float> nb) {
-            const cpx<float> eh = sEh[a];
-            const float c1 = sc[1][a];
-            const cpx<float> ua = U[a], ub = U[b];
-            S2[a] = eh * ua + c1 * na;
-            S3[a] = na;
-            S2[b] = eh * ub + c1 * nb;
-            S3[b] = nb;
+          for_slots([&](int i, int k, bool up, cpx<float> n) {
+            S2[i] = cmul(sEh[k], U[i], up) + sc[1][k] * n;
+            S3[i] = n;
           });
           break;
         case 18:
-          for_owned([&](int a, int b, cpx<float> na, cpx<float> nb) {
-            const cpx<float> eh = sEh[a];
-            const float c2 = sc[2][a];
-            const cpx<float> aa = S0[a], ab = S0[b], pa = S1[a], pb = S1[b], qa = S3[a], qb = S3[b];
-            S2[a] = eh * aa + c2 * (2.f * na - pa);
-            S3[a] = qa + na;
-            S2[b] = eh * ab + c2 * (2.f * nb - pb);
-            S3[b] = qb + nb;
+          for_slots([&](int i, int k, bool up, cpx<float> n) {
+            const cpx<float> q = S3[i];
+            S2[i] = cmul(sEh[k], S0[i], up) + sc[2][k] * (2.f * n - S1[i]);
+            S3[i] = q + n;
           });
           break;
         default:  // 19
-          for_owned([&](int a, int b, cpx<float> na, cpx<float> nb) {
-            const cpx<float> e = sE[a];
-            const float c3 = sc[3][a], c4 = sc[4][a], c5 = sc[5][a];
-            const cpx<float> ua = U[a], ub = U[b], pa = S1[a], pb = S1[b], qa = S3[a], qb = S3[b];
-            U[a] = e * ua + c3 * pa + c4 * (2.f * qa) + c5 * na;
-            U[b] = e * ub + c3 * pb + c4 * (2.f * qb) + c5 * nb;
+          for_slots([&](int i, int k, bool up, cpx<float> n) {
+            U[i] = cmul(sE[k], U[i], up) + sc[3][k] * S1[i] + sc[4][k] * (2.f * S3[i]) + sc[5][k] * n;
           });
           break;
       }
-      __syncwarp();
 #if EXB_1D_CTA_SYNC
-      // No data is shared between warps: the barrier only keeps the warps of the CTA at the same place of
-      // the (fully unrolled, > 64 KB) step body, so that they share instruction-cache lines instead of
-      // each streaming the body from L2 on its own (ncu r01: `no_instruction` was the top stall reason).
-#if EXB_1D_SPLIT_BAR
-      // two half-CTA barriers (even / odd warps) instead of one: the halves drift apart, so that the FMA-pipe phases
-      // (butterflies) of one half overlap the shared-memory phases (exchanges, state updates) of the other
-      {
-        const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-        const int half = warp & 1, cnt = ((nw + 1 - half) >> 1) * 32;
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + half), "r"(cnt) : "memory");
-      }
-#else
+      // No data is shared between warps: the barrier only keeps the warps of the CTA at the same place of the step
+      // body so that they share instruction-cache lines (round 1: `no_instruction` was the top stall reason; with the
+      // lean body it costs more than it saves -- off by default).
       __syncthreads();
-#endif
-#if EXB_1D_SKEW_NS
-      // de-phase the odd warps by a fraction of a transform: the butterflies of one half then overlap the exchanges
-      // of the other instead of all warps saturating the FMA pipe and the shared-memory pipe in turns
-      if ((threadIdx.x >> 5) & 1) __nanosleep(EXB_1D_SKEW_NS);
-#endif
 #endif
     }
   }
@@ -571,7 +436,6 @@ __global__ void __launch_bounds__(256, 2) k1d_fast_kernel(const K1dParams<float>
   constexpr int N = R * R, Nh = N / 2 + 1;
   constexpr int GROUPS_PER_WARP = 32 / R;
   using F1 = Fast1d<R, S, NINV, NFWD>;
-  constexpr int NOWN = F1::NOWN;
   // ---- cooperative load of the tables ----
   {
     cpx<float>* tw2 = (cpx<float>*)(smem_raw + lay.off_tw2);
@@ -587,7 +451,7 @@ __global__ void __launch_bounds__(256, 2) k1d_fast_kernel(const K1dParams<float>
       for (int i = 0; i < 6; ++i)
         if (p.K.c[i]) ((float*)(smem_raw + lay.off_c[i]))[q] = p.K.c[i][q];
       const bool keep = !(p.P.kmax >= 0 && q > p.P.kmax);
-      ((float*)(smem_raw + lay.off_h))[q] = F1::post_factor_half(p.P, q);
+      ((float*)(smem_raw + lay.off_h))[q] = F1::post_factor(p.P, q);
       ((float2*)(smem_raw + lay.off_mk))[q] =
           keep ? make_float2(p.P.inv_norm, (p.P.dscale * (float)q) * p.P.inv_norm) : make_float2(0.f, 0.f);
     }
@@ -603,12 +467,12 @@ __global__ void __launch_bounds__(256, 2) k1d_fast_kernel(const K1dParams<float>
   F.tw2 = (const cpx<float>*)(smem_raw + lay.off_tw2);
   unsigned char* pb = smem_raw + lay.off_pairs + (size_t)local_group * lay.pair_bytes;
   F.st = (cpx<float>*)pb;
-  F.xb = (cpx<float>*)(pb + (size_t)lay.nstate * 2 * lay.nhp * sizeof(cpx<float>));
+  F.xb = (cpx<float>*)(pb + (size_t)lay.nstate * F1::ZS * sizeof(cpx<float>));
   F.sE = (const cpx<float>*)(smem_raw + lay.off_exp);
   F.sEh = (const cpx<float>*)(smem_raw + lay.off_hexp);
   for (int i = 0; i < 6; ++i) F.sc[i] = (const float*)(smem_raw + lay.off_c[i]);
   F.sMK = (const float2*)(smem_raw + lay.off_mk);
-  F.sH = (const float*)(smem_raw + lay.off_h);
+  F.sC = (const float*)(smem_raw + lay.off_h);
   const int order = p.K.order;
 
   const long long t1 = 2ll * group, t2 = t1 + 1;
@@ -637,34 +501,29 @@ __global__ void __launch_bounds__(256, 2) k1d_fast_kernel(const K1dParams<float>
   }
   o1 += j;
   o2 += j;
-  auto store_phys = [&](const cpx<float> (&v)[R], long long slot, float scale) {
+  auto store_phys = [&](const cpx<float> (&v)[R], long long slot) {
     float* a = o1 + (size_t)slot * slot_stride;
     float* b = o2 + (size_t)slot * slot_stride;
     if (act1) {
 #pragma unroll
-      for (int r = 0; r < R; ++r) a[R * r] = v[r].x * scale;
+      for (int r = 0; r < R; ++r) a[R * r] = v[r].x;
     }
     if (act2) {
 #pragma unroll
-      for (int r = 0; r < R; ++r) b[R * r] = v[r].y * scale;
+      for (int r = 0; r < R; ++r) b[R * r] = v[r].y;
     }
   };
 
   cpx<float>* U = F.state(0);
+  // physical pair line -> packed spectral state
   auto to_state = [&](cpx<float> (&line)[R]) {
     fft_reg<R, -1>(line, F.xb, j, F.tw2);
-    cpx<float> X1[NOWN], X2[NOWN];
-    F.unpack_owned(line, X1, X2);
 #pragma unroll
-    for (int sl = 0; sl < R / 2; ++sl) {
-      U[j + R * sl] = X1[sl];
-      U[lay.nhp + j + R * sl] = X2[sl];
+    for (int r = 0; r < R; ++r) U[j + R * r] = line[r];
+    if (j == 0) {   // X1[N/2], X2[N/2] are real
+      U[N] = cpx<float>(line[R / 2].x, 0.f);
+      U[N + 1] = cpx<float>(line[R / 2].y, 0.f);
     }
-    if (j == 0) {
-      U[N / 2] = X1[R / 2];
-      U[lay.nhp + N / 2] = X2[R / 2];
-    }
-    __syncwarp();
   };
 
   // ---- u0 -> spectral state ----
@@ -677,52 +536,52 @@ __global__ void __launch_bounds__(256, 2) k1d_fast_kernel(const K1dParams<float>
       float b = act2 ? in[(size_t)t2 * N + j + R * r] : 0.f;
       v[r] = cpx<float>(a, b);
     }
-    if (include_init && !final_only) store_phys(v, 0, 1.0f);
+    if (include_init && !final_only) store_phys(v, 0);
     to_state(v);
   }
 
   const float invN = p.P.inv_norm;
   for (long long s = 0; s < p.n_saved; ++s) {
-    if (p.forcing) {  // u_hat += dt * f_hat (ForcedStepper), owned modes of both trajectories
+    if (p.forcing) {  // u_hat += dt * f_hat (ForcedStepper): packed F1[k] + i F2[k], conjugated inputs for the negative half
       const cpx<float>* f1 = p.forcing + s * p.fstep + t1 * p.fbatch;
       const cpx<float>* f2 = p.forcing + s * p.fstep + t2 * p.fbatch;
+      const cpx<float> zero(0.f, 0.f);
 #pragma unroll
-      for (int sl = 0; sl < R / 2; ++sl) {
-        const int k = j + R * sl;
-        if (act1) U[k] = axpy(p.fscale, f1[k], U[k]);
-        if (act2) U[lay.nhp + k] = axpy(p.fscale, f2[k], U[lay.nhp + k]);
+      for (int r = 0; r < R; ++r) {
+        const int k = F.kidx(r);
+        const cpx<float> a = act1 ? f1[k] : zero, b = act2 ? f2[k] : zero;
+        cpx<float> add = F1::upper(r) ? conj(a) + mul_i(conj(b)) : a + mul_i(b);
+        if (r == 0 && j == 0) add = cpx<float>(a.x, b.x);   // DC: real parts only (irfft)
+        U[j + R * r] = axpy(p.fscale, add, U[j + R * r]);
       }
       if (j == 0) {
-        if (act1) U[N / 2] = axpy(p.fscale, f1[N / 2], U[N / 2]);
-        if (act2) U[lay.nhp + N / 2] = axpy(p.fscale, f2[N / 2], U[lay.nhp + N / 2]);
+        if (act1) U[N] = axpy(p.fscale, f1[N / 2], U[N]);
+        if (act2) U[N + 1] = axpy(p.fscale, f2[N / 2], U[N + 1]);
       }
-      __syncwarp();
     }
     for (int sub = 0; sub < p.substeps; ++sub) F.etdrk_step(order);
     const bool last = (s == p.n_saved - 1);
     const bool store = !final_only || last;
     if (store || !spectral_carry) {
-      cpx<float> z[1][R];
-      F.template build_lines<1, false>(U, z);
-      fft_reg<R, +1>(z[0], F.xb, j, F.tw2);
+      cpx<float> z[R];
+      F.build_plain(U, z);
+      fft_reg<R, +1>(z, F.xb, j, F.tw2);
 #pragma unroll
-      for (int r = 0; r < R; ++r) z[0][r] = invN * z[0][r];    // one packed scaling serves the snapshot and the carry
-      if (store) store_phys(z[0], final_only ? 0 : s + (include_init ? 1 : 0), 1.0f);
+      for (int r = 0; r < R; ++r) z[r] = invN * z[r];    // one packed scaling serves the snapshot and the carry
+      if (store) store_phys(z, final_only ? 0 : s + (include_init ? 1 : 0));
       if (last) break;
       if (!spectral_carry) {
-        to_state(z[0]);
+        to_state(z);
         continue;
       }
     }
     if (last) break;
-    // spectral carry: the reference's irfft -> rfft round trip == Hermitian projection
+    // spectral carry: the reference's irfft -> rfft round trip == Hermitian projection (the packed DC slot holds the
+    // real parts only by construction; the Nyquist values lose their imaginary parts)
     if (j == 0) {
-      U[0].y = 0.f;
-      U[N / 2].y = 0.f;
-      U[lay.nhp].y = 0.f;
-      U[lay.nhp + N / 2].y = 0.f;
+      U[N].y = 0.f;
+      U[N + 1].y = 0.f;
     }
-    __syncwarp();
   }
 }
 
