@@ -182,6 +182,15 @@ __device__ __forceinline__ void fft_reg(cpx<float> (&v)[R], cpx<float>* xb, int 
 #endif
 }
 
+#ifndef EXB_1D_UPD_BATCH
+#define EXB_1D_UPD_BATCH 8
+#endif
+// what one slot of an ETDRK stage update reads: coefficients and up to three state / stage values (unused members vanish)
+struct SlotLd {
+  cpx<float> e, u, p, q;
+  float f0, f1, f2;
+};
+
 // ---- the pair as ONE complex trajectory -------------------------------------------------------------------------
 // z = x1 + i x2 has the spectrum Z[n] = X1[n] + i X2[n], n = 0 .. N-1, and because X1, X2 are spectra of real signals,
 // Z[N - k] = conj(X1[k]) + i conj(X2[k]).  Every operation of the step is complex-linear per mode with coefficients
@@ -336,8 +345,14 @@ template <int R, class S, int NINV, int NFWD> struct Fast1d {
   __device__ __forceinline__ void etdrk_step(int order) {
     cpx<float>* __restrict__ U = state(0);
     if (order == 0) {
+      cpx<float> u[R], e[R];
 #pragma unroll
-      for (int r = 0; r < R; ++r) U[nidx(r)] = cmul(sE[kidx(r)], U[nidx(r)], upper(r));
+      for (int r = 0; r < R; ++r) {
+        u[r] = U[nidx(r)];
+        e[r] = sE[kidx(r)];
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) U[nidx(r)] = cmul(e[r], u[r], upper(r));
       if (j == 0) {
         const cpx<float> e = sE[N / 2];
         U[N] = e * U[N];
@@ -355,69 +370,91 @@ template <int R, class S, int NINV, int NFWD> struct Fast1d {
       cpx<float>* __restrict__ S1 = state(lay.nstate > 2 ? 2 : 0);
       cpx<float>* __restrict__ S2 = state(lay.nstate > 3 ? 3 : 0);
       cpx<float>* __restrict__ S3 = state(lay.nstate > 4 ? 4 : 0);
-      // One (order, stage) dispatch per stage; fn(i, k, up, n): state slot i, table index k, conjugated coefficients,
-      // packed nonlinear term.  The Nyquist pair of lane 0 goes through the same formulas (positive wavenumber).
-      auto for_slots = [&](auto&& fn) {
+      // One (order, stage) dispatch per stage.  Each case is a load function ld(i, k) -> SlotLd (state slot i, table
+      // index k) and an apply function ap(i, up, L, n) (up: conjugated coefficients, n: packed nonlinear term).  The
+      // loads of EXB_1D_UPD_BATCH slots are issued ahead of their arithmetic and stores: the compiler cannot hoist a
+      // shared-memory load over the (possibly aliasing) store of the previous slot by itself, and one slot at a time
+      // exposes the full load latency 16 times per stage.  The Nyquist pair of lane 0 uses the same formulas.
+      auto slots = [&](auto&& ld, auto&& ap) {
+        constexpr int B = EXB_1D_UPD_BATCH;
 #pragma unroll
-        for (int r = 0; r < R; ++r) fn(nidx(r), kidx(r), upper(r), npk[r]);
+        for (int r0 = 0; r0 < R; r0 += B) {
+          SlotLd L[B];
+#pragma unroll
+          for (int q = 0; q < B; ++q) L[q] = ld(nidx(r0 + q), kidx(r0 + q));
+#pragma unroll
+          for (int q = 0; q < B; ++q) ap(nidx(r0 + q), upper(r0 + q), L[q], npk[r0 + q]);
+        }
         if (j == 0) {
-          fn(N, N / 2, false, ny1);
-          fn(N + 1, N / 2, false, ny2);
+          const SlotLd a = ld(N, N / 2), b = ld(N + 1, N / 2);
+          ap(N, false, a, ny1);
+          ap(N + 1, false, b, ny2);
         }
       };
       switch (order * 4 + s) {
         case 4:   // ETDRK1 (_etdrk_1.py:78-82)
-          for_slots([&](int i, int k, bool up, cpx<float> n) { U[i] = cmul(sE[k], U[i], up) + sc[0][k] * n; });
+          slots([&](int i, int k) { SlotLd L; L.e = sE[k]; L.f0 = sc[0][k]; L.u = U[i]; return L; },
+                [&](int i, bool up, const SlotLd& L, cpx<float> n) { U[i] = cmul(L.e, L.u, up) + L.f0 * n; });
           break;
         case 8:   // ETDRK2 (_etdrk_2.py:91-102), a overwrites u
-          for_slots([&](int i, int k, bool up, cpx<float> n) {
-            U[i] = cmul(sE[k], U[i], up) + sc[0][k] * n;
-            S0[i] = n;
-          });
+          slots([&](int i, int k) { SlotLd L; L.e = sE[k]; L.f0 = sc[0][k]; L.u = U[i]; return L; },
+                [&](int i, bool up, const SlotLd& L, cpx<float> n) {
+                  U[i] = cmul(L.e, L.u, up) + L.f0 * n;
+                  S0[i] = n;
+                });
           break;
         case 9:
-          for_slots([&](int i, int k, bool up, cpx<float> n) { U[i] = U[i] + sc[1][k] * (n - S0[i]); });
+          slots([&](int i, int k) { SlotLd L; L.f0 = sc[1][k]; L.u = U[i]; L.p = S0[i]; return L; },
+                [&](int i, bool up, const SlotLd& L, cpx<float> n) { U[i] = L.u + L.f0 * (n - L.p); });
           break;
         case 12:  // ETDRK3 (_etdrk_3.py:191-212)
-          for_slots([&](int i, int k, bool up, cpx<float> n) {
-            S0[i] = cmul(sEh[k], U[i], up) + sc[0][k] * n;
-            S1[i] = n;
-          });
+        case 16:  // ETDRK4 (_etdrk_4.py:198-224), first stage: the same formula
+          slots([&](int i, int k) { SlotLd L; L.e = sEh[k]; L.f0 = sc[0][k]; L.u = U[i]; return L; },
+                [&](int i, bool up, const SlotLd& L, cpx<float> n) {
+                  S0[i] = cmul(L.e, L.u, up) + L.f0 * n;
+                  S1[i] = n;
+                });
           break;
         case 13:
-          for_slots([&](int i, int k, bool up, cpx<float> n) {
-            S0[i] = cmul(sE[k], U[i], up) + sc[1][k] * (2.f * n - S1[i]);
-            S2[i] = n;
-          });
+          slots([&](int i, int k) { SlotLd L; L.e = sE[k]; L.f0 = sc[1][k]; L.u = U[i]; L.p = S1[i]; return L; },
+                [&](int i, bool up, const SlotLd& L, cpx<float> n) {
+                  S0[i] = cmul(L.e, L.u, up) + L.f0 * (2.f * n - L.p);
+                  S2[i] = n;
+                });
           break;
         case 14:
-          for_slots([&](int i, int k, bool up, cpx<float> n) {
-            U[i] = cmul(sE[k], U[i], up) + sc[2][k] * S1[i] + sc[3][k] * S2[i] + sc[4][k] * n;
-          });
-          break;
-        case 16:  // ETDRK4 (_etdrk_4.py:198-224)
-          for_slots([&](int i, int k, bool up, cpx<float> n) {
-            S0[i] = cmul(sEh[k], U[i], up) + sc[0][k] * n;
-            S1[i] = n;
-          });
+          slots([&](int i, int k) {
+                  SlotLd L; L.e = sE[k]; L.f0 = sc[2][k]; L.f1 = sc[3][k]; L.f2 = sc[4][k];
+                  L.u = U[i]; L.p = S1[i]; L.q = S2[i]; return L;
+                },
+                [&](int i, bool up, const SlotLd& L, cpx<float> n) {
+                  U[i] = cmul(L.e, L.u, up) + L.f0 * L.p + L.f1 * L.q + L.f2 * n;
+                });
           break;
         case 17:
-          for_slots([&](int i, int k, bool up, cpx<float> n) {
-            S2[i] = cmul(sEh[k], U[i], up) + sc[1][k] * n;
-            S3[i] = n;
-          });
+          slots([&](int i, int k) { SlotLd L; L.e = sEh[k]; L.f0 = sc[1][k]; L.u = U[i]; return L; },
+                [&](int i, bool up, const SlotLd& L, cpx<float> n) {
+                  S2[i] = cmul(L.e, L.u, up) + L.f0 * n;
+                  S3[i] = n;
+                });
           break;
         case 18:
-          for_slots([&](int i, int k, bool up, cpx<float> n) {
-            const cpx<float> q = S3[i];
-            S2[i] = cmul(sEh[k], S0[i], up) + sc[2][k] * (2.f * n - S1[i]);
-            S3[i] = q + n;
-          });
+          slots([&](int i, int k) {
+                  SlotLd L; L.e = sEh[k]; L.f0 = sc[2][k]; L.u = S0[i]; L.p = S1[i]; L.q = S3[i]; return L;
+                },
+                [&](int i, bool up, const SlotLd& L, cpx<float> n) {
+                  S2[i] = cmul(L.e, L.u, up) + L.f0 * (2.f * n - L.p);
+                  S3[i] = L.q + n;
+                });
           break;
         default:  // 19
-          for_slots([&](int i, int k, bool up, cpx<float> n) {
-            U[i] = cmul(sE[k], U[i], up) + sc[3][k] * S1[i] + sc[4][k] * (2.f * S3[i]) + sc[5][k] * n;
-          });
+          slots([&](int i, int k) {
+                  SlotLd L; L.e = sE[k]; L.f0 = sc[3][k]; L.f1 = sc[4][k]; L.f2 = sc[5][k];
+                  L.u = U[i]; L.p = S1[i]; L.q = S3[i]; return L;
+                },
+                [&](int i, bool up, const SlotLd& L, cpx<float> n) {
+                  U[i] = cmul(L.e, L.u, up) + L.f0 * L.p + L.f1 * (2.f * L.q) + L.f2 * n;
+                });
           break;
       }
 #if EXB_1D_CTA_SYNC

@@ -1,5 +1,5 @@
 #!/bin/bash
-# c2 A/B: split-state kernel (previous commit) vs packed complex-pair state; then the GPU parity suite
+# c2 A/B: previous library vs working tree; then the GPU parity suite
 mkdir -p gpurun_out
 for v in prev default; do
   lib=build/libexb_$v.so; [ $v = default ] && lib=exponax_b200/libexb.so
