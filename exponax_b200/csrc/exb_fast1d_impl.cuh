@@ -23,7 +23,7 @@ int launch_fast_t(cudaStream_t st, const K1dParams<float>& p, int nscr, int max_
   const long long npairs_all = (p.batch + 1) / 2;
   const int pair_bytes_est = (nstate * (NN + 2) + (R + 1) * R) * 8;   // packed state arrays + exchange buffer
   // shared memory per SM: 228 KB minus 2 x (coefficient/twiddle tables + 1 KB system reserve)
-  int max_pairs_sm = (228 * 1024 - 2 * (R * R * 8 + NNh * 52 + 256 + 1024)) / pair_bytes_est;
+  int max_pairs_sm = (228 * 1024 - 2 * (R * R * 8 + NNh * 48 + 256 + 1024)) / pair_bytes_est;
   max_pairs_sm -= max_pairs_sm % (2 * gpw);
   if (max_pairs_sm > 16 * gpw) max_pairs_sm = 16 * gpw;                 // register bound: 16 warps/SM
   if (max_pairs_sm < 2 * gpw) max_pairs_sm = 2 * gpw;
@@ -46,7 +46,6 @@ int launch_fast_t(cudaStream_t st, const K1dParams<float>& p, int nscr, int max_
   lay.off_hexp = take(NNh * 8);
   for (int i = 0; i < 6; ++i) lay.off_c[i] = take(NNh * 4);
   lay.off_mk = take(NNh * 8);
-  lay.off_h = take(NNh * 4);
   lay.nstate = nstate;
   (void)nscr;
   lay.nhp = (NNh + 1) / 2 * 2;
@@ -57,16 +56,23 @@ int launch_fast_t(cudaStream_t st, const K1dParams<float>& p, int nscr, int max_
     *err = "fast 1-D kernel: not enough shared memory";
     return EXB_EUNSUPPORTED;
   }
-  {  // per device attribute: set on every launch (a process may drive several devices)
-    cudaError_t e = cudaFuncSetAttribute(k1d_fast_kernel<R, S, NI, NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  long long npairs = (p.batch + 1) / 2;
+  long long grid = (npairs + groups - 1) / groups;
+  // ETDRK2 (the reference's default order) has its own instance: no order dispatch, state slots handed over in registers
+  auto launch = [&](auto kernel) -> cudaError_t {
+    // per device attribute: set on every launch (a process may drive several devices)
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    if (e != cudaSuccess) return e;
+    kernel<<<(unsigned)grid, warps * 32, smem, st>>>(p, lay);
+    return cudaSuccess;
+  };
+  {
+    cudaError_t e = p.K.order == 2 ? launch(k1d_fast_kernel<R, S, NI, NF, 2>) : launch(k1d_fast_kernel<R, S, NI, NF, 0>);
     if (e != cudaSuccess) {
       *err = cudaGetErrorString(e);
       return EXB_ECUDA;
     }
   }
-  long long npairs = (p.batch + 1) / 2;
-  long long grid = (npairs + groups - 1) / groups;
-  k1d_fast_kernel<R, S, NI, NF><<<(unsigned)grid, warps * 32, smem, st>>>(p, lay);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     *err = cudaGetErrorString(e);

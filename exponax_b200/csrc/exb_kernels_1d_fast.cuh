@@ -23,7 +23,6 @@ struct FastLayout {
   int off_exp;       // cpx[Nh]
   int off_hexp;      // cpx[Nh]
   int off_c[6];      // float[Nh] each
-  int off_h;         // float[Nh]: mask * real post-factor of the nonlinear function (Fast1d::post_factor)
   int off_mk;        // float2[Nh]: (keep / N, keep * kd / N) -- pre-dealiasing mask, derivative scale and 1/N of the inverse transform
   int off_pairs;     // start of per-pair storage
   int pair_bytes;    // bytes per pair
@@ -182,6 +181,64 @@ __device__ __forceinline__ void fft_reg(cpx<float> (&v)[R], cpx<float>* xb, int 
 #endif
 }
 
+// NL independent lines through one transform, phase by phase: all first passes, then the exchanges (one buffer, one
+// line after the other), then all second passes.  The lines share the inter-pass twiddles (loaded / derived once), and
+// the scheduler may overlap the exchange latency of one line with the butterflies of the other -- called line by line,
+// the __syncwarp()s around each exchange keep the transforms strictly one after the other.
+#ifndef EXB_1D_FFT_LINES
+#define EXB_1D_FFT_LINES 1
+#endif
+template <int R, int DIR, int NL>
+__device__ __forceinline__ void fft_reg_lines(cpx<float> (&v)[NL][R], cpx<float>* xb, int j, const cpx<float>* tw2) {
+#if EXB_1D_FFT_LINES && !EXB_1D_FFT_CALL
+#pragma unroll
+  for (int f = 0; f < NL; ++f) dft_reg<R, DIR>(v[f]);
+  cpx<float> w[R];
+#if EXB_1D_DERIVE_TW
+#pragma unroll
+  for (int b = 1; b < R; b <<= 1) w[b] = twd<float, DIR>(tw2[b * R + j]);
+#pragma unroll
+  for (int r = 3; r < R; ++r)
+    if (r & (r - 1)) w[r] = w[r & (r - 1)] * w[r & -r];
+#else
+#pragma unroll
+  for (int r = 1; r < R; ++r) w[r] = twd<float, DIR>(tw2[r * R + j]);
+#endif
+#pragma unroll
+  for (int f = 0; f < NL; ++f) {
+    __syncwarp();
+#pragma unroll
+    for (int p = 0; p < R; ++p) xb[(R + 1) * j + xidx<R>(p)] = v[f][p];
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      cpx<float> t = xb[j + (R + 1) * r];
+      v[f][r] = r > 0 ? t * w[r] : t;
+    }
+  }
+#pragma unroll
+  for (int f = 0; f < NL; ++f) {
+    dft_reg<R, DIR>(v[f]);
+    if (R == 16) {
+      cpx<float> o[R];
+#pragma unroll
+      for (int p = 0; p < R; ++p) o[xidx<R>(p)] = v[f][p];
+#pragma unroll
+      for (int p = 0; p < R; ++p) v[f][p] = o[p];
+    }
+  }
+#else
+#pragma unroll
+  for (int f = 0; f < NL; ++f) fft_reg<R, DIR>(v[f], xb, j, tw2);
+#endif
+}
+
+// ETDRK2 instance: the two stages as a 2-iteration loop around ONE copy of the nonlinear evaluation (three transforms)
+// instead of straight-line code with two copies: 3048 instead of 3944 instructions, and c2 2.06e11 -> 2.32e11 -- the step
+// body has to stay inside the instruction cache (profiles/r02v_c2_lean_1d.md)
+#ifndef EXB_1D_O2_LOOP
+#define EXB_1D_O2_LOOP 1
+#endif
 #ifndef EXB_1D_UPD_BATCH
 #define EXB_1D_UPD_BATCH 8
 #endif
@@ -221,7 +278,6 @@ template <int R, class S, int NINV, int NFWD> struct Fast1d {
   const cpx<float>* sEh;
   const float* sc[6];
   const float2* sMK;
-  const float* sC;
 
   __device__ Fast1d(const K1dParams<float>& p_, const FastLayout& l_) : p(p_), lay(l_) {}
 
@@ -251,11 +307,12 @@ template <int R, class S, int NINV, int NFWD> struct Fast1d {
     return (S::kind == EXB_NL_CONVECTION && !(S::var & 1) && f >= 1) || S::kind == EXB_NL_GRADIENT_NORM ||
            (S::kind == EXB_NL_GENERAL && f >= 1);
   }
-  template <int NL>
-  __device__ __forceinline__ void build_nl(const cpx<float>* src, cpx<float> (&z)[NL][R]) const {
+  // zr (REGS): the thread's slots of `src` are already in registers (the previous update / transform left them there)
+  template <int NL, bool REGS = false>
+  __device__ __forceinline__ void build_nl(const cpx<float>* src, cpx<float> (&z)[NL][R], const cpx<float>* zr = nullptr) const {
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const cpx<float> z0 = src[nidx(r)];
+      const cpx<float> z0 = REGS ? zr[r] : src[nidx(r)];
       const float2 t = sMK[kidx(r)];
 #pragma unroll
       for (int f = 0; f < NL; ++f) {
@@ -289,15 +346,15 @@ template <int R, class S, int NINV, int NFWD> struct Fast1d {
   }
 
   // N(src): the packed nonlinear term at the thread's R slots, plus the two Nyquist values (meaningful for j == 0)
+  template <bool REGS = false>
   __device__ __forceinline__ void eval_nl(const cpx<float>* src, cpx<float> (&npk)[R], cpx<float>& ny1,
-                                          cpx<float>& ny2) const {
+                                          cpx<float>& ny2, const cpx<float>* zr = nullptr) const {
     const NlParams<float>& P = p.P;
     cpx<float> w[NFWD][R];
     {
       cpx<float> z[NINV][R];
-      build_nl<NINV>(src, z);
-#pragma unroll
-      for (int f = 0; f < NINV; ++f) fft_reg<R, +1>(z[f], xb, j, tw2);
+      build_nl<NINV, REGS>(src, z, zr);
+      fft_reg_lines<R, +1, NINV>(z, xb, j, tw2);
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         // the two lanes of a packed line value are the same grid point of the two trajectories
@@ -309,14 +366,14 @@ template <int R, class S, int NINV, int NFWD> struct Fast1d {
         for (int g = 0; g < NFWD; ++g) w[g][r] = as_cpx(ov[g]);
       }
     }
-#pragma unroll
-    for (int g = 0; g < NFWD; ++g) fft_reg<R, -1>(w[g], xb, j, tw2);
+    fft_reg_lines<R, -1, NFWD>(w, xb, j, tw2);
     if constexpr (kRealPost) {
+      // the real post-factor c(k) is folded into the ETDRK coefficient tables (every update term is c_i(k) * N, see the
+      // table load in the kernel prologue): the transformed product is the nonlinear term as far as this kernel goes
 #pragma unroll
-      for (int r = 0; r < R; ++r) npk[r] = sC[kidx(r)] * w[0][r];
-      const float c = sC[N / 2];
-      ny1 = c * cpx<float>(w[0][R / 2].x, 0.f);
-      ny2 = c * cpx<float>(w[0][R / 2].y, 0.f);
+      for (int r = 0; r < R; ++r) npk[r] = w[0][r];
+      ny1 = cpx<float>(w[0][R / 2].x, 0.f);
+      ny2 = cpx<float>(w[0][R / 2].y, 0.f);
     } else {
       // the post-processing (nl_from_fwd) is complex-linear in the transformed fields with coefficients that are
       // polynomials in i kd: evaluated at -kd for the negative-wavenumber slots it acts on the packed values as is
@@ -339,6 +396,129 @@ template <int R, class S, int NINV, int NFWD> struct Fast1d {
       post(N / 2, false, true, 0, R / 2, ny1);
       post(N / 2, false, true, 1, R / 2, ny2);
     }
+  }
+
+  // ETDRK2 (_etdrk_2.py:91-102) with the thread's slots of the state handed over in registers from the update (or
+  // transform) that produces them to the line builder that consumes them (zr: in = u, out = u+).  The state arrays in
+  // shared memory are then read by the updates only: three line builds per step cost no shared-memory traffic.
+  __device__ __forceinline__ void etdrk2_step(cpx<float> (&zr)[R]) {
+    cpx<float>* __restrict__ U = state(0);
+    cpx<float>* __restrict__ S0 = state(1);
+    constexpr int B = EXB_1D_UPD_BATCH;
+    cpx<float> npk[R], ny1, ny2;
+#if EXB_1D_O2_LOOP
+    // one copy of the nonlinear evaluation (three transforms) in the instruction stream instead of two
+#pragma unroll 1
+    for (int stg = 0; stg < 2; ++stg) {
+      eval_nl<true>(U, npk, ny1, ny2, zr);
+      if (stg == 0) {
+    #pragma unroll
+        for (int r0 = 0; r0 < R; r0 += B) {     // a = e u + c0 N(u), overwrites u; N(u) kept for stage 1
+          cpx<float> e[B], u[B];
+          float c0[B];
+    #pragma unroll
+          for (int q = 0; q < B; ++q) {
+            e[q] = sE[kidx(r0 + q)];
+            c0[q] = sc[0][kidx(r0 + q)];
+            u[q] = U[nidx(r0 + q)];
+          }
+    #pragma unroll
+          for (int q = 0; q < B; ++q) {
+            const cpx<float> a = cmul(e[q], u[q], upper(r0 + q)) + c0[q] * npk[r0 + q];
+            U[nidx(r0 + q)] = a;
+            S0[nidx(r0 + q)] = npk[r0 + q];
+            zr[r0 + q] = a;
+          }
+        }
+        if (j == 0) {
+          const cpx<float> e = sE[N / 2];
+          const float c0 = sc[0][N / 2];
+          const cpx<float> u1 = U[N], u2 = U[N + 1];
+          U[N] = e * u1 + c0 * ny1;
+          S0[N] = ny1;
+          U[N + 1] = e * u2 + c0 * ny2;
+          S0[N + 1] = ny2;
+        }
+      } else {
+    #pragma unroll
+        for (int r0 = 0; r0 < R; r0 += B) {     // u+ = a + c1 (N(a) - N(u))
+          cpx<float> u[B], n0[B];
+          float c1[B];
+    #pragma unroll
+          for (int q = 0; q < B; ++q) {
+            c1[q] = sc[1][kidx(r0 + q)];
+            u[q] = U[nidx(r0 + q)];
+            n0[q] = S0[nidx(r0 + q)];
+          }
+    #pragma unroll
+          for (int q = 0; q < B; ++q) {
+            const cpx<float> un = u[q] + c1[q] * (npk[r0 + q] - n0[q]);
+            U[nidx(r0 + q)] = un;
+            zr[r0 + q] = un;
+          }
+        }
+        if (j == 0) {
+          const float c1 = sc[1][N / 2];
+          const cpx<float> u1 = U[N], u2 = U[N + 1], p1 = S0[N], p2 = S0[N + 1];
+          U[N] = u1 + c1 * (ny1 - p1);
+          U[N + 1] = u2 + c1 * (ny2 - p2);
+        }
+      }
+    }
+#else
+    eval_nl<true>(U, npk, ny1, ny2, zr);
+#pragma unroll
+    for (int r0 = 0; r0 < R; r0 += B) {     // a = e u + c0 N(u), overwrites u; N(u) kept for stage 1
+      cpx<float> e[B], u[B];
+      float c0[B];
+#pragma unroll
+      for (int q = 0; q < B; ++q) {
+        e[q] = sE[kidx(r0 + q)];
+        c0[q] = sc[0][kidx(r0 + q)];
+        u[q] = U[nidx(r0 + q)];
+      }
+#pragma unroll
+      for (int q = 0; q < B; ++q) {
+        const cpx<float> a = cmul(e[q], u[q], upper(r0 + q)) + c0[q] * npk[r0 + q];
+        U[nidx(r0 + q)] = a;
+        S0[nidx(r0 + q)] = npk[r0 + q];
+        zr[r0 + q] = a;
+      }
+    }
+    if (j == 0) {
+      const cpx<float> e = sE[N / 2];
+      const float c0 = sc[0][N / 2];
+      const cpx<float> u1 = U[N], u2 = U[N + 1];
+      U[N] = e * u1 + c0 * ny1;
+      S0[N] = ny1;
+      U[N + 1] = e * u2 + c0 * ny2;
+      S0[N + 1] = ny2;
+    }
+    eval_nl<true>(U, npk, ny1, ny2, zr);
+#pragma unroll
+    for (int r0 = 0; r0 < R; r0 += B) {     // u+ = a + c1 (N(a) - N(u))
+      cpx<float> u[B], n0[B];
+      float c1[B];
+#pragma unroll
+      for (int q = 0; q < B; ++q) {
+        c1[q] = sc[1][kidx(r0 + q)];
+        u[q] = U[nidx(r0 + q)];
+        n0[q] = S0[nidx(r0 + q)];
+      }
+#pragma unroll
+      for (int q = 0; q < B; ++q) {
+        const cpx<float> un = u[q] + c1[q] * (npk[r0 + q] - n0[q]);
+        U[nidx(r0 + q)] = un;
+        zr[r0 + q] = un;
+      }
+    }
+    if (j == 0) {
+      const float c1 = sc[1][N / 2];
+      const cpx<float> u1 = U[N], u2 = U[N + 1], p1 = S0[N], p2 = S0[N + 1];
+      U[N] = u1 + c1 * (ny1 - p1);
+      U[N + 1] = u2 + c1 * (ny2 - p2);
+    }
+#endif
   }
 
   // one ETDRK step on the shared-memory state (array 0); stage formulas: exponax/etdrk/_etdrk_{0..4}.py
@@ -467,7 +647,8 @@ template <int R, class S, int NINV, int NFWD> struct Fast1d {
   }
 };
 
-template <int R, class S, int NINV, int NFWD>
+// ORD = 2: the ETDRK2 instance (register hand-over between updates and line builders, no order dispatch); ORD = 0: any order
+template <int R, class S, int NINV, int NFWD, int ORD>
 __global__ void __launch_bounds__(256, 2) k1d_fast_kernel(const K1dParams<float> p, const FastLayout lay) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int N = R * R, Nh = N / 2 + 1;
@@ -485,10 +666,10 @@ __global__ void __launch_bounds__(256, 2) k1d_fast_kernel(const K1dParams<float>
     for (int q = threadIdx.x; q < Nh; q += blockDim.x) {
       e[q] = p.K.exp_term[q];
       if (p.K.half_exp) eh[q] = p.K.half_exp[q];
+      const float post = F1::kRealPost ? F1::post_factor(p.P, q) : 1.f;
       for (int i = 0; i < 6; ++i)
-        if (p.K.c[i]) ((float*)(smem_raw + lay.off_c[i]))[q] = p.K.c[i][q];
+        if (p.K.c[i]) ((float*)(smem_raw + lay.off_c[i]))[q] = p.K.c[i][q] * post;
       const bool keep = !(p.P.kmax >= 0 && q > p.P.kmax);
-      ((float*)(smem_raw + lay.off_h))[q] = F1::post_factor(p.P, q);
       ((float2*)(smem_raw + lay.off_mk))[q] =
           keep ? make_float2(p.P.inv_norm, (p.P.dscale * (float)q) * p.P.inv_norm) : make_float2(0.f, 0.f);
     }
@@ -509,7 +690,6 @@ __global__ void __launch_bounds__(256, 2) k1d_fast_kernel(const K1dParams<float>
   F.sEh = (const cpx<float>*)(smem_raw + lay.off_hexp);
   for (int i = 0; i < 6; ++i) F.sc[i] = (const float*)(smem_raw + lay.off_c[i]);
   F.sMK = (const float2*)(smem_raw + lay.off_mk);
-  F.sC = (const float*)(smem_raw + lay.off_h);
   const int order = p.K.order;
 
   const long long t1 = 2ll * group, t2 = t1 + 1;
@@ -552,11 +732,15 @@ __global__ void __launch_bounds__(256, 2) k1d_fast_kernel(const K1dParams<float>
   };
 
   cpx<float>* U = F.state(0);
+  cpx<float> zr[R];   // ORD == 2: the thread's slots of U, valid whenever U is
   // physical pair line -> packed spectral state
   auto to_state = [&](cpx<float> (&line)[R]) {
     fft_reg<R, -1>(line, F.xb, j, F.tw2);
 #pragma unroll
-    for (int r = 0; r < R; ++r) U[j + R * r] = line[r];
+    for (int r = 0; r < R; ++r) {
+      U[j + R * r] = line[r];
+      if (ORD == 2) zr[r] = line[r];
+    }
     if (j == 0) {   // X1[N/2], X2[N/2] are real
       U[N] = cpx<float>(line[R / 2].x, 0.f);
       U[N + 1] = cpx<float>(line[R / 2].y, 0.f);
@@ -589,19 +773,30 @@ __global__ void __launch_bounds__(256, 2) k1d_fast_kernel(const K1dParams<float>
         const cpx<float> a = act1 ? f1[k] : zero, b = act2 ? f2[k] : zero;
         cpx<float> add = F1::upper(r) ? conj(a) + mul_i(conj(b)) : a + mul_i(b);
         if (r == 0 && j == 0) add = cpx<float>(a.x, b.x);   // DC: real parts only (irfft)
-        U[j + R * r] = axpy(p.fscale, add, U[j + R * r]);
+        const cpx<float> uf = axpy(p.fscale, add, U[j + R * r]);
+        U[j + R * r] = uf;
+        if (ORD == 2) zr[r] = uf;
       }
       if (j == 0) {
         if (act1) U[N] = axpy(p.fscale, f1[N / 2], U[N]);
         if (act2) U[N + 1] = axpy(p.fscale, f2[N / 2], U[N + 1]);
       }
     }
-    for (int sub = 0; sub < p.substeps; ++sub) F.etdrk_step(order);
+    for (int sub = 0; sub < p.substeps; ++sub) {
+      if constexpr (ORD == 2) F.etdrk2_step(zr);
+      else F.etdrk_step(order);
+    }
     const bool last = (s == p.n_saved - 1);
     const bool store = !final_only || last;
     if (store || !spectral_carry) {
       cpx<float> z[R];
       F.build_plain(U, z);
+      if constexpr (ORD == 2) {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          if (r != R / 2) z[r] = zr[r];
+        if (j != 0) z[R / 2] = zr[R / 2];
+      }
       fft_reg<R, +1>(z, F.xb, j, F.tw2);
 #pragma unroll
       for (int r = 0; r < R; ++r) z[r] = invN * z[r];    // one packed scaling serves the snapshot and the carry
