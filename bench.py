@@ -481,6 +481,8 @@ def measure_exb(args, w, rank, world, local_rank, *, steps, warmup, with_e2e, wi
             # exchanges are shared by a PAIR of trajectories; per N-point complex transform one exchange
             # (8 B store + 8 B load per point) + twiddles (8 B per point) + state / stage / table traffic
             smem_bytes_per_pair_step = (4 * 24 + 96) * N
+            if "ncu_shared_wavefronts_per_pair_step" in ncu_ctx:   # measured: 128 B per shared-memory wavefront
+                smem_bytes_per_pair_step = 128 * ncu_ctx["ncu_shared_wavefronts_per_pair_step"]
             smem_gbs = (units_per_call / N / 2) * smem_bytes_per_pair_step / (ms_per_step * 1e-3) / 1e9
             roofline["fp32"] = {"achieved_tflops_fft_model": tfl, "peak_tflops_ffma": f2[0], "peak_tflops_ffma2": f2[1],
                                 "frac_of_ffma_peak": tfl / f2[0],
@@ -490,9 +492,10 @@ def measure_exb(args, w, rank, world, local_rank, *, steps, warmup, with_e2e, wi
             roofline["smem"] = {"achieved_gbs_model": smem_gbs, "peak_gbs_lds64": s2[0], "peak_gbs_lds128": s2[1],
                                 "frac_of_lds64_peak": smem_gbs / s2[0]}
             if "ncu_issue_slot_utilisation" in ncu_ctx:
-                roofline["bound"] = "fp32-issue/shared-memory (ncu: issue slots %.0f %%, LSU wavefronts %.0f %%); HBM is %.0f %% used" % (
-                    100 * ncu_ctx["ncu_issue_slot_utilisation"], 100 * ncu_ctx.get("ncu_shared_wavefront_utilisation", 0),
-                    100 * achieved / peak)
+                roofline["bound"] = ("shared-memory pipe / fp32 pipe (ncu: LSU pipe %.0f %%, FMA pipe %.0f %%, issue slots %.0f %%); "
+                                     "HBM is %.0f %% used") % (
+                    100 * ncu_ctx.get("ncu_shared_wavefront_utilisation", 0), 100 * ncu_ctx.get("ncu_fma_pipe_utilisation", 0),
+                    100 * ncu_ctx["ncu_issue_slot_utilisation"], 100 * achieved / peak)
         except Exception as e:  # measurement utility only
             roofline["fp32"] = {"error": str(e)}
         roofline["fp32_fft_tflops"] = tfl

@@ -23,6 +23,16 @@ if which in ("all", "1d"):
         got = ex.vmap(ex.rollout(st, 3))(torch.as_tensor(u0, device="cuda")).cpu().numpy()
         ref = np.stack([ox.rollout(ost, 3)(u) for u in u0])
         print("1d", N, rel(got, ref)); assert rel(got, ref) < 1e-5
+        # the any-order instance (ETDRK4), a complex post-factor (conservative convection), an odd-derivative operator
+        # (complex Nyquist coefficients) and an odd batch
+        for name, kw in (("KuramotoSivashinskyConservative", dict(order=4)), ("KortewegDeVries", dict(order=3)),
+                         ("KuramotoSivashinsky", dict(order=1)), ("FisherKPP", dict(order=0))):
+            cls = getattr(ex.stepper, name, None) or getattr(ex.stepper.reaction, name)
+            st, ost = cls(1, 20.0, N, 0.01, **kw), getattr(ox, name)(1, 20.0, N, 0.01, **kw)
+            v0 = (0.3 * u0[:3]).astype(np.float32)
+            got = ex.vmap(ex.rollout(st, 2))(torch.as_tensor(v0, device="cuda")).cpu().numpy()
+            ref = np.stack([ox.rollout(ost, 2)(u) for u in v0])
+            print("1d", name, N, rel(got, ref)); assert rel(got, ref) < 2e-5
 if which in ("all", "2d"):
     N = 128
     u0 = (0.1 * rng.standard_normal((3, 1, N, N))).astype(np.float32)
