@@ -103,6 +103,14 @@ static void factorize(int N, FftDesc& fd) {
       fd.radix[fd.nst++] = p;
     }
   if (n > 1) fd.radix[fd.nst++] = n;
+  int Ns = 1;
+  for (int s = 0; s < fd.nst; ++s) {
+    const int R = fd.radix[s];
+    fd.tunit[s] = N / (Ns * R);
+    fd.m_ns[s] = fastdiv_magic((unsigned)Ns);
+    fd.m_nr[s] = fastdiv_magic((unsigned)(N / R));
+    Ns *= R;
+  }
 }
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

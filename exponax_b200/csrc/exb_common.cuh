@@ -110,7 +110,14 @@ struct FftDesc {
   int N;
   int nst;
   int radix[EXB_MAX_STAGES];
+  // per stage, host-computed (exb_api.cu: factorize): the butterfly index arithmetic of the shared-memory Stockham
+  // transform without run-time integer divisions.  m_* = floor(2^32 / d) + 1: q / d == __umulhi(q, m) for q * d < 2^32.
+  int tunit[EXB_MAX_STAGES];        // N / (Ns * R): twiddle index step of the stage
+  unsigned m_ns[EXB_MAX_STAGES];    // for d = Ns (product of the radices already applied)
+  unsigned m_nr[EXB_MAX_STAGES];    // for d = N / R (butterflies per line)
 };
+__host__ __device__ inline unsigned fastdiv_magic(unsigned d) { return (unsigned)(0x100000000ull / d) + 1u; }
+__device__ __forceinline__ int fastdiv(int q, int d, unsigned m) { return d == 1 ? q : (int)__umulhi((unsigned)q, m); }
 
 // Parameters of the nonlinear function + spectral geometry, passed by value.
 template <class T> struct NlParams {

@@ -105,19 +105,17 @@ template <class T, int R, int DIR> __device__ __forceinline__ void dftR(cpx<T>* 
   if (R == 8) dft8<T, DIR>(v);
 }
 
-// One Stockham butterfly of radix R at position j (0 <= j < N/R); `Ns` = product of the radices
-// already applied.  Element i of the line is at base[i * istr].
+// One Stockham butterfly of radix R at position j (0 <= j < NR = N/R); `Ns` = product of the radices
+// already applied, k = j % Ns, tunit = N / (Ns * R).  Element i of the line is at base[i * istr].
 template <class T, int R, int DIR>
 __device__ __forceinline__ void stockham_bfly(const cpx<T>* __restrict__ in, cpx<T>* __restrict__ out,
-                                              int j, int Ns, int N, int istr,
+                                              int j, int k, int Ns, int NR, int tunit, int istr,
                                               const cpx<T>* __restrict__ tw) {
-  const int NR = N / R;
-  const int k = j % Ns;
   cpx<T> v[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) v[r] = in[(size_t)(j + r * NR) * istr];
   if (Ns > 1) {
-    const int tstep = (N / (Ns * R)) * k;
+    const int tstep = tunit * k;
 #pragma unroll
     for (int r = 1; r < R; ++r) v[r] = v[r] * twd<T, DIR>(tw[r * tstep]);
   }
@@ -159,7 +157,9 @@ __device__ __noinline__ cpx<T>* fft_lines(cpx<T>* A, cpx<T>* B, int nlines, int 
   int Ns = 1;
   for (int s = 0; s < fd.nst; ++s) {
     const int R = fd.radix[s];
-    const int NR = N / R;
+    const int tunit = fd.tunit[s];
+    const int NR = tunit * Ns;                       // N / R
+    const unsigned m_ns = fd.m_ns[s], m_nr = fd.m_nr[s];
     const int total = nlines * NR;
     for (int q = threadIdx.x; q < total; q += blockDim.x) {
       int l, j;
@@ -167,17 +167,18 @@ __device__ __noinline__ cpx<T>* fft_lines(cpx<T>* A, cpx<T>* B, int nlines, int 
         j = q / nlines;
         l = q - j * nlines;
       } else {
-        l = q / NR;
+        l = fastdiv(q, NR, m_nr);                    // (q * NR < 2^32: q < nlines * NR, a few thousand lines at most)
         j = q - l * NR;
       }
+      const int k = j - fastdiv(j, Ns, m_ns) * Ns;   // j % Ns
       const cpx<T>* in = A + (size_t)l * lstr;
       cpx<T>* out = B + (size_t)l * lstr;
       switch (R) {
-        case 8: stockham_bfly<T, 8, DIR>(in, out, j, Ns, N, istr, tw); break;
-        case 4: stockham_bfly<T, 4, DIR>(in, out, j, Ns, N, istr, tw); break;
-        case 2: stockham_bfly<T, 2, DIR>(in, out, j, Ns, N, istr, tw); break;
-        case 3: stockham_bfly<T, 3, DIR>(in, out, j, Ns, N, istr, tw); break;
-        case 5: stockham_bfly<T, 5, DIR>(in, out, j, Ns, N, istr, tw); break;
+        case 8: stockham_bfly<T, 8, DIR>(in, out, j, k, Ns, NR, tunit, istr, tw); break;
+        case 4: stockham_bfly<T, 4, DIR>(in, out, j, k, Ns, NR, tunit, istr, tw); break;
+        case 2: stockham_bfly<T, 2, DIR>(in, out, j, k, Ns, NR, tunit, istr, tw); break;
+        case 3: stockham_bfly<T, 3, DIR>(in, out, j, k, Ns, NR, tunit, istr, tw); break;
+        case 5: stockham_bfly<T, 5, DIR>(in, out, j, k, Ns, NR, tunit, istr, tw); break;
         default: stockham_bfly_generic<T, DIR>(in, out, j, Ns, N, R, istr, tw); break;
       }
     }

@@ -542,6 +542,51 @@ def test_c2_production_batch_sampled_trajectories():
     assert rel(sel[:, -1], ref[:, -1]) < 1e-3
 
 
+@pytest.mark.parametrize("N", [64, 256])
+@pytest.mark.parametrize("name,kw", [("Burgers", dict(diffusivity=0.05)), ("KortewegDeVries", {}),
+                                     ("KuramotoSivashinskyConservative", {}), ("KuramotoSivashinsky", {})])
+def test_fast_1d_trajectory_pairs_are_independent(name, kw, N):
+    """The persistent 1-D kernel carries two trajectories as ONE complex trajectory z = x1 + i x2 (packed spectrum, no
+    two-for-one split).  A trajectory's result must not depend on its partner beyond float rounding: the same initial
+    condition next to a different partner, next to zero, and alone in an odd batch, all vs the oracle."""
+    L, dt, T = 20.0, 0.01, 20
+    ua = ic(1, N, [3])[0]
+    ub = 0.7 * ic(1, N, [11])[0]
+    st = getattr(ex.stepper, name)(1, L, N, dt, **kw)
+    ost = getattr(ox, name)(1, L, N, dt, **kw)
+    ref = ox.rollout(ost, T)(ua)
+    roll = ex.vmap(ex.rollout(st, T))
+    with_b = host(roll(dev(np.stack([ua, ub]))))[0]
+    with_0 = host(roll(dev(np.stack([ua, np.zeros_like(ua)]))))[0]
+    second = host(roll(dev(np.stack([ub, ua]))))[1]
+    alone = host(roll(dev(np.stack([ub, ub, ua]))))[2]          # odd batch: the last pair has an inactive partner
+    for got in (with_b, with_0, second, alone):
+        assert rel(got[0], ref[0]) < F32_STEP
+        assert rel(got, ref) < ROLLOUT_100
+    assert rel(with_b, with_0) < 2e-6 and rel(second, with_0) < 2e-6 and rel(alone, with_0) < 2e-6
+
+
+@pytest.mark.parametrize("order", [0, 1, 2, 3, 4])
+def test_fast_1d_nyquist_and_full_spectrum_state(order):
+    """White-noise initial condition (energy in every mode incl. the Nyquist mode and all dealiased ones) through the
+    persistent kernel with an odd-derivative operator (KdV: complex exp(dt L) at the Nyquist mode, whose imaginary part
+    irfft drops): the packed state keeps the two Nyquist values of a pair separately -- every order vs the oracle."""
+    N, L, dt = 256, 2 * np.pi, 1e-4
+    rng = np.random.default_rng(order)
+    u0 = (0.5 * rng.standard_normal((3, 1, N))).astype(np.float32)
+    # no hyper-diffusion: the Nyquist mode survives, rotating by k^3 dt = 210 rad per step and projected by every irfft
+    st = ex.stepper.KortewegDeVries(1, L, N, dt, order=order, hyper_diffusivity=0.0)
+    ost = ox.KortewegDeVries(1, L, N, dt, order=order, hyper_diffusivity=0.0)
+    got = host(ex.vmap(ex.rollout(st, 3))(dev(u0)))
+    ref = per_sample(ox.rollout(ost, 3), u0)
+    assert rel(got[:, 0], ref[:, 0]) < F32_STEP
+    assert rel(got, ref) < 3 * F32_STEP
+    gh, rh = np.fft.rfft(got[:, -1], axis=-1), np.fft.rfft(ref[:, -1], axis=-1)
+    assert np.abs(rh[..., N // 2]).min() > 0.1                   # (it has not decayed)
+    assert rel(gh[..., N // 2], rh[..., N // 2]) < 1e-4          # the Nyquist mode itself
+    assert rel(gh[..., 100:], rh[..., 100:]) < 1e-4              # the dealiased band
+
+
 @pytest.mark.parametrize("name,D,N,C,order,L", [
     ("KolmogorovFlowVorticity", 2, 128, 1, 2, 2 * np.pi), ("KolmogorovFlowVorticity", 2, 128, 1, 4, 2 * np.pi),
     ("KolmogorovFlowVorticity", 2, 24, 1, 3, 2 * np.pi), ("KuramotoSivashinsky", 2, 128, 1, 1, 200.0),
