@@ -113,6 +113,21 @@ __device__ __forceinline__ void invpro_fields_1ch(const NlParams<float>& Pn, con
   }
 }
 
+#ifndef EXB_COL_LONG_LINE_REGS
+#define EXB_COL_LONG_LINE_REGS 1
+#endif
+// Resident CTAs per SM the column kernels are compiled for (= the register cap).  The long lines (N >= 1024: four
+// register-FFT passes) need more registers than the short ones: at the caps of the short lines the three-field
+// epilogue spilled 300 B per thread and the plain pass 24 B (cuobjdump -res-usage), and the N = 2048 passes of config
+// c5 ran at 1.5 TB/s (scripts/c5_phases.py).
+template <int N, int TW, int NFWD, int MODE, int FUSE> __host__ __device__ constexpr int col_min_blocks() {
+  constexpr int threads = (N / 8) * TW;
+  if (MODE == COL_PLAIN) return (N >= 1024 && EXB_COL_LONG_LINE_REGS) ? 3 : 2048 / threads;
+  if (MODE == COL_INV_PRO) return 2;
+  if (FUSE) return 2;
+  if (NFWD == 1) return 3;
+  return (N >= 1024 && EXB_COL_LONG_LINE_REGS) ? 1 : EXB_EPI_MULTI_MINBLOCKS;
+}
 // ------------------------------------------------------------------------------- column pass
 // Index bookkeeping is the expensive part of these kernels (ncu r01j: 50-60 % of the executed instructions of a
 // column pass were integer / address / control, the butterflies 20-35 %), so everything that does not depend on
@@ -127,8 +142,7 @@ __device__ __forceinline__ void invpro_fields_1ch(const NlParams<float>& Pn, con
 //        transforms of the next N(u) run right here (p.out = the inverse-field buffer): one launch, one read of the
 //        stage input and the start-up latency of the prologue pass less per stage.
 template <int N, int TW, class S, int NFWD, int MODE, int DIR, int STG = 0, int FUSE = 0>
-__global__ void __launch_bounds__((N / 8) * TW, (MODE == COL_PLAIN ? 2048 / ((N / 8) * TW)
-                                                 : (MODE == COL_INV_PRO ? 2 : (FUSE ? 2 : (NFWD == 1 ? 3 : EXB_EPI_MULTI_MINBLOCKS)))))
+__global__ void __launch_bounds__((N / 8) * TW, col_min_blocks<N, TW, NFWD, MODE, FUSE>())
 col_fast_kernel(const ColParams<float> p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int P = N / 8;
