@@ -48,7 +48,6 @@ int launch_fast_t(cudaStream_t st, const K1dParams<float>& p, int nscr, int max_
   lay.off_mk = take(NNh * 8);
   lay.nstate = nstate;
   (void)nscr;
-  lay.nhp = (NNh + 1) / 2 * 2;
   lay.pair_bytes = (lay.nstate * (NN + 2) + (R + 1) * R) * 8;
   lay.off_pairs = take(0);
   size_t smem = (size_t)off + (size_t)groups * lay.pair_bytes;

@@ -1,18 +1,21 @@
 // Fast 1-D persistent rollout kernel for N = R*R (R = 16 -> N = 256, R = 8 -> N = 64), f32, C = 1.
 //
 // Work decomposition (B200: 148 SMs, 64K regs, 227 KB smem / SM):
-//   * a PAIR of trajectories shares every complex FFT (two-for-one: z = x1 + i*x2);
-//   * a pair is owned by R threads (a half-warp for N = 256) for the whole rollout: every
-//     synchronisation is a __syncwarp, there is no __syncthreads after the table load;
-//   * each thread keeps R points of the line in registers; an N-point FFT is two in-register
-//     radix-R passes with ONE shared-memory exchange in between (padded, conflict-free);
-//   * the pointwise nonlinearity happens in registers between the inverse and forward
-//     transforms (the output mapping of the inverse FFT is the input mapping of the forward);
-//   * spectral state, ETDRK stage buffers and coefficient tables live in shared memory; HBM
-//     sees the initial condition once and the saved snapshots;
-//   * the nonlinear function is a compile-time descriptor S (NlS<...>): no per-element branching.
-// Reference semantics identical to k1d_kernel (exb_kernels_1d.cuh); parity is tested against
-// the same oracle.
+//   * a PAIR of trajectories is carried as ONE complex trajectory z = x1 + i*x2: the state is the packed spectrum
+//     Z[n] = X1[n] + i X2[n] over all N modes (see Fast1d below) -- no two-for-one split or packing anywhere;
+//   * a pair is owned by R threads (a half-warp for N = 256) for the whole rollout; thread j owns the modes / points
+//     n = j + R*r, so every state access is thread-private and the only synchronisation is the __syncwarp pair around
+//     the transform's exchange (no __syncthreads after the table load);
+//   * each thread keeps R points of the line in registers; an N-point FFT is two in-register radix-R passes with ONE
+//     shared-memory exchange in between (padded, conflict-free); 11 of the 15 inter-pass twiddles are derived;
+//   * the pointwise nonlinearity happens in registers between the inverse and forward transforms (the output
+//     mapping of the inverse FFT is the input mapping of the forward);
+//   * packed spectral state, ETDRK stage buffers, coefficient and factor tables live in shared memory; HBM sees the
+//     initial condition once and the saved snapshots;
+//   * the nonlinear function is a compile-time descriptor S (NlS<...>): no per-element branching; ETDRK2 (the
+//     reference's default order) has its own kernel instance (ORD = 2).
+// How this structure was arrived at, step by step with measurements: profiles/r02v_c2_lean_1d.md, DESIGN.md section 6.
+// Reference semantics identical to k1d_kernel (exb_kernels_1d.cuh); parity is tested against the same oracle.
 #pragma once
 #include "exb_kernels_1d.cuh"
 
@@ -26,8 +29,7 @@ struct FastLayout {
   int off_mk;        // float2[Nh]: (keep / N, keep * kd / N) -- pre-dealiasing mask, derivative scale and 1/N of the inverse transform
   int off_pairs;     // start of per-pair storage
   int pair_bytes;    // bytes per pair
-  int nstate;        // spectral state arrays per pair (1 + scratch)
-  int nhp;           // (unused since the packed-state layout: a state array is N + 2 complex values)
+  int nstate;        // spectral state arrays per pair (1 + scratch), each N + 2 complex values (Fast1d::ZS)
 };
 
 // ---- in-register DFTs; output position p holds X[xidx<R>(p)] --------------------------------
@@ -117,12 +119,6 @@ __device__ __forceinline__ void fft_reg_body(cpx<float> (&v)[R], cpx<float>* xb,
 
 #ifndef EXB_1D_CTA_SYNC
 #define EXB_1D_CTA_SYNC 0
-#endif
-#ifndef EXB_1D_SPLIT_BAR
-#define EXB_1D_SPLIT_BAR 0
-#endif
-#ifndef EXB_1D_SKEW_NS
-#define EXB_1D_SKEW_NS 0
 #endif
 
 // The step body calls the transform from five places.  Round 1 (scalar FP32, per-trajectory masks and selects in the
