@@ -411,3 +411,46 @@ def test_row16_kernel_is_the_shipped_n256_row_pass():
     assert b"row16_kernel" in open(lib, "rb").read()
     impl = open(os.path.join(ROOT, "exponax_b200", "csrc", "exb_fastnd_impl.cuh")).read()
     assert "#define EXB_ROW16 1" in impl
+
+
+def test_fastdiv_magic_is_exact_where_the_kernels_use_it():
+    """exb_common.cuh: `fastdiv(q, d, m)` with m = floor(2^32 / d) + 1 replaces the run-time divisions of the generic
+    Stockham transform's index arithmetic (q / NR, j % Ns).  Restated here with NumPy integers: exact whenever
+    q * d < 2^32 -- which the kernels guarantee (q < nlines * NR with d = NR, j < NR with d = Ns < N; N <= 16384)."""
+    rng = np.random.default_rng(0)
+    for d in list(range(1, 600)) + [625, 1000, 1024, 2048, 3125, 4096, 5000, 8192, 16384]:
+        m = np.uint64((1 << 32) // d + 1)
+        qmax = min((1 << 32) // d - 1, 1 << 24)
+        q = np.unique(np.concatenate([np.arange(0, min(qmax, 70000)), rng.integers(0, qmax + 1, 20000),
+                                      [qmax, qmax - 1, max(qmax - d, 0)]])).astype(np.uint64)
+        got = (q * m) >> np.uint64(32) if d > 1 else q          # d == 1 is special-cased on the device
+        assert np.array_equal(got, q // np.uint64(d)), d
+
+
+def test_pair_as_one_complex_trajectory_identity():
+    """The identity behind the packed state of the 1-D persistent kernel (exb_kernels_1d_fast.cuh):
+    two real trajectories x1, x2 evolve under per-mode complex factors c(k), c(-k) = conj(c(k)), exactly like the ONE
+    complex trajectory z = x1 + i x2 whose full spectrum Z[n] is multiplied by c(+k) for n = k <= N/2 and conj(c(k))
+    for n = N - k -- except at the Nyquist mode, where irfft keeps Re(c U) per trajectory: the kernel carries the two
+    Nyquist values separately and overrides the packed slot with (Re(c U1), Re(c U2))."""
+    rng = np.random.default_rng(3)
+    N = 64
+    x1, x2 = rng.standard_normal(N), rng.standard_normal(N)
+    k = np.arange(N // 2 + 1)
+    c = np.exp((-0.01 * k**2 + 0.3j * k**3) * 0.05)            # diffusion + dispersion: complex, also at k = N/2
+    ref1 = np.fft.irfft(c * np.fft.rfft(x1), n=N)
+    ref2 = np.fft.irfft(c * np.fft.rfft(x2), n=N)
+    Z = np.fft.fft(x1 + 1j * x2)
+    cfull = np.concatenate([c, np.conj(c[1:N // 2][::-1])])     # n = 0 .. N/2, then n = N - k for k = N/2 - 1 .. 1
+    Zc = cfull * Z
+    naive = np.fft.ifft(Zc)
+    assert np.abs(naive.real - ref1).max() > 1e-3               # the packed Nyquist slot alone is NOT enough ...
+    U1n, U2n = np.fft.rfft(x1)[N // 2], np.fft.rfft(x2)[N // 2]
+    Zc[N // 2] = (c[N // 2] * U1n).real + 1j * (c[N // 2] * U2n).real
+    z = np.fft.ifft(Zc)
+    assert np.allclose(z.real, ref1, atol=1e-12) and np.allclose(z.imag, ref2, atol=1e-12)   # ... with the override it is
+    # the packed nonlinear term needs no two-for-one split either: FFT(w1 + i w2)[n] = W1[n] + i W2[n]
+    w1, w2 = x1 * x1, x2 * x2
+    W = np.fft.fft(w1 + 1j * w2)
+    assert np.allclose(W[:N // 2 + 1], np.fft.rfft(w1) + 1j * np.fft.rfft(w2))
+    assert np.allclose(W[N // 2 + 1:], (np.conj(np.fft.rfft(w1)) + 1j * np.conj(np.fft.rfft(w2)))[1:N // 2][::-1])
