@@ -454,3 +454,35 @@ def test_pair_as_one_complex_trajectory_identity():
     W = np.fft.fft(w1 + 1j * w2)
     assert np.allclose(W[:N // 2 + 1], np.fft.rfft(w1) + 1j * np.fft.rfft(w2))
     assert np.allclose(W[N // 2 + 1:], (np.conj(np.fft.rfft(w1)) + 1j * np.conj(np.fft.rfft(w2)))[1:N // 2][::-1])
+
+
+@pytest.mark.parametrize("R", [8, 16])
+def test_fast_1d_slot_ownership_and_exchange_model(R):
+    """Model of the ownership maps of the 1-D persistent kernel (Fast1d::nidx / kidx / upper, exb_kernels_1d_fast.cuh):
+    the R threads of a pair own every line index n exactly once, slot r >= R/2 is the negative wavenumber -(N - n), and
+    both access patterns of the padded exchange buffer ((R+1)*j + X-index store, j + (R+1)*r load) are conflict-free for
+    the 64-bit accesses of a half-warp (16 lanes x 8 B = all 32 banks once)."""
+    N = R * R
+    own = {}
+    for j in range(R):
+        for r in range(R):
+            n = j + R * r
+            k = n if r < R // 2 else N - n
+            assert n not in own
+            own[n] = (j, r)
+            freq = n if n <= N // 2 else n - N                 # FFT frequency of index n
+            assert k == abs(freq) and (r >= R // 2) == (freq < 0 or n == N // 2)
+    assert sorted(own) == list(range(N))
+
+    def xidx(p):                                               # output position p of the in-register radix-16 DFT
+        return 4 * (p & 3) + (p >> 2) if R == 16 else p
+    lanes = min(R, 16)                                         # one pair group per half-warp (N = 256) / two (N = 64)
+    for p_ in range(R):                                        # store: thread j writes slot (R + 1) * j + xidx(p)
+        banks = [(2 * ((R + 1) * j + xidx(p_))) % 32 for j in range(lanes)]
+        assert len(set(banks)) == lanes
+    for r in range(R):                                         # load: thread j reads slot j + (R + 1) * r
+        banks = [(2 * (j + (R + 1) * r)) % 32 for j in range(lanes)]
+        assert len(set(banks)) == lanes
+    src = open(os.path.join(ROOT, "exponax_b200", "csrc", "exb_kernels_1d_fast.cuh")).read()
+    assert "xb[(R + 1) * j + xidx<R>(p)] = v[p];" in src and "xb[j + (R + 1) * r]" in src
+    assert "return r < R / 2 ? j + R * r : N - (j + R * r);" in src
