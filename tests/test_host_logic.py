@@ -486,3 +486,73 @@ def test_fast_1d_slot_ownership_and_exchange_model(R):
     src = open(os.path.join(ROOT, "exponax_b200", "csrc", "exb_kernels_1d_fast.cuh")).read()
     assert "xb[(R + 1) * j + xidx<R>(p)] = v[p];" in src and "xb[j + (R + 1) * r]" in src
     assert "return r < R / 2 ? j + R * r : N - (j + R * r);" in src
+
+
+def _packed_pair_etdrk2_emulator(ost, u1, u2, steps):
+    """NumPy (float64) emulation of the DATAFLOW of the 1-D persistent kernel's ETDRK2 instance
+    (exb_kernels_1d_fast.cuh: Fast1d::build_nl / eval_nl / etdrk2_step, kRealPost path, physical carry):
+    packed state Z[0..N-1] + the two Nyquist values, factor table (mask / N, mask * kd / N), real post-factor folded
+    into the coefficient tables, conjugated coefficients for the negative wavenumbers."""
+    N = ost.num_points
+    it, nl = ost._integrator, ost._integrator._nonlinear_fun
+    k = np.arange(N // 2 + 1)
+    e = np.asarray(it._exp_term, dtype=np.complex128)[0]
+    c1 = np.asarray(it._coef_1, dtype=np.complex128)[0].real
+    c2 = np.asarray(it._coef_2, dtype=np.complex128)[0].real
+    mask = np.ones(N // 2 + 1) if nl.dealiasing_mask is None else np.asarray(nl.dealiasing_mask, dtype=float)[0]
+    kd = (2 * np.pi / ost.domain_extent) * k
+    post = -nl.scale * mask                                   # non-conservative convection: N = -scale * mask * F(u u_x)
+    c1, c2 = c1 * post, c2 * post                             # folded (kernel prologue)
+    mk, kdm = mask / N, mask * kd / N
+    n = np.arange(N)
+    kk = np.where(n <= N // 2, n, N - n)                      # Fast1d::kidx
+    up = n > N // 2                                           # negative wavenumber (n = N/2 is overridden)
+    ny = N // 2
+
+    def cm(c, z):                                             # c(+-k) * z
+        return np.where(up, np.conj(c[kk]), c[kk]) * z
+
+    def eval_nl(Z, U1n, U2n):
+        lu = mk[kk] * Z                                       # u line
+        ld = np.where(up, -1j, 1j) * kdm[kk] * Z              # u_x line: (+- i kd) Z
+        lu[ny] = mk[ny] * U1n.real + 1j * mk[ny] * U2n.real   # Nyquist override: Re(F1), Re(F2)
+        ld[ny] = -kdm[ny] * U1n.imag - 1j * kdm[ny] * U2n.imag
+        a, b = np.fft.ifft(lu) * N, np.fft.ifft(ld) * N       # unnormalised inverse (1/N rides on the factors)
+        w = a.real * b.real + 1j * (a.imag * b.imag)          # pointwise product, lane by lane
+        W = np.fft.fft(w)
+        return W, complex(W[ny].real), complex(W[ny].imag)
+
+    Z = np.fft.fft(u1 + 1j * u2)
+    U1n, U2n = complex(Z[ny].real), complex(Z[ny].imag)
+    out = []
+    for _ in range(steps):
+        n0, a1, a2 = eval_nl(Z, U1n, U2n)
+        Z = cm(e, Z) + c1[kk] * n0
+        U1n, U2n = e[ny] * U1n + c1[ny] * a1, e[ny] * U2n + c1[ny] * a2
+        n1, b1, b2 = eval_nl(Z, U1n, U2n)
+        Z = Z + c2[kk] * (n1 - n0)
+        U1n, U2n = U1n + c2[ny] * (b1 - a1), U2n + c2[ny] * (b2 - a2)
+        line = Z.copy()
+        line[ny] = U1n.real + 1j * U2n.real
+        phys = np.fft.ifft(line)                              # snapshot: (x1, x2) = (Re, Im)
+        out.append(phys.copy())
+        Z = np.fft.fft(phys)                                  # physical carry
+        U1n, U2n = complex(Z[ny].real), complex(Z[ny].imag)
+    return np.array(out)
+
+
+@pytest.mark.parametrize("name,kw", [("Burgers", dict(diffusivity=0.05)),
+                                     ("KortewegDeVries", dict(hyper_diffusivity=0.0))])
+def test_packed_pair_etdrk2_dataflow_matches_the_oracle(name, kw):
+    """The kernel's algorithm, restated on the CPU in float64, against the oracle's rollout of each trajectory on its
+    own: white-noise states (all modes incl. Nyquist and the dealiased band), complex exp(dt L) for KdV."""
+    from oracle import exponax_np as ox
+    N, L, dt, T = 64, 2 * np.pi, 1e-3, 4
+    rng = np.random.default_rng(5)
+    u1, u2 = 0.5 * rng.standard_normal(N), 0.3 * rng.standard_normal(N)
+    ost = getattr(ox, name)(1, L, N, dt, dtype=np.float64, **kw)
+    got = _packed_pair_etdrk2_emulator(ost, u1, u2, T)
+    ref1 = ox.rollout(ost, T)(u1[None])[:, 0]
+    ref2 = ox.rollout(ost, T)(u2[None])[:, 0]
+    assert np.abs(got.real - ref1).max() < 1e-11 * max(1.0, np.abs(ref1).max())
+    assert np.abs(got.imag - ref2).max() < 1e-11 * max(1.0, np.abs(ref2).max())
